@@ -1,0 +1,308 @@
+/*
+ * psob200.h -- C ABI of the B200-native (sm_100a) PSO training-step hot path.
+ *
+ * This is the drop-in boundary.  The reference
+ * (yaramohamadi/Pairwise_Sample_Optimization) is pure Python/PyTorch and has no FFI
+ * of its own; each entry point below names the reference code it replaces
+ * (paths relative to the reference root):
+ *
+ *   TS = human_preference_tuning/pso_pytorch/diffusers_patch/turbo_inference_with_logprob.py
+ *   DS = human_preference_tuning/pso_pytorch/diffusers_patch/distilled_inference_with_logprob.py
+ *   TP = human_preference_tuning/pso_pytorch/diffusers_patch/sdxl_turbo_with_logprob.py
+ *   DP = human_preference_tuning/pso_pytorch/diffusers_patch/sdxl_dmd_with_logprob.py
+ *   T  = human_preference_tuning/train_online_pso_sdxl_turbo.py
+ *   D  = human_preference_tuning/train_online_pso_sdxl_dmd2.py
+ *   P  = personalization/train_pso_sdxl_turbo_dreambooth.py
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer on the
+ *     current CUDA device; tensors are dense row-major ("NCHW contiguous"), a sample
+ *     is N = C*H*W consecutive elements;
+ *   - `stream` is a cudaStream_t passed as void*; work is stream-ordered;
+ *   - functions never allocate, never synchronise, never throw; scratch memory is a
+ *     caller-provided workspace;
+ *   - return 0 on success, a negative PSOB200_ERR_* otherwise (psob200_strerror());
+ *   - data-dependent failures that only the device can see (a timestep that is not in
+ *     the schedule: TS:63 raises IndexError there) set bits in `*status` (device int,
+ *     may be NULL) and poison the affected outputs with NaN.
+ */
+#ifndef PSOB200_H
+#define PSOB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSOB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PSOB200_API __attribute__((visibility("default")))
+#else
+#define PSOB200_API
+#endif
+
+/* element types */
+enum { PSOB200_F32 = 0, PSOB200_BF16 = 1, PSOB200_F16 = 2 };
+/* timestep element types */
+enum { PSOB200_TS_I64 = 0, PSOB200_TS_F32 = 1, PSOB200_TS_I32 = 2 };
+/* scheduler families */
+enum { PSOB200_SCHED_TURBO = 0, PSOB200_SCHED_DMD = 1, PSOB200_SCHED_AFFINE = 2 };
+/* DreamBooth loss types (P:1924-1929) */
+enum { PSOB200_DB_PSO = 0, PSOB200_DB_PSO_DB = 1 };
+
+/* error codes */
+enum {
+  PSOB200_OK = 0,
+  PSOB200_ERR_INVALID_ARG = -1,
+  PSOB200_ERR_DTYPE = -2,
+  PSOB200_ERR_ALIGNMENT = -3,
+  PSOB200_ERR_LAUNCH = -4,
+  PSOB200_ERR_SHAPE = -5,
+  PSOB200_ERR_WORKSPACE = -6,
+  PSOB200_ERR_DRIVER = -7
+};
+
+/* bits set in *status by kernels */
+#define PSOB200_STATUS_TIMESTEP_NOT_IN_SCHEDULE 1
+#define PSOB200_STATUS_NONFINITE_COEFFICIENT 2
+
+/*
+ * How per-sample step coefficients are obtained.  Both reference step functions are the
+ * affine Gaussian  x' ~ N(k*x + a*eps, s^2)  (SURVEY.md App. A.2):
+ *   TURBO  (TS:61-92):  idx = first i with sched_timesteps[i] == t  (TS:63);
+ *                       sigma = table[idx], sigma_to = table[idx+1]   (TS:77-78)
+ *                       k = 1, a = sigma_down - sigma, s = sigma_up    (TS:79-92)
+ *   DMD    (DS:36-42,102-112): abar_t = table[t], abar_p = table[t_prev] (negative
+ *                       indices wrap like torch indexing);
+ *                       k = sqrt(abar_p/abar_t), a = -sqrt(abar_p (1-abar_t)/abar_t),
+ *                       s = sqrt(1-abar_p)
+ *   AFFINE: k, a, s given directly as device float arrays of length B.
+ */
+typedef struct psob200_schedule {
+  int32_t kind;                 /* PSOB200_SCHED_*                                         */
+  int32_t n_table;              /* TURBO: number of timesteps (table has n_table+1 sigmas);
+                                   DMD: length of alphas_cumprod                           */
+  const float* sched_timesteps; /* TURBO: device float[n_table] (diffusers keeps fp32)     */
+  const float* table;           /* TURBO: sigmas; DMD: alphas_cumprod (device float)       */
+  int32_t ts_dtype;             /* PSOB200_TS_* of the per-sample timestep arrays          */
+  int32_t reserved;
+} psob200_schedule;
+
+PSOB200_API int psob200_abi_version(void);
+PSOB200_API const char* psob200_strerror(int rc);
+/* Number of SMs / compute capability the library was queried with; -1 if no device. */
+PSOB200_API int psob200_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Workspace for the pair-loss kernels: >= psob200_pair_loss_workspace_bytes(B) bytes,
+ * 16-byte aligned, ZERO-INITIALISED once by the caller; the kernels leave it zeroed.
+ * One workspace must not be shared by launches that may run concurrently.
+ */
+PSOB200_API size_t psob200_pair_loss_workspace_bytes(int64_t B);
+
+/*
+ * Fused online-PSO loss + gradient: replaces the four step-with-logprob calls, the
+ * inline loss and its autograd backward of one training micro-step
+ * (T:810-850 + T:857, D:812-854 + D:859) with ONE kernel launch:
+ *
+ *   logp_{m,k}[b] = mean_CHW[-(next_k - mu_{m,k})^2/(2 s^2) - log s - 0.5 log 2pi],
+ *                   m in {policy, ref}, k in {0,1}                        (TS:108-114, DS:129-135)
+ *   ratio_k = clamp(exp(logp_pol,k - logp_ref,k), 1-eps, 1+eps)           (T:844-845)
+ *   loss    = loss_scale * mean_b[-log sigmoid(beta*(h0*log ratio_0 + h1*log ratio_1))]   (T:847-850)
+ *   grad_k  = d loss / d pred_k   (dtype of pred)                         (T:857 autograd)
+ *
+ * pred_k/ref_k: policy / frozen-reference UNet outputs, [B,N] of `pred_dtype`.
+ * sample_k/next_k: current latent and stored next latent, [B,N] of `latent_dtype`.
+ * ts_k (and ts_prev_k for DMD): per-sample timesteps [B]; for AFFINE, coef_k points to
+ * float[3*B] = k[B], a[B], s[B] and ts_* are ignored.
+ * human_prefer: float[B*2] rows (h0,h1) as produced by T:401-416 / D:420-434.
+ * Outputs: grad_k [B,N] pred_dtype; loss float[1]; stats float[B*8] (may be NULL) =
+ *   (logp_pol0, logp_ref0, logp_pol1, logp_ref1, delta0, delta1, z, pair_loss) per pair.
+ * tune_threads / tune_cluster: 0 = library heuristics.
+ */
+typedef struct psob200_online_pso_args {
+  const void* pred[2];
+  const void* ref[2];
+  const void* sample[2];
+  const void* next[2];
+  const void* ts[2];
+  const void* ts_prev[2];
+  const float* coef[2];
+  const float* human_prefer;
+  /* element stride between consecutive samples of each input (0 = dense, i.e. N); lets the
+     trainers' views `latents[:, j]` of a [B,T,C,H,W] tensor be consumed without a copy */
+  int64_t stride_pred[2];
+  int64_t stride_ref[2];
+  int64_t stride_sample[2];
+  int64_t stride_next[2];
+  void* grad[2];
+  float* loss;
+  float* stats;
+  int32_t* status;
+  void* workspace;
+  size_t workspace_bytes;
+  int64_t B;
+  int64_t N;
+  int32_t pred_dtype;
+  int32_t latent_dtype;
+  float beta;
+  float eps;
+  float loss_scale;
+  int32_t tune_threads;
+  int32_t tune_cluster;
+  int32_t reserved;
+} psob200_online_pso_args;
+
+PSOB200_API int psob200_online_pso_loss_grad(const psob200_schedule* sched, const psob200_online_pso_args* args,
+                                 void* stream);
+
+/*
+ * Fused DreamBooth-PSO loss + gradient: replaces P:1847-1865 (EDM-style epsilon
+ * preconditioning, non-EDM scheduler) + P:1881-1935 + the autograd backward (P:1953).
+ * model_pred/ref_pred: raw UNet outputs [2b,N] (`pred_dtype`), rows [0,b) = win images,
+ * [b,2b) = lose images; ref_pred is ignored (may be NULL) for PSOB200_DB_PSO_DB.
+ * noisy/target: noisy_model_input and model_input [2b,N] (`latent_dtype`);
+ * sigmas: float[2b].
+ *   x0_hat = -sigma*pred + noisy ; L_i = mean_CHW(sigma^-2 (x0_hat - target)^2)
+ *   logits = (Lref_w - nu Lref_l) - (L_w - nu L_l)        (pso)   | -(L_w - nu L_l)  (pso_db)
+ *   loss   = mean -logsigmoid(beta logits)                (pso)   | mean relu(1 - beta logits)
+ *            + lambda * mean(L_l)   if lambda > 0
+ * Outputs: grad [2b,N]; loss float[1]; stats float[b*8] (may be NULL) =
+ *   (L_w, L_l, Lref_w, Lref_l, logits, pair_loss, 0, 0).
+ */
+typedef struct psob200_dreambooth_args {
+  const void* model_pred;
+  const void* ref_pred;
+  const void* noisy;
+  const void* target;
+  const float* sigmas;
+  void* grad;
+  float* loss;
+  float* stats;
+  int32_t* status;
+  void* workspace;
+  size_t workspace_bytes;
+  int64_t b; /* pairs; tensors have 2*b rows */
+  int64_t N;
+  int32_t pred_dtype;
+  int32_t latent_dtype;
+  int32_t loss_type;
+  float beta_pso;
+  float neg_defactor;
+  float prior_loss_weight;
+  float loss_scale;
+  int32_t tune_threads;
+  int32_t tune_cluster;
+  int32_t reserved;
+} psob200_dreambooth_args;
+
+PSOB200_API int psob200_dreambooth_pso_loss_grad(const psob200_dreambooth_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * One scheduler update + Gaussian log-prob: the body of turbo_step_with_logprob
+ * (TS:24-116) and distilled_step_with_logprob (DS:45-137).
+ *
+ * Scoring mode (prev_sample != NULL, noise == NULL): log_prob[b] of the given
+ * prev_sample (TS:100-114, DS:129-135).
+ * Sampling mode (prev_sample == NULL, noise != NULL): prev_out = mu + s*noise
+ * (TS:94-99, DS:121-126) and its log_prob.  noise is [noise_rows,N] with noise_rows == B
+ * (turbo) or 1 (DMD: one draw shared by the batch, DS:123-124), of `out_dtype`.
+ * prev_out [B,N] `out_dtype` (model_output dtype for turbo TS:116, sample dtype for DMD
+ * DS:137).  scaled_next_out (may be NULL) = prev_out_fp32 / sqrt(sigma_next^2+1), the
+ * next UNet input of the turbo sampler (TP:120-121), `out_dtype`.
+ */
+typedef struct psob200_step_args {
+  const void* model_output; /* [B,N] pred_dtype   */
+  const void* sample;       /* [B,N] latent_dtype */
+  const void* prev_sample;  /* [B,N] latent_dtype, scoring mode */
+  const void* noise;        /* [noise_rows,N] out_dtype, sampling mode */
+  const void* ts;           /* [B] or [1] (ts_rows) */
+  const void* ts_prev;      /* DMD only */
+  const float* coef;        /* AFFINE only: k[B], a[B], s[B] */
+  void* prev_out;           /* sampling mode */
+  void* scaled_next_out;    /* sampling mode, optional */
+  float* log_prob;          /* [B] */
+  int32_t* status;
+  int64_t B;
+  int64_t N;
+  int64_t noise_rows;
+  int64_t ts_rows; /* B, or 1 to broadcast one timestep over the batch (TP:139) */
+  int64_t stride_model_output; /* element strides between samples, 0 = dense */
+  int64_t stride_sample;
+  int64_t stride_prev_sample;
+  int32_t pred_dtype;
+  int32_t latent_dtype;
+  int32_t out_dtype;
+  int32_t tune_threads;
+  int32_t tune_cluster;
+  int32_t reserved;
+} psob200_step_args;
+
+PSOB200_API int psob200_step_logprob(const psob200_schedule* sched, const psob200_step_args* args, void* stream);
+
+/*
+ * Backward of the scoring-mode log-prob into model_output (autograd of TS:108-114 /
+ * DS:129-135 as run by T:857):  grad[b,:] = grad_log_prob[b] * a/(s^2 N) * (prev - mu).
+ */
+typedef struct psob200_step_bwd_args {
+  const void* model_output;
+  const void* sample;
+  const void* prev_sample;
+  const void* ts;
+  const void* ts_prev;
+  const float* coef;
+  const float* grad_log_prob; /* [B] */
+  void* grad_model_output;    /* [B,N] pred_dtype */
+  int32_t* status;
+  int64_t B;
+  int64_t N;
+  int64_t ts_rows;
+  int64_t stride_model_output; /* element strides between samples, 0 = dense */
+  int64_t stride_sample;
+  int64_t stride_prev_sample;
+  int32_t pred_dtype;
+  int32_t latent_dtype;
+  int32_t reserved0;
+  int32_t reserved1;
+} psob200_step_bwd_args;
+
+PSOB200_API int psob200_step_logprob_backward(const psob200_schedule* sched, const psob200_step_bwd_args* args,
+                                  void* stream);
+
+/*
+ * x0 = (sample - sqrt(1-abar_t) * model_output) / sqrt(abar_t)   (DS:36-42; the last DMD
+ * sampler step, DP:158-162).  Output dtype = out_dtype.
+ */
+PSOB200_API int psob200_dmd_x0_from_noise(const float* alphas_cumprod, int32_t n_table, const void* model_output,
+                              const void* sample, const void* ts, int32_t ts_dtype, int64_t ts_rows,
+                              void* x0_out, int64_t B, int64_t N, int32_t pred_dtype,
+                              int32_t latent_dtype, int32_t out_dtype, int32_t* status, void* stream);
+
+/*
+ * out = in * scale[0 or b]  -- the sampler's elementwise glue:  latents*init_noise_sigma
+ * (TP:99, DP:49) and latents/sqrt(sigma^2+1) (TP:121, P:1796).  scale is a HOST float.
+ */
+PSOB200_API int psob200_scale(const void* in, void* out, int64_t count, float scale, int32_t in_dtype,
+                  int32_t out_dtype, void* stream);
+
+/*
+ * data[i] *= scale_dev[0] for a DEVICE-resident scalar; returns immediately on the device
+ * when the scalar is exactly 1.0f.  Used to apply autograd's upstream gradient of the loss
+ * to gradients that the fused kernels already produced (T:857: accelerate hands
+ * loss/gradient_accumulation_steps to backward()).
+ */
+PSOB200_API int psob200_scale_inplace_by_device_scalar(void* data, int64_t count, int32_t dtype,
+                                                       const float* scale_dev, void* stream);
+
+/* sizeof() of the argument structs as compiled into the library, for FFI bindings to
+ * verify their mirror of this header: which = 0 schedule, 1 online_pso_args,
+ * 2 dreambooth_args, 3 step_args, 4 step_bwd_args.  Returns 0 for unknown ids. */
+PSOB200_API size_t psob200_struct_size(int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSOB200_H */

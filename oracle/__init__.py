@@ -1,0 +1,35 @@
+"""CPU oracle for the PSO training-step hot path.  TEST INFRASTRUCTURE ONLY.
+
+Nothing under ``oracle/`` is product code.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it, and there only as the checker or the
+reported CPU baseline -- never as the thing measured or shipped.  The product
+package ``pairwise_sample_optimization_b200`` must not import this package.
+
+What is in here (each function cites the reference file:line it follows;
+paths are relative to ``/root/reference``):
+
+* ``reference_loader``  -- executes the reference's own two step files
+  *verbatim from /root/reference* under a tiny ``diffusers`` import stub.  Only
+  usable in the build container (the GPU box has no /root/reference); it is
+  what pins the restatement (``oracle/make_golden.py`` -> ``tests/golden``).
+* ``schedules``  -- the diffusers==0.27.0 scheduler constants the path reads
+  (third-party, absent from /root/reference; restated from the published
+  formula, anchored on sigma(999)=14.6146).
+* ``steps``      -- torch-fp32 restatement of the two step functions, plus an
+  fp64 closed form.
+* ``losses``     -- restated inline online-PSO loss, ``sample_compare`` /
+  ``compare`` and the DreamBooth-PSO loss.
+* ``lora``       -- restated peft==0.11.1 ``lora.Linear`` forward and the
+  diffusers==0.27.0 ``AttnProcessor2_0`` data flow (third-party, restated).
+* ``samplers``   -- the two few-step sampler loops.
+
+Parity pinning status: the reference ships NO tests, golden vectors or
+fixtures, so the pin is "outputs of the reference itself
+run here": ``tests/golden/*.npz`` were produced by ``oracle/make_golden.py``
+calling the verbatim reference functions, and ``tests/test_oracle_golden.py``
+checks the restatement against them.  The inline losses exist only as trainer
+code that cannot be imported (needs diffusers/peft/accelerate); they are
+restated line by line and cross-checked against autograd + the fp64 closed
+form -- that part is "parity pinned to a restatement", stated in DESIGN.md.
+"""
