@@ -169,8 +169,6 @@ def run_b200(args):
     d = {k: v.to(dev) for k, v in host.items()}
     sched = types.SimpleNamespace(alphas_cumprod=alphas_cumprod().to(dev))
     torch.cuda.manual_seed(99 + rank)  # sampler noise comes from the default CUDA generator (graph-capturable)
-    for k in (0, 1):
-        d[f"pred{k}"].requires_grad_(True)
     launches_per_step = 5
 
     def step(t):
@@ -180,12 +178,12 @@ def run_b200(args):
         for k in (0, 1):  # sampler update under the frozen reference policy -> stored next latents
             xn, _ = pso.distilled_step_with_logprob(sched, t[f"ref{k}"], ts, tp, t[f"x{k}"])
             nxt.append(xn)
-        for k in (0, 1):
-            t[f"pred{k}"].grad = None
-        loss = pso.pso_pair_loss(t["pred0"], t["pred1"], t["ref0"], t["ref1"], t["x0"], t["x1"], nxt[0], nxt[1],
+        # fresh autograd leaves every step (what a UNet forward would hand over)
+        p0, p1 = t["pred0"].detach().requires_grad_(True), t["pred1"].detach().requires_grad_(True)
+        loss = pso.pso_pair_loss(p0, p1, t["ref0"], t["ref1"], t["x0"], t["x1"], nxt[0], nxt[1],
                                  ts, ts, t["h"], scheduler=sched, kind="dmd", beta=50.0, eps=0.1, step_ratio=STEP_RATIO)
         loss.backward()
-        return loss, nxt
+        return loss, nxt, (p0.grad, p1.grad)
 
     def barrier():
         if world > 1:
@@ -205,11 +203,11 @@ def run_b200(args):
     side = torch.cuda.Stream(dev)
     with torch.cuda.stream(side):
         for _ in range(max(W, 3)):
-            loss, nxt = step(d)
+            loss, nxt, grads = step(d)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph, stream=side):
-        g_loss, g_nxt = step(d)
+        g_loss, g_nxt, g_grads = step(d)
     for _ in range(max(W, 3)):
         graph.replay()
     pso.check_status(dev)
@@ -238,12 +236,21 @@ def run_b200(args):
             return pso.pso_pair_loss(d["pred0"].detach(), d["pred1"].detach(), d["ref0"], d["ref1"], d["x0"], d["x1"],
                                      nxt[0], nxt[1], ts, ts, d["h"], scheduler=sched, kind="dmd", beta=50.0, eps=0.1,
                                      step_ratio=STEP_RATIO, tune=tune)
-    for _ in range(3):
+    # the Python/ctypes cost of one call exceeds the kernel's run time, so the launch is captured in a CUDA graph:
+    # the host then runs ahead of the GPU and each event pair brackets device time only
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            loss_only()
+    torch.cuda.synchronize()
+    kgraph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(kgraph, stream=side):
         loss_only()
+    for _ in range(3):
+        kgraph.replay()
     torch.cuda.synchronize()
     for a, b in evs:
         a.record()
-        loss_only()
+        kgraph.replay()
         b.record()
     torch.cuda.synchronize()
     kern_ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
@@ -263,7 +270,7 @@ def run_b200(args):
         with torch.no_grad():
             for k, v in host.items():
                 d[k].copy_(v, non_blocking=True)
-        loss, _ = step(d)
+        loss, _, _ = step(d)
         loss_pinned.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_pinned)

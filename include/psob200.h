@@ -93,6 +93,8 @@ typedef struct psob200_schedule {
 
 PSOB200_API int psob200_abi_version(void);
 PSOB200_API const char* psob200_strerror(int rc);
+/* What the CUDA runtime reported for this thread's most recent PSOB200_ERR_LAUNCH ("" if none). */
+PSOB200_API const char* psob200_last_error_detail(void);
 /* Number of SMs / compute capability the library was queried with; -1 if no device. */
 PSOB200_API int psob200_device_sm_count(void);
 

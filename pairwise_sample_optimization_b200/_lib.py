@@ -75,6 +75,7 @@ _STRUCTS = {0: Schedule, 1: OnlinePsoArgs, 2: DreamboothArgs, 3: StepArgs, 4: St
 SIGNATURES = {
     "psob200_abi_version": (C.c_int, []),
     "psob200_strerror": (C.c_char_p, [C.c_int]),
+    "psob200_last_error_detail": (C.c_char_p, []),
     "psob200_device_sm_count": (C.c_int, []),
     "psob200_struct_size": (C.c_size_t, [C.c_int]),
     "psob200_pair_loss_workspace_bytes": (C.c_size_t, [C.c_int64]),
@@ -119,7 +120,8 @@ def lib() -> C.CDLL:
 
 def check(rc: int, what: str) -> None:
     if rc != 0:
-        raise Psob200Error(f"{what} failed: {lib().psob200_strerror(rc).decode()} (rc={rc})")
+        detail = lib().psob200_last_error_detail().decode() if rc == -4 else ""
+        raise Psob200Error(f"{what} failed: {lib().psob200_strerror(rc).decode()} (rc={rc}){' -- ' + detail if detail else ''}")
 
 
 def dtype_code(t: torch.Tensor) -> int:

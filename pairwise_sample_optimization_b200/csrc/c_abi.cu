@@ -1,6 +1,17 @@
 // Library-level entry points of the C ABI (include/psob200.h).
 #include "common.cuh"
 
+#include <cstdio>
+
+namespace psob200 {
+static thread_local char g_error_detail[256] = "";
+void set_error_detail(const char* where, cudaError_t e) {
+  std::snprintf(g_error_detail, sizeof(g_error_detail), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+}  // namespace psob200
+
+extern "C" const char* psob200_last_error_detail(void) { return psob200::g_error_detail; }
+
 extern "C" int psob200_abi_version(void) { return PSOB200_ABI_VERSION; }
 
 extern "C" const char* psob200_strerror(int rc) {

@@ -36,6 +36,12 @@ struct Vec8;
 template <>
 struct Vec8<float> {
   static constexpr int kBytes = 32;
+  struct Raw { uint4 a, b; };
+  static __device__ __forceinline__ Raw load_raw(const float* p) { return Raw{ldg_stream_u4(p), ldg_stream_u4(p + 4)}; }
+  static __device__ __forceinline__ void decode(const Raw& r, float (&v)[8]) {
+    v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+    v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+  }
   static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
     uint4 a = ldg_stream_u4(p), b = ldg_stream_u4(p + 4);
     v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
@@ -55,6 +61,16 @@ struct Vec8<float> {
 template <>
 struct Vec8<__nv_bfloat16> {
   static constexpr int kBytes = 16;
+  struct Raw { uint4 a; };
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) { return Raw{ldg_stream_u4(p)}; }
+  static __device__ __forceinline__ void decode(const Raw& r, float (&v)[8]) {
+    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 a = ldg_stream_u4(p);
     const uint32_t w[4] = {a.x, a.y, a.z, a.w};
@@ -83,6 +99,17 @@ struct Vec8<__nv_bfloat16> {
 template <>
 struct Vec8<__half> {
   static constexpr int kBytes = 16;
+  struct Raw { uint4 a; };
+  static __device__ __forceinline__ Raw load_raw(const __half* p) { return Raw{ldg_stream_u4(p)}; }
+  static __device__ __forceinline__ void decode(const Raw& r, float (&v)[8]) {
+    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
   static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
     uint4 a = ldg_stream_u4(p);
     const uint32_t w[4] = {a.x, a.y, a.z, a.w};
@@ -193,6 +220,17 @@ __device__ __forceinline__ StepCoef resolve_coef(const psob200_schedule& sc, con
 // ---------------------------------------------------------------------------------------------
 // Host-side helpers
 // ---------------------------------------------------------------------------------------------
+// Records what CUDA said about the last failed call of this thread (psob200_last_error_detail()).
+void set_error_detail(const char* where, cudaError_t e);
+// Consumes the sticky-free last error; returns PSOB200_ERR_LAUNCH (and records the detail) if there was one.
+inline int consume_launch_error(const char* where, cudaError_t e) {
+  if (e == cudaSuccess) e = cudaPeekAtLastError();
+  if (e == cudaSuccess) return PSOB200_OK;
+  set_error_detail(where, e);
+  cudaGetLastError();
+  return PSOB200_ERR_LAUNCH;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t dtype_size(int32_t dt) { return dt == PSOB200_F32 ? 4 : 2; }
 inline bool valid_dtype(int32_t dt) { return dt == PSOB200_F32 || dt == PSOB200_BF16 || dt == PSOB200_F16; }

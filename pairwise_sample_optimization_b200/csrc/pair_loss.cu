@@ -1,16 +1,29 @@
 // Fused pairwise PSO loss + gradient (sm_100a).
 //
-// One thread-block CLUSTER per (win, lose) pair.  Pass 1 streams the pair's eight tensors
-// (policy / frozen-reference predictions, current and next latents, for both branches) from HBM
-// with 128-bit loads, keeps the policy residual r = x' - (k x + a eps) in shared memory (fp32) and
-// reduces the per-branch sums of squares with warp shuffles -> shared memory -> distributed shared
-// memory across the cluster.  Every CTA then evaluates the pair's scalar loss function redundantly
-// (deterministic, no atomics on the data path) and pass 2 writes grad = g_k * r from shared memory.
+// One thread-block CLUSTER per (win, lose) pair.  Every CTA owns a contiguous slab of the pair's
+// eight tensors (policy / frozen-reference predictions, current and next latents, both branches):
+//
+//   pass 1  stream the slab from HBM, form the policy residual r = x' - (k x + a eps) and the three
+//           per-branch sums  S_pol = sum r^2,  S_ref = sum r_ref^2,  D = sum (r_ref^2 - r^2);
+//   reduce  warp shuffles -> shared memory -> distributed shared memory all-gather over the cluster;
+//           every CTA evaluates the pair's scalar loss function redundantly in fp64 (deterministic,
+//           no atomics on the data path);
+//   pass 2  write grad = g_k * r from the residuals kept ON CHIP.
+//
 // HBM traffic is the algorithmic 8N reads + 2N writes per pair.
+//
+// Two kernels share that structure:
+//   pair_loss_grad_tma_kernel  (fast path) the slab is fetched by 1-D TMA bulk copies
+//           (cp.async.bulk ... mbarrier::complete_tx) issued up front by one thread into a shared-memory
+//           ring: the whole slab is in flight at once with no register staging, overlapping the fp64
+//           coefficient prologue; residuals live in registers (32 per thread).
+//   pair_loss_grad_kernel      (general path) vectorised or scalar LDG, residuals in shared memory;
+//           any N, any alignment, up to 25600 elements per branch per CTA.
 //
 // Replaces: train_online_pso_sdxl_turbo.py:810-850,857 / train_online_pso_sdxl_dmd2.py:812-854,859
 // (online) and train_pso_sdxl_turbo_dreambooth.py:1847-1865,1881-1935,1953 (DreamBooth).
 #include <atomic>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -39,6 +52,7 @@ struct PairKernelArgs {
   float* pair_loss;
   long long B, N;
   long long stride[4][2];  // element stride between samples: pred, ref, x, xn
+  double log_lo, log_hi;   // log(1-eps), log(1+eps): the clamp of T:844-845 expressed on delta
   int chunks_per_cta;
   int mode;
   float beta, eps, loss_scale, nu, lam;
@@ -51,13 +65,172 @@ __device__ __forceinline__ double sigmoid_neg(double z) {  // sigmoid(-z)
   return 1.0 / (1.0 + exp(z));
 }
 
+__device__ __forceinline__ void resolve_pair_coefs(const PairKernelArgs& a, long long pair, int k, StepCoef* out) {
+  if (a.mode == kModeOnline) {
+    *out = resolve_coef(a.sched, a.ts[k], a.ts_prev[k], a.coef[k], pair, pair, a.B, a.N, a.status);
+  } else {
+    const double sg = (double)a.sigmas[(long long)k * a.B + pair];  // P:1855: x0_hat = -sigma*pred + noisy
+    *out = make_coef(1.0, -sg, sg, a.N, a.status);
+  }
+}
+
+// The pair's scalar function, evaluated by ONE thread of every CTA of the cluster on identical inputs
+// (partials summed in rank order), so all CTAs obtain bit-identical gradient multipliers.
+__device__ __forceinline__ void pair_scalar_function(const PairKernelArgs& a, long long pair, unsigned rank, unsigned C,
+                                                     const float (*s_part)[8], const StepCoef* s_coef, float* s_g) {
+  double S[2][3];
+  for (int k = 0; k < 2; ++k)
+    for (int j = 0; j < 3; ++j) {
+      double v = 0.0;
+      for (unsigned r = 0; r < C; ++r) v += (double)s_part[r][k * 3 + j];
+      S[k][j] = v;
+    }
+  const StepCoef c0 = s_coef[0], c1 = s_coef[1];
+  const double i0 = (double)c0.inv_2s2n, i1 = (double)c1.inv_2s2n;
+  const double invB = 1.0 / (double)a.B;
+  double g0, g1, per;
+  float st[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (a.mode == kModeOnline) {
+    const double kHalfLog2Pi = 0.91893853320467274178;
+    const double d0 = S[0][2] * i0, d1 = S[1][2] * i1;  // delta_k = logp_pol,k - logp_ref,k
+    const double beta = (double)a.beta, lo = a.log_lo, hi = a.log_hi;
+    const bool open0 = (d0 >= lo) && (d0 <= hi), open1 = (d1 >= lo) && (d1 <= hi);
+    // log(clamp(exp(d), 1-eps, 1+eps)): inside the clamp that is d itself (T:844-845); NaN propagates
+    const double lr0 = open0 ? d0 : (d0 < lo ? lo : (d0 > hi ? hi : d0));
+    const double lr1 = open1 ? d1 : (d1 < lo ? lo : (d1 > hi ? hi : d1));
+    const double h0 = (double)a.human_prefer[pair * 2], h1 = (double)a.human_prefer[pair * 2 + 1];
+    const double z = beta * (h0 * lr0 + h1 * lr1);  // T:847-850
+    per = softplus_neg(z);
+    const double common = -sigmoid_neg(z) * invB * beta * (double)a.loss_scale;
+    g0 = open0 ? common * h0 * (double)c0.a_over_s2n : 0.0;  // torch.clamp passes grad on the closed interval
+    g1 = open1 ? common * h1 * (double)c1.a_over_s2n : 0.0;
+    st[0] = (float)(-S[0][0] * i0 - (double)c0.log_s - kHalfLog2Pi);  // TS:108-114 / DS:129-135
+    st[1] = (float)(-S[0][1] * i0 - (double)c0.log_s - kHalfLog2Pi);
+    st[2] = (float)(-S[1][0] * i1 - (double)c1.log_s - kHalfLog2Pi);
+    st[3] = (float)(-S[1][1] * i1 - (double)c1.log_s - kHalfLog2Pi);
+    st[4] = (float)d0;
+    st[5] = (float)d1;
+    st[6] = (float)z;
+    st[7] = (float)per;
+  } else {
+    const double nu = (double)a.nu, beta = (double)a.beta;
+    const double lam = a.lam > 0.f ? (double)a.lam : 0.0;           // P:1932
+    const double Lw = 2.0 * S[0][0] * i0, Ll = 2.0 * S[1][0] * i1;  // P:1885-1891
+    double logits, dl;
+    if (a.mode == kModeDbPso) {
+      logits = 2.0 * S[0][2] * i0 - nu * (2.0 * S[1][2] * i1);  // (Lref_w-L_w) - nu (Lref_l-L_l)  P:1919
+      per = softplus_neg(beta * logits);                         // P:1925
+      dl = -beta * sigmoid_neg(beta * logits) * invB;
+      st[2] = (float)(2.0 * S[0][1] * i0);
+      st[3] = (float)(2.0 * S[1][1] * i1);
+    } else {
+      logits = -(Lw - nu * Ll);  // P:1922
+      const double m = 1.0 - beta * logits;
+      per = m > 0.0 ? m : (m == m ? 0.0 : m);  // relu, NaN propagates   P:1927
+      dl = m > 0.0 ? -beta * invB : 0.0;
+    }
+    per += lam * Ll;  // P:1932-1935
+    const double Gw = -dl, Gl = nu * dl + lam * invB;
+    g0 = (double)a.loss_scale * Gw * (-2.0 * (double)c0.a_over_s2n);
+    g1 = (double)a.loss_scale * Gl * (-2.0 * (double)c1.a_over_s2n);
+    st[0] = (float)Lw;
+    st[1] = (float)Ll;
+    st[4] = (float)logits;
+    st[5] = (float)per;
+  }
+  s_g[0] = (float)g0;
+  s_g[1] = (float)g1;
+  if (rank == 0) {
+    a.pair_loss[pair] = (float)per;
+    if (a.stats != nullptr) {
+      float4* dst = reinterpret_cast<float4*>(a.stats + pair * 8);
+      dst[0] = make_float4(st[0], st[1], st[2], st[3]);
+      dst[1] = make_float4(st[4], st[5], st[6], st[7]);
+    }
+  }
+}
+
+// CTA-level sum of the six accumulators and all-gather of the CTA partials over the cluster through
+// distributed shared memory.  On return s_part[r][0..5] holds CTA r's partials in every CTA.
+__device__ __forceinline__ void reduce_and_allgather(cg::cluster_group& cluster, const float (&acc)[2][3],
+                                                     float (*s_warp)[kMaxThreads / 32], float (*s_part)[8]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float v = warp_sum(acc[k][j]);
+      if (lane == 0) s_warp[k * 3 + j][warp] = v;
+    }
+  __syncthreads();
+  float part = 0.f;
+  if (tid < 6)
+    for (int w = 0; w < nwarps; ++w) part += s_warp[tid][w];
+  cluster.barrier_wait();  // pairs with barrier_arrive() at kernel entry: every CTA of the cluster is running
+  if (tid < 6)
+    for (unsigned r = 0; r < C; ++r) *cluster.map_shared_rank(&s_part[rank][tid], r) = part;
+  cluster.sync();  // arrive.release / wait.acquire: the partials are visible in every CTA
+}
+
+// mean over pairs by the last cluster to finish (fixed summation order: deterministic); leaves the
+// workspace counter zeroed for the next launch.
+__device__ __forceinline__ void finalize_mean(const PairKernelArgs& a, int lane) {
+  unsigned ticket = 0;
+  if (lane == 0) {
+    __threadfence();
+    ticket = atomicAdd(a.counter, 1u);
+  }
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  if (ticket == (unsigned)(a.B - 1)) {
+    __threadfence();
+    double s = 0.0;
+    for (long long i = lane; i < a.B; i += 32) s += (double)__ldcg(a.pair_loss + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      a.loss[0] = (float)((double)a.loss_scale * s / (double)a.B);
+      *a.counter = 0u;
+    }
+  }
+}
+
+template <bool HAS_REF>
+__device__ __forceinline__ void residual8(const float (&vx)[8], const float (&vn)[8], const float (&vp)[8],
+                                          const float (&vr)[8], float kx, float ca, float (&r)[8], float& s_t,
+                                          float& s_r, float& s_d) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float b0 = fmaf(-kx, vx[i], vn[i]);
+    const float rt = fmaf(-ca, vp[i], b0);
+    r[i] = rt;
+    s_t = fmaf(rt, rt, s_t);
+    if constexpr (HAS_REF) {
+      const float rr = fmaf(-ca, vr[i], b0);
+      s_r = fmaf(rr, rr, s_r);
+      // sum(rr^2 - rt^2) = sum((rr-rt)(rr+rt)) with rr-rt = a*(eps_pol - eps_ref) formed from the
+      // predictions themselves: no cancellation against the (much larger) latents
+      s_d = fmaf(ca * (vp[i] - vr[i]), rr + rt, s_d);
+    }
+  }
+}
+
+}  // namespace psob200
+
+#include "pair_loss_tma.cuh"  // fast path: persistent clusters + TMA ring
+
+namespace psob200 {
+
+// =============================================================================================
+// General path: LDG (vector or scalar), residuals in shared memory.
+// =============================================================================================
 template <typename TP, typename TL, bool HAS_REF, int W>
 __global__ void __launch_bounds__(kMaxThreads) pair_loss_grad_kernel(const PairKernelArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned C = cluster.num_blocks();
   const unsigned rank = cluster.block_rank();
   const long long pair = blockIdx.x / C;
-  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* res = reinterpret_cast<float*>(smem_raw);  // [2 branches][chunks_per_cta * W] residuals
@@ -66,27 +239,15 @@ __global__ void __launch_bounds__(kMaxThreads) pair_loss_grad_kernel(const PairK
   __shared__ StepCoef s_coef[2];
   __shared__ float s_g[2];
 
-  cluster.barrier_arrive();  // matched by barrier_wait() just before the DSMEM exchange
-
-  if (tid < 2) {
-    StepCoef c;
-    if (a.mode == kModeOnline) {
-      c = resolve_coef(a.sched, a.ts[tid], a.ts_prev[tid], a.coef[tid], pair, pair, a.B, a.N, a.status);
-    } else {
-      const double sg = (double)a.sigmas[(long long)tid * a.B + pair];  // P:1855: x0_hat = -sigma*pred + noisy
-      c = make_coef(1.0, -sg, sg, a.N, a.status);
-    }
-    s_coef[tid] = c;
-  }
+  cluster.barrier_arrive();
+  if (tid < 2) resolve_pair_coefs(a, pair, tid, &s_coef[tid]);
   __syncthreads();
 
   const int cpc = a.chunks_per_cta;
   const long long nchunk = (a.N + W - 1) / W;
   const long long cbeg = (long long)rank * cpc;
   const long long cend = (cbeg + cpc < nchunk) ? cbeg + cpc : nchunk;
-  const long long base = pair * a.N;
 
-  // ------------------------------------------------------------------ pass 1: residuals + sums
   float acc[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
@@ -107,18 +268,7 @@ __global__ void __launch_bounds__(kMaxThreads) pair_loss_grad_kernel(const PairK
         Vec8<TL>::load(xn + c * 8, vn);
         Vec8<TP>::load(pred + c * 8, vp);
         if constexpr (HAS_REF) Vec8<TP>::load(ref + c * 8, vr);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float b0 = fmaf(-kx, vx[i], vn[i]);
-          const float rt = fmaf(-ca, vp[i], b0);
-          r[i] = rt;
-          s_t = fmaf(rt, rt, s_t);
-          if constexpr (HAS_REF) {
-            const float rr = fmaf(-ca, vr[i], b0);
-            s_r = fmaf(rr, rr, s_r);
-            s_d = fmaf(rr - rt, rr + rt, s_d);  // sum(rr^2 - rt^2) without cancellation
-          }
-        }
+        residual8<HAS_REF>(vx, vn, vp, vr, kx, ca, r, s_t, s_r, s_d);
         const int l = (int)(c - cbeg);
         plane0[l] = make_float4(r[0], r[1], r[2], r[3]);
         plane1[l] = make_float4(r[4], r[5], r[6], r[7]);
@@ -126,12 +276,14 @@ __global__ void __launch_bounds__(kMaxThreads) pair_loss_grad_kernel(const PairK
     } else {
       for (long long c = cbeg + tid; c < cend; c += T) {
         const float b0 = fmaf(-kx, Vec8<TL>::load1(x + c), Vec8<TL>::load1(xn + c));
-        const float rt = fmaf(-ca, Vec8<TP>::load1(pred + c), b0);
+        const float ep = Vec8<TP>::load1(pred + c);
+        const float rt = fmaf(-ca, ep, b0);
         s_t = fmaf(rt, rt, s_t);
         if constexpr (HAS_REF) {
-          const float rr = fmaf(-ca, Vec8<TP>::load1(ref + c), b0);
+          const float er = Vec8<TP>::load1(ref + c);
+          const float rr = fmaf(-ca, er, b0);
           s_r = fmaf(rr, rr, s_r);
-          s_d = fmaf(rr - rt, rr + rt, s_d);
+          s_d = fmaf(ca * (ep - er), rr + rt, s_d);
         }
         resk[c - cbeg] = rt;
       }
@@ -141,104 +293,14 @@ __global__ void __launch_bounds__(kMaxThreads) pair_loss_grad_kernel(const PairK
     acc[k][2] = s_d;
   }
 
-  // ------------------------------------------------------------------ CTA reduce, cluster all-gather
-#pragma unroll
-  for (int k = 0; k < 2; ++k)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float v = warp_sum(acc[k][j]);
-      if (lane == 0) s_warp[k * 3 + j][warp] = v;
-    }
-  __syncthreads();
-  float part = 0.f;
-  if (tid < 6)
-    for (int w = 0; w < nwarps; ++w) part += s_warp[tid][w];
-  cluster.barrier_wait();  // every CTA of the cluster has started: remote shared memory is addressable
-  if (tid < 6)
-    for (unsigned r = 0; r < C; ++r) *cluster.map_shared_rank(&s_part[rank][tid], r) = part;
-  cluster.sync();  // arrive.release / wait.acquire: all partials visible in every CTA
-
-  // ------------------------------------------------------------------ pair scalar function (fp64)
-  if (tid == 0) {
-    double S[2][3];
-    for (int k = 0; k < 2; ++k)
-      for (int j = 0; j < 3; ++j) {
-        double v = 0.0;
-        for (unsigned r = 0; r < C; ++r) v += (double)s_part[r][k * 3 + j];  // fixed order: deterministic
-        S[k][j] = v;
-      }
-    const StepCoef c0 = s_coef[0], c1 = s_coef[1];
-    const double i0 = (double)c0.inv_2s2n, i1 = (double)c1.inv_2s2n;
-    const double invB = 1.0 / (double)a.B;
-    double g0, g1, per;
-    float st[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (a.mode == kModeOnline) {
-      const double kHalfLog2Pi = 0.91893853320467274178;
-      const double d0 = S[0][2] * i0, d1 = S[1][2] * i1;  // delta_k = logp_pol,k - logp_ref,k
-      const double beta = (double)a.beta, eps = (double)a.eps;
-      const double lo = (1.0 - eps > 0.0) ? log(1.0 - eps) : -__longlong_as_double(0x7ff0000000000000LL);
-      const double hi = log(1.0 + eps);
-      const bool open0 = (d0 >= lo) && (d0 <= hi), open1 = (d1 >= lo) && (d1 <= hi);
-      // log(clamp(exp(d), 1-eps, 1+eps)); inside the clamp that is d itself (T:844-845); NaN propagates
-      const double lr0 = open0 ? d0 : (d0 < lo ? lo : (d0 > hi ? hi : d0));
-      const double lr1 = open1 ? d1 : (d1 < lo ? lo : (d1 > hi ? hi : d1));
-      const double h0 = (double)a.human_prefer[pair * 2], h1 = (double)a.human_prefer[pair * 2 + 1];
-      const double z = beta * (h0 * lr0 + h1 * lr1);  // T:847-850
-      per = softplus_neg(z);
-      const double common = -sigmoid_neg(z) * invB * beta * (double)a.loss_scale;
-      g0 = open0 ? common * h0 * (double)c0.a_over_s2n : 0.0;
-      g1 = open1 ? common * h1 * (double)c1.a_over_s2n : 0.0;
-      st[0] = (float)(-S[0][0] * i0 - (double)c0.log_s - kHalfLog2Pi);
-      st[1] = (float)(-S[0][1] * i0 - (double)c0.log_s - kHalfLog2Pi);
-      st[2] = (float)(-S[1][0] * i1 - (double)c1.log_s - kHalfLog2Pi);
-      st[3] = (float)(-S[1][1] * i1 - (double)c1.log_s - kHalfLog2Pi);
-      st[4] = (float)d0;
-      st[5] = (float)d1;
-      st[6] = (float)z;
-    } else {
-      const double nu = (double)a.nu, beta = (double)a.beta;
-      const double lam = a.lam > 0.f ? (double)a.lam : 0.0;  // P:1932
-      const double Lw = 2.0 * S[0][0] * i0, Ll = 2.0 * S[1][0] * i1;  // P:1885-1891
-      double logits, dl;
-      if (a.mode == kModeDbPso) {
-        logits = 2.0 * S[0][2] * i0 - nu * (2.0 * S[1][2] * i1);  // (Lref_w-L_w) - nu (Lref_l-L_l)  P:1919
-        per = softplus_neg(beta * logits);                         // P:1925
-        dl = -beta * sigmoid_neg(beta * logits) * invB;
-        st[2] = (float)(2.0 * S[0][1] * i0);
-        st[3] = (float)(2.0 * S[1][1] * i1);
-      } else {
-        logits = -(Lw - nu * Ll);  // P:1922
-        const double m = 1.0 - beta * logits;
-        per = m > 0.0 ? m : (m == m ? 0.0 : m);  // relu, NaN propagates   P:1927
-        dl = m > 0.0 ? -beta * invB : 0.0;
-      }
-      per += lam * Ll;  // P:1932-1935
-      const double Gw = -dl, Gl = nu * dl + lam * invB;
-      g0 = (double)a.loss_scale * Gw * (-2.0 * (double)c0.a_over_s2n);
-      g1 = (double)a.loss_scale * Gl * (-2.0 * (double)c1.a_over_s2n);
-      st[0] = (float)Lw;
-      st[1] = (float)Ll;
-      st[4] = (float)logits;
-    }
-    s_g[0] = (float)g0;
-    s_g[1] = (float)g1;
-    if (rank == 0) {
-      a.pair_loss[pair] = (float)per;
-      if (a.stats != nullptr) {
-        if (a.mode == kModeOnline) st[7] = (float)per; else st[5] = (float)per;
-        float4* dst = reinterpret_cast<float4*>(a.stats + pair * 8);
-        dst[0] = make_float4(st[0], st[1], st[2], st[3]);
-        dst[1] = make_float4(st[4], st[5], st[6], st[7]);
-      }
-    }
-  }
+  reduce_and_allgather(cluster, acc, s_warp, s_part);
+  if (tid == 0) pair_scalar_function(a, pair, rank, C, s_part, s_coef, s_g);
   __syncthreads();
 
-  // ------------------------------------------------------------------ pass 2: grad = g_k * r
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const float g = s_g[k];
-    TP* grad = reinterpret_cast<TP*>(a.grad[k]) + base;
+    TP* grad = reinterpret_cast<TP*>(a.grad[k]) + pair * a.N;
     const float* resk = res + (size_t)k * cpc * W;
     if constexpr (W == 8) {
       const float4* plane0 = reinterpret_cast<const float4*>(resk);
@@ -254,55 +316,111 @@ __global__ void __launch_bounds__(kMaxThreads) pair_loss_grad_kernel(const PairK
       for (long long c = cbeg + tid; c < cend; c += T) Vec8<TP>::store1(grad + c, g * resk[c - cbeg]);
     }
   }
-
-  // ------------------------------------------------------------------ mean over pairs: last cluster to finish
-  if (rank == 0 && warp == 0) {
-    unsigned ticket = 0;
-    if (lane == 0) {
-      __threadfence();
-      ticket = atomicAdd(a.counter, 1u);
-    }
-    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if (ticket == (unsigned)(a.B - 1)) {
-      __threadfence();
-      double s = 0.0;
-      for (long long i = lane; i < a.B; i += 32) s += (double)__ldcg(a.pair_loss + i);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) {
-        a.loss[0] = (float)((double)a.loss_scale * s / (double)a.B);
-        *a.counter = 0u;  // leave the workspace zeroed for the next launch
-      }
-    }
-  }
+  if (rank == 0 && warp == 0) finalize_mean(a, lane);
 }
 
 // ----------------------------------------------------------------------------------------------
-template <typename TP, typename TL, bool HAS_REF, int W>
-static int launch_pair_inst(const PairKernelArgs& ka, int threads, int cluster, size_t smem, cudaStream_t stream) {
-  auto kern = pair_loss_grad_kernel<TP, TL, HAS_REF, W>;
-  static std::atomic<int> configured{0};
-  if (!configured.load(std::memory_order_acquire)) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-      cudaGetLastError();
-      return PSOB200_ERR_LAUNCH;
-    }
-    configured.store(1, std::memory_order_release);
-  }
-  const cudaError_t e = launch_cluster(kern, dim3((unsigned)(ka.B * cluster)), dim3(threads), smem, stream,
-                                       (unsigned)cluster, ka);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    return PSOB200_ERR_LAUNCH;
-  }
+template <typename K>
+static int ensure_dynamic_smem(K kern, size_t smem, std::atomic<size_t>& configured, const char* what) {
+  if (smem <= configured.load(std::memory_order_acquire)) return PSOB200_OK;
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return consume_launch_error(what, e);
+  const size_t limit = (size_t)227 * 1024 - fa.sharedSizeBytes;
+  if (smem > limit) return PSOB200_ERR_SHAPE;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+  if (e != cudaSuccess) return consume_launch_error(what, e);
+  configured.store(limit, std::memory_order_release);
   return PSOB200_OK;
 }
 
+template <typename TP, typename TL, bool HAS_REF, int W>
+static int launch_pair_inst(const PairKernelArgs& ka, int threads, int cluster, size_t smem, cudaStream_t stream) {
+  auto kern = pair_loss_grad_kernel<TP, TL, HAS_REF, W>;
+  static std::atomic<size_t> configured{48 * 1024};
+  const int rc = ensure_dynamic_smem(kern, smem, configured, "configure pair_loss_grad_kernel");
+  if (rc != PSOB200_OK) return rc;
+  const cudaError_t e = launch_cluster(kern, dim3((unsigned)(ka.B * cluster)), dim3(threads), smem, stream,
+                                       (unsigned)cluster, ka);
+  return consume_launch_error("launch pair_loss_grad_kernel", e);
+}
+
+// Clusters of `cluster` CTAs that can be co-resident for this kernel (cached per instantiation and cluster size).
+template <typename K>
+static int max_active_clusters(K kern, int threads, size_t smem, int cluster, int sm_count, int ctas_per_sm,
+                               std::atomic<int>* cache) {
+  int idx = cluster == 1 ? 0 : cluster == 2 ? 1 : cluster == 4 ? 2 : 3;
+  int v = cache[idx].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(sm_count * ctas_per_sm / cluster * cluster));
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = sm_count * ctas_per_sm / cluster;  // optimistic fallback: the grid is still correct, only less balanced
+  }
+  cache[idx].store(n, std::memory_order_relaxed);
+  return n;
+}
+
+template <typename TP, typename TL, bool HAS_REF>
+static int launch_pair_tma_inst(const PairKernelArgs& ka, int cluster, int sm_count, cudaStream_t stream) {
+  auto kern = pair_loss_grad_tma_kernel<TP, TL, HAS_REF>;
+  using Cfg = TmaCfg<TP, TL, HAS_REF>;
+  constexpr size_t smem = Cfg::kSmemBytes;
+  static std::atomic<size_t> configured{48 * 1024};
+  static std::atomic<int> active[4];
+  const int rc = ensure_dynamic_smem(kern, smem, configured, "configure pair_loss_grad_tma_kernel");
+  if (rc != PSOB200_OK) return rc;
+  long long clusters = max_active_clusters(kern, kTmaThreads, smem, cluster, sm_count, 1, active);
+  if (clusters > ka.B) clusters = ka.B;  // persistent: every cluster loops over pairs cluster_id, +clusters, ...
+  const cudaError_t e = launch_cluster(kern, dim3((unsigned)(clusters * cluster)), dim3(kTmaThreads), smem, stream,
+                                       (unsigned)cluster, ka);
+  return consume_launch_error("launch pair_loss_grad_tma_kernel", e);
+}
+
+// tune_threads: 0 = heuristics (the persistent TMA kernel, 512 threads); > 0 = the general (LDG) kernel with that
+//               many threads.  tune_cluster: 0 = heuristics.
 static int launch_pair(PairKernelArgs ka, bool has_ref, int32_t pred_dtype, int32_t latent_dtype, bool vec_ok,
                        int tune_threads, int tune_cluster, int sm_count, cudaStream_t stream) {
+  if (tune_cluster != 0 && tune_cluster != 1 && tune_cluster != 2 && tune_cluster != 4 && tune_cluster != 8)
+    return PSOB200_ERR_INVALID_ARG;
+  if (tune_threads < 0) return PSOB200_ERR_INVALID_ARG;
+  // ---- fast path: persistent TMA ring, <= 2 * kTmaThreads chunks per branch per CTA
+  if (vec_ok && tune_threads == 0) {
+    const long long nchunk = ka.N / 8;
+    int cluster = tune_cluster;
+    if (cluster == 0) {
+      cluster = 1;
+      while (cluster < kMaxCluster && (nchunk + cluster - 1) / cluster > 2 * kTmaThreads) cluster <<= 1;
+      // small batches: spread a pair over more SMs as long as every CTA keeps >= 256 chunks
+      while (cluster < kMaxCluster && ka.B * cluster < sm_count && nchunk / (cluster * 2) >= 256) cluster <<= 1;
+    }
+    const long long cpc = (nchunk + cluster - 1) / cluster;
+    if (cpc <= 2 * kTmaThreads) {
+      ka.chunks_per_cta = (int)cpc;
+      return dispatch2(pred_dtype, latent_dtype, [&](auto tp, auto tl) -> int {
+        using TP = decltype(tp);
+        using TL = decltype(tl);
+        return has_ref ? launch_pair_tma_inst<TP, TL, true>(ka, cluster, sm_count, stream)
+                       : launch_pair_tma_inst<TP, TL, false>(ka, cluster, sm_count, stream);
+      });
+    }
+    if (tune_cluster != 0) return PSOB200_ERR_SHAPE;
+  }
+  // ---- general path
   const int W = vec_ok ? 8 : 1;
   const long long nchunk = (ka.N + W - 1) / W;
-  int threads = tune_threads > 0 ? tune_threads : 256;
+  const int threads = tune_threads > 0 ? tune_threads : 256;
   if (threads > kMaxThreads || threads < 32 || (threads & 31)) return PSOB200_ERR_INVALID_ARG;
   // cluster size: keep the fp32 residual slab <= 64 KB per CTA (>= 3 CTAs per SM) when possible,
   // and spread small batches over more SMs for latency.
@@ -313,7 +431,6 @@ static int launch_pair(PairKernelArgs ka, bool has_ref, int32_t pred_dtype, int3
     while (cluster < kMaxCluster && (ka.N + cluster - 1) / cluster > per_branch_cap) cluster <<= 1;
     while (cluster < kMaxCluster && ka.B * cluster < 2LL * sm_count && nchunk / (cluster * 2) >= threads) cluster <<= 1;
   }
-  if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) return PSOB200_ERR_INVALID_ARG;
   const long long cpc = (nchunk + cluster - 1) / cluster;
   if (cpc * W > hard_cap) return PSOB200_ERR_SHAPE;
   ka.chunks_per_cta = (int)cpc;
@@ -392,6 +509,9 @@ extern "C" int psob200_online_pso_loss_grad(const psob200_schedule* sched, const
   ka.pair_loss = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(p.workspace) + 16);
   ka.B = p.B; ka.N = p.N; ka.mode = kModeOnline;
   ka.beta = p.beta; ka.eps = p.eps; ka.loss_scale = p.loss_scale;
+  const double eps = (double)p.eps;
+  ka.log_lo = (1.0 - eps > 0.0) ? std::log(1.0 - eps) : -HUGE_VAL;  // exp(d) > 0 >= 1-eps: never clamped from below
+  ka.log_hi = std::log1p(eps);
   return launch_pair(ka, true, p.pred_dtype, p.latent_dtype, vec_ok, p.tune_threads, p.tune_cluster,
                      cached_sm_count(), reinterpret_cast<cudaStream_t>(stream));
 }

@@ -18,6 +18,7 @@ namespace psob200 {
 
 constexpr int kStepMaxThreads = 512;
 constexpr int kStepMaxCluster = 8;
+constexpr int kBatch = 4;  // chunks requested per thread before the first is consumed
 enum { kScore = 0, kSampleOutPred = 1, kSampleOutLatent = 2 };
 
 struct StepKernelArgs {
@@ -70,31 +71,50 @@ __global__ void __launch_bounds__(kStepMaxThreads) step_logprob_kernel(const Ste
 
   float acc = 0.f;
   if constexpr (W == 8) {
-#pragma unroll 2
-    for (long long c = cbeg + tid; c < cend; c += T) {
-      float ve[8], vx[8], vn[8];
-      Vec8<TP>::load(eps + c * 8, ve);
-      Vec8<TL>::load(x + c * 8, vx);
-      if constexpr (MODE == kScore) Vec8<TL>::load(xn + c * 8, vn);
-      else Vec8<TO>::load(noise + c * 8, vn);
-      float o[8], o2[8];
+    // kBatch chunks per thread are requested back to back (raw 128-bit registers) before any is
+    // decoded, so every thread keeps 3*kBatch independent 16-byte loads in flight
+    using TN = typename std::conditional<MODE == kScore, TL, TO>::type;
+    const TN* third = MODE == kScore ? reinterpret_cast<const TN*>(xn) : reinterpret_cast<const TN*>(noise);
+    for (long long c0 = cbeg + tid; c0 < cend; c0 += (long long)T * kBatch) {
+      typename Vec8<TP>::Raw re[kBatch];
+      typename Vec8<TL>::Raw rx[kBatch];
+      typename Vec8<TN>::Raw rn[kBatch];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float mu = fmaf(ca, ve[i], kx * vx[i]);
-        float r;
-        if constexpr (MODE == kScore) {
-          r = vn[i] - mu;
-        } else {
-          const float nx = fmaf(vn[i], sd, mu);  // TS:99 / DS:126
-          r = nx - mu;                           // TS:109 uses the fp32 prev_sample
-          o[i] = nx;
-          o2[i] = nx * nscale;
+      for (int u = 0; u < kBatch; ++u) {
+        const long long c = c0 + (long long)u * T;
+        if (c < cend) {
+          re[u] = Vec8<TP>::load_raw(eps + c * 8);
+          rx[u] = Vec8<TL>::load_raw(x + c * 8);
+          rn[u] = Vec8<TN>::load_raw(third + c * 8);
         }
-        acc = fmaf(r, r, acc);
       }
-      if constexpr (MODE != kScore) {
-        Vec8<TO>::store(prev_out + c * 8, o);
-        if (scaled_out != nullptr) Vec8<TO>::store(scaled_out + c * 8, o2);
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const long long c = c0 + (long long)u * T;
+        if (c < cend) {
+          float ve[8], vx[8], vn[8], o[8], o2[8];
+          Vec8<TP>::decode(re[u], ve);
+          Vec8<TL>::decode(rx[u], vx);
+          Vec8<TN>::decode(rn[u], vn);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float mu = fmaf(ca, ve[i], kx * vx[i]);
+            float r;
+            if constexpr (MODE == kScore) {
+              r = vn[i] - mu;
+            } else {
+              const float nx = fmaf(vn[i], sd, mu);  // TS:99 / DS:126
+              r = nx - mu;                           // TS:109 uses the fp32 prev_sample
+              o[i] = nx;
+              o2[i] = nx * nscale;
+            }
+            acc = fmaf(r, r, acc);
+          }
+          if constexpr (MODE != kScore) {
+            Vec8<TO>::store(prev_out + c * 8, o);
+            if (scaled_out != nullptr) Vec8<TO>::store(scaled_out + c * 8, o2);
+          }
+        }
       }
     }
   } else {
@@ -163,16 +183,35 @@ __global__ void __launch_bounds__(256) step_logprob_bwd_kernel(const StepBwdKern
   TP* out = reinterpret_cast<TP*>(a.grad_eps) + base;
   const long long nchunk = (a.N + W - 1) / W;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < nchunk; c += stride) {
-    if constexpr (W == 8) {
-      float ve[8], vx[8], vn[8], o[8];
-      Vec8<TP>::load(eps + c * 8, ve);
-      Vec8<TL>::load(x + c * 8, vx);
-      Vec8<TL>::load(xn + c * 8, vn);
+  if constexpr (W == 8) {
+    for (long long c0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; c0 < nchunk; c0 += stride * kBatch) {
+      typename Vec8<TP>::Raw re[kBatch];
+      typename Vec8<TL>::Raw rx[kBatch], rn[kBatch];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = g * (vn[i] - fmaf(ca, ve[i], kx * vx[i]));
-      Vec8<TP>::store(out + c * 8, o);
-    } else {
+      for (int u = 0; u < kBatch; ++u) {
+        const long long c = c0 + (long long)u * stride;
+        if (c < nchunk) {
+          re[u] = Vec8<TP>::load_raw(eps + c * 8);
+          rx[u] = Vec8<TL>::load_raw(x + c * 8);
+          rn[u] = Vec8<TL>::load_raw(xn + c * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const long long c = c0 + (long long)u * stride;
+        if (c < nchunk) {
+          float ve[8], vx[8], vn[8], o[8];
+          Vec8<TP>::decode(re[u], ve);
+          Vec8<TL>::decode(rx[u], vx);
+          Vec8<TL>::decode(rn[u], vn);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = g * (vn[i] - fmaf(ca, ve[i], kx * vx[i]));
+          Vec8<TP>::store(out + c * 8, o);
+        }
+      }
+    }
+  } else {
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < nchunk; c += stride) {
       const float mu = fmaf(ca, Vec8<TP>::load1(eps + c), kx * Vec8<TL>::load1(x + c));
       Vec8<TP>::store1(out + c, g * (Vec8<TL>::load1(xn + c) - mu));
     }
@@ -255,10 +294,7 @@ __global__ void __launch_bounds__(256) scale_inplace_dev_kernel(T* __restrict__ 
   }
 }
 
-static inline int check_launch() {
-  if (cudaGetLastError() != cudaSuccess) return PSOB200_ERR_LAUNCH;
-  return PSOB200_OK;
-}
+static inline int check_launch() { return consume_launch_error("elementwise kernel launch", cudaSuccess); }
 
 static inline unsigned elementwise_blocks(long long nchunk, long long rows) {
   long long per_row = (nchunk + 255) / 256;
@@ -289,11 +325,7 @@ static int launch_step(const StepKernelArgs& ka, bool vec_ok, int threads, int c
   else
     e = launch_cluster(step_logprob_kernel<TP, TL, MODE, 1>, dim3((unsigned)(ka.B * cluster)), dim3(threads), 0,
                        stream, (unsigned)cluster, ka);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    return PSOB200_ERR_LAUNCH;
-  }
-  return PSOB200_OK;
+  return consume_launch_error("launch step_logprob_kernel", e);
 }
 
 }  // namespace psob200
@@ -333,10 +365,10 @@ extern "C" int psob200_step_logprob(const psob200_schedule* sched, const psob200
   if (threads > kStepMaxThreads || threads < 32 || (threads & 31)) return PSOB200_ERR_INVALID_ARG;
   int cluster = p.tune_cluster;
   if (cluster <= 0) {
+    // Clusters are costly on B200 (measured: 4.9 TB/s at cluster size 1, 2.5 TB/s at 8 for this kernel), so a
+    // sample is split over a cluster only while there are fewer samples than SMs.
     cluster = 1;
-    // ~4 chunks per thread, more CTAs for small batches
-    while (cluster < kStepMaxCluster && nchunk / cluster > 4LL * threads) cluster <<= 1;
-    while (cluster < kStepMaxCluster && p.B * cluster < 2 * 148 && nchunk / (cluster * 2) >= threads) cluster <<= 1;
+    while (cluster < kStepMaxCluster && p.B * cluster < 148 && nchunk / (cluster * 2) >= threads) cluster <<= 1;
   }
   if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) return PSOB200_ERR_INVALID_ARG;
   StepKernelArgs ka = {};

@@ -55,5 +55,11 @@ def assert_rounded_equal(got, want64, dtype, max_mismatch_frac=0.01):
     exact = (g == w)
     frac = 1.0 - exact.float().mean().item()
     assert frac <= max_mismatch_frac, f"{frac:.4%} of elements differ from the correctly rounded value"
-    ulp = torch.maximum(w.abs(), torch.full_like(w, 1e-30)) * (2.0 ** (-7 if dtype == torch.bfloat16 else -10))
-    assert bool(((g - w).abs() <= ulp).all()), "an element is off by more than 1 ulp"
+    # spacing of representable values around w (fp16 subnormals have a fixed spacing of 2^-24)
+    ulp = w.abs() * (2.0 ** (-7 if dtype == torch.bfloat16 else -10))
+    ulp = torch.clamp(ulp, min=(2.0 ** -133 if dtype == torch.bfloat16 else 2.0 ** -24))
+    # where the residual cancels (|r| << |x'|, |x|, |eps|) the fp32 evaluation carries an ABSOLUTE error of a few
+    # fp32 ulps of the operands; grant that on top of the output rounding
+    slack = 4e-6 * w.abs().max()
+    bad = (g - w).abs() > ulp + slack
+    assert not bool(bad.any()), f"{int(bad.sum())} elements are off by more than 1 ulp (+fp32 cancellation slack)"

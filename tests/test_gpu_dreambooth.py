@@ -49,10 +49,10 @@ def test_dreambooth_config4_half_storage(pso, loss_type, pd, ld):
     mp, rp = d["model_pred"].to(U.DT[pd]), d["ref_pred"].to(U.DT[pd])
     nz, x0 = d["noisy"].to(U.DT[ld]), d["x0"].to(U.DT[ld])
     cf = olosses.dreambooth_closed_form(mp.double(), rp.double(), nz.double(), x0.double(), d["sigmas"], loss_type,
-                                        5.0, 0.1, 0.5)
+                                        5.0, 0.1, 0.3)
     mpc = U.cuda(mp).requires_grad_(True)
     loss, lw, ll, logits = pso.pso_db_loss(mpc, U.cuda(rp), U.cuda(nz), U.cuda(x0), U.cuda(d["sigmas"]),
-                                           loss_type=loss_type, beta_pso=5.0, neg_defactor=0.1, prior_loss_weight=0.5)
+                                           loss_type=loss_type, beta_pso=5.0, neg_defactor=0.1, prior_loss_weight=0.3)
     loss.backward()
     assert abs(loss.item() - cf["loss"].item()) <= 1e-5 * abs(cf["loss"].item())
     np.testing.assert_allclose(logits.cpu().numpy(), cf["logits"].numpy(), rtol=2e-5, atol=1e-8)

@@ -145,8 +145,9 @@ def test_timestep_not_in_schedule_is_reported(pso):
     pso.check_status()  # cleared
 
 
-@pytest.mark.parametrize("tune", [(128, 1), (256, 2), (512, 4), (256, 8), (64, 8)])
+@pytest.mark.parametrize("tune", [(128, 1), (256, 2), (512, 4), (256, 8), (64, 8), (0, 2), (0, 4), (0, 8)])
 def test_launch_geometries_agree(pso, tune):
+    """threads > 0: the general LDG kernel; threads == 0: the persistent TMA-ring kernel at a forced cluster size."""
     d = U.synth("turbo", 3, (4, 64, 64), 14)
     base = U.run_fused(pso, d)
     got = U.run_fused(pso, d, tune=tune)
@@ -183,3 +184,19 @@ def test_full_size_properties(pso):
     U.assert_rounded_equal(e0, cf["grads"][0], torch.bfloat16)
     # mean of the per-pair losses is the loss
     assert abs(s1[:, 7].double().mean().item() - l1.item()) < 1e-6
+
+
+@pytest.mark.parametrize("B", [1, 37, 300, 700])
+def test_persistent_clusters_cover_every_pair(pso, B):
+    """More pairs than co-resident clusters: every cluster loops over several pairs (the TMA ring runs ahead across
+    pairs); fewer: one cluster per pair.  Per-pair statistics must equal the fp64 oracle for every pair."""
+    d = U.synth("turbo", B, (4, 32, 32), 200 + B, 0.02, 5, torch.bfloat16, torch.bfloat16)
+    cf = U.oracle_fp64(d)
+    for tune in ((0, 0), (0, 1), (0, 8)):
+        loss, st, g0, g1 = U.run_fused(pso, d, tune=tune)
+        assert abs(loss.item() - cf["loss"].item()) <= 1e-5 * cf["loss"].item()
+        np.testing.assert_allclose(st[:, 4:6].T.cpu().numpy(), torch.stack(cf["delta"]).numpy(), rtol=2e-5, atol=1e-9)
+        np.testing.assert_allclose(st[:, 6].cpu().numpy(), cf["z"].numpy(), rtol=2e-5, atol=5e-7)  # z = beta*(d1-d0) in fp32
+        U.assert_rounded_equal(g0, cf["grads"][0], torch.bfloat16)
+        U.assert_rounded_equal(g1, cf["grads"][1], torch.bfloat16)
+    pso.check_status()

@@ -118,16 +118,18 @@ def test_unmodified_trainer_flow_matches_fused_and_oracle(pso, kind, pd, ld):
 
 
 class _ToyUNet(torch.nn.Module):
-    """Stand-in for the UNet call sites TP:126-132 / DP:117-122 (the UNet itself is out of scope)."""
+    """Stand-in for the UNet call sites TP:126-132 / DP:117-122 (the UNet itself is out of scope).  Purely
+    elementwise fp32 so that the GPU (under the pipelines' autocast region) and the CPU oracle agree to rounding."""
 
     def __init__(self):
         super().__init__()
         self.config = types.SimpleNamespace(in_channels=4)
-        self.conv = torch.nn.Conv2d(4, 4, 3, padding=1)
+        self.w = torch.nn.Parameter(torch.tensor([0.7, -0.4, 0.9, 0.3]).reshape(1, 4, 1, 1))
+        self.b = torch.nn.Parameter(torch.tensor([0.1, 0.0, -0.2, 0.05]).reshape(1, 4, 1, 1))
 
     def forward(self, x, t, encoder_hidden_states=None, added_cond_kwargs=None, return_dict=True):
         t = torch.as_tensor(t, device=x.device, dtype=torch.float32).reshape(-1, 1, 1, 1) / 1000.0
-        y = torch.tanh(self.conv(x.float())) * (1.0 + t)
+        y = torch.tanh(x.float() * self.w + self.b) * (1.0 + t)
         return (y,) if not return_dict else types.SimpleNamespace(sample=y)
 
 
