@@ -299,9 +299,51 @@ PSOB200_API int psob200_scale(const void* in, void* out, int64_t count, float sc
 PSOB200_API int psob200_scale_inplace_by_device_scalar(void* data, int64_t count, int32_t dtype,
                                                        const float* scale_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * LoRA projection GEMMs on the tcgen05 tensor cores (TMA-fed, accumulators in tensor memory).
+ *
+ *   D[M,N] = alpha * ( A1[M,K1] * B1[N,K1]^T  +  A2[M,K2] * B2[N,K2]^T ) + bias[N]
+ *
+ * replaces the three library GEMMs + scale + add that peft==0.11.1 `lora.Linear.forward` issues per
+ * wrapped projection (installed by `unet.add_adapter`, T:338-345, D:361-368, P:1319-1326) and their
+ * autograd backward (T:857).  All operands are 16-bit (`ab_dtype` = PSOB200_BF16 or PSOB200_F16),
+ * row-major with the reduction dimension contiguous ("K-major"), leading dimensions in elements and a
+ * multiple of 8, base pointers 16-byte aligned; M, N, K1, K2 are otherwise arbitrary (tails are
+ * zero-filled by the TMA unit).  K2 == 0 disables the second segment.
+ *
+ * a_reduction_major != 0: A1 is given as [K1, M] row-major (the output-row index contiguous), i.e. the
+ *   product A1^T-as-stored: used for the weight-gradient reductions dA = U^T X, dB = dY^T T where the
+ *   activations are only available token-major.  Requires K2 == 0.
+ * d / dt: row-major output [M,N] (leading dimension ldd) and / or its transpose [N,M] (lddt);
+ *   element type d_dtype.  accumulate != 0: fp32 outputs are accumulated with atomic adds (gradient
+ *   accumulation into .grad) and the reduction may be split over CTAs (split_k: 0 = heuristics).
+ * bias: optional [N] of bias_dtype.  tune_bn: tile width (multiple of 16, <= 256), 0 = heuristics.
+ */
+typedef struct psob200_gemm_args {
+  const void* a1;
+  const void* b1;
+  const void* a2;
+  const void* b2;
+  const void* bias;
+  void* d;
+  void* dt;
+  int64_t lda1, ldb1, lda2, ldb2, ldd, lddt;
+  int64_t M, N, K1, K2;
+  float alpha;
+  int32_t ab_dtype;
+  int32_t d_dtype;
+  int32_t bias_dtype;
+  int32_t a_reduction_major;
+  int32_t accumulate;
+  int32_t split_k;
+  int32_t tune_bn;
+} psob200_gemm_args;
+
+PSOB200_API int psob200_lora_gemm(const psob200_gemm_args* args, void* stream);
+
 /* sizeof() of the argument structs as compiled into the library, for FFI bindings to
  * verify their mirror of this header: which = 0 schedule, 1 online_pso_args,
- * 2 dreambooth_args, 3 step_args, 4 step_bwd_args.  Returns 0 for unknown ids. */
+ * 2 dreambooth_args, 3 step_args, 4 step_bwd_args, 5 gemm_args.  Returns 0 for unknown ids. */
 PSOB200_API size_t psob200_struct_size(int which);
 
 #ifdef __cplusplus

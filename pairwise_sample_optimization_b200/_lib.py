@@ -69,7 +69,16 @@ class StepBwdArgs(C.Structure):
                 ("latent_dtype", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32)]
 
 
-_STRUCTS = {0: Schedule, 1: OnlinePsoArgs, 2: DreamboothArgs, 3: StepArgs, 4: StepBwdArgs}
+class GemmArgs(C.Structure):
+    _fields_ = [("a1", _vp), ("b1", _vp), ("a2", _vp), ("b2", _vp), ("bias", _vp), ("d", _vp), ("dt", _vp),
+                ("lda1", C.c_int64), ("ldb1", C.c_int64), ("lda2", C.c_int64), ("ldb2", C.c_int64),
+                ("ldd", C.c_int64), ("lddt", C.c_int64), ("M", C.c_int64), ("N", C.c_int64), ("K1", C.c_int64),
+                ("K2", C.c_int64), ("alpha", C.c_float), ("ab_dtype", C.c_int32), ("d_dtype", C.c_int32),
+                ("bias_dtype", C.c_int32), ("a_reduction_major", C.c_int32), ("accumulate", C.c_int32),
+                ("split_k", C.c_int32), ("tune_bn", C.c_int32)]
+
+
+_STRUCTS = {0: Schedule, 1: OnlinePsoArgs, 2: DreamboothArgs, 3: StepArgs, 4: StepBwdArgs, 5: GemmArgs}
 
 # name -> (restype, argtypes): every symbol include/psob200.h declares
 SIGNATURES = {
@@ -85,6 +94,7 @@ SIGNATURES = {
     "psob200_step_logprob_backward": (C.c_int, [C.POINTER(Schedule), C.POINTER(StepBwdArgs), _vp]),
     "psob200_dmd_x0_from_noise": (C.c_int, [_fp, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64,
                                             C.c_int64, C.c_int32, C.c_int32, C.c_int32, _ip, _vp]),
+    "psob200_lora_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "psob200_scale": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, C.c_int32, C.c_int32, _vp]),
     "psob200_scale_inplace_by_device_scalar": (C.c_int, [_vp, C.c_int64, C.c_int32, _fp, _vp]),
 }

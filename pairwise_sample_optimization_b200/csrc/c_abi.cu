@@ -44,6 +44,7 @@ extern "C" size_t psob200_struct_size(int which) {
     case 2: return sizeof(psob200_dreambooth_args);
     case 3: return sizeof(psob200_step_args);
     case 4: return sizeof(psob200_step_bwd_args);
+    case 5: return sizeof(psob200_gemm_args);
     default: return 0;
   }
 }

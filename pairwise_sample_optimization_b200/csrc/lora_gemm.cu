@@ -1,0 +1,409 @@
+// LoRA projection GEMMs on the 5th-generation tensor cores (sm_100a): TMA-fed tcgen05.mma with the
+// accumulators in tensor memory.
+//
+// One persistent, warp-specialised kernel computes
+//
+//     D[M,N] = alpha * ( A1[M,K1] * B1[N,K1]^T  +  A2[M,K2] * B2[N,K2]^T ) + bias[N]
+//
+// The second K segment is what makes the LoRA-wrapped projection ONE tensor-core pass over the frozen
+// weight instead of the reference stack's three GEMMs + scale + add (peft lora.Linear.forward, reached from
+// train_online_pso_sdxl_turbo.py:338-345):   y = x W^T + b + (s x A^T) B^T   is   [x | T] [W | B]^T  with
+// T = s x A^T  a skinny first pass of the same kernel.  The backward uses the same two shapes
+// (dX = dY W + U A with U = s dY B) plus a split-M reduction with MN-major A operand for dA / dB.
+//
+// Warp roles (256 threads, 1 CTA per SM, grid = min(tiles, SMs), static round-robin tile schedule):
+//   warp 0      TMA producer: 128B-swizzled [128 x 64] A and [bn x 64] B boxes into a 4-stage ring (192 KB)
+//   warp 1      MMA issuer: one thread, 4 x tcgen05.mma (128 x bn x 16) per stage, tcgen05.commit frees the stage
+//   warp 2      tensor-memory allocator (512 columns = two accumulator buffers of <= 256 columns)
+//   warps 4-7   epilogue: tcgen05.ld 32x32b -> alpha, bias, convert -> global (also a transposed copy, or
+//               fp32 atomic accumulation for the split reductions); overlaps the next tile's MMAs.
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace psob200 {
+
+constexpr int kBM = 128;            // UMMA M: rows of an output tile
+constexpr int kBNMax = 256;         // widest UMMA N
+constexpr int kBK = 64;             // reduction elements per stage = one 128-byte swizzle span of a 16-bit type
+constexpr int kStages = 4;
+constexpr int kGemmThreads = 256;
+constexpr int kStageABytes = kBM * kBK * 2;      // 16 KB
+constexpr int kStageBBytes = kBNMax * kBK * 2;   // 32 KB
+constexpr int kGemmSmemBytes = kStages * (kStageABytes + kStageBBytes) + 1024;  // + slack for 1024 B alignment
+constexpr int kTmemCols = 512;
+
+struct GemmKernelParams {
+  long long M, N;         // output extent
+  int nk1, nk2;           // 64-wide k-blocks of the two segments
+  int bn;                 // tile width, multiple of 16, <= 256
+  int m_tiles, n_tiles, splits, kb_per_split;
+  void* d; long long ldd;     // row-major output (may be null)
+  void* dt; long long lddt;   // transposed output [N, M] (may be null)
+  const void* bias;
+  float alpha;
+  int d_dtype, bias_dtype, ab_format, a_mn, atomic;
+};
+
+template <typename T>
+__device__ __forceinline__ T cvt_out(float v);
+template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
+
+__device__ __forceinline__ float load_bias(const void* bias, int dt, long long n) {
+  if (dt == PSOB200_F32) return __ldg(reinterpret_cast<const float*>(bias) + n);
+  if (dt == PSOB200_BF16) return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(bias) + n));
+  return __half2float(__ldg(reinterpret_cast<const __half*>(bias) + n));
+}
+
+// One 32-column chunk of one accumulator row: v[j] belongs to (row, n0 + j).
+template <typename TD>
+__device__ __forceinline__ void store_chunk(const GemmKernelParams& p, const float (&v)[32], long long row, long long n0) {
+  const bool row_ok = row < p.M;
+  const long long nleft = p.N - n0;  // columns of this chunk that exist
+  if (p.d != nullptr && row_ok) {
+    TD* dst = reinterpret_cast<TD*>(p.d) + row * p.ldd + n0;
+    if (p.atomic) {
+      if constexpr (sizeof(TD) == 4) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nleft) atomicAdd(reinterpret_cast<float*>(dst) + j, v[j]);
+      }
+    } else if (nleft >= 32 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+      if constexpr (sizeof(TD) == 4) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const float o[8] = {v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]};
+          Vec8<TD>::store(dst + j, o);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nleft) dst[j] = cvt_out<TD>(v[j]);
+    }
+  }
+  if (p.dt != nullptr && row_ok) {  // lanes hold consecutive rows: every column is a coalesced store
+    TD* dst = reinterpret_cast<TD*>(p.dt) + n0 * p.lddt + row;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < nleft) {
+        if (p.atomic) {
+          if constexpr (sizeof(TD) == 4) atomicAdd(reinterpret_cast<float*>(dst) + (long long)j * p.lddt, v[j]);
+        } else {
+          dst[(long long)j * p.lddt] = cvt_out<TD>(v[j]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
+                 const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
+                 const GemmKernelParams p) {
+  extern __shared__ unsigned char gemm_smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + kStages * kStageABytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = p.nk1 + p.nk2;
+  const long long total_tiles = (long long)p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a1);
+    ptx::prefetch_tensormap(&map_b1);
+    if (p.nk2 > 0) {
+      ptx::prefetch_tensormap(&map_a2);
+      ptx::prefetch_tensormap(&map_b2);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);   // producer's arrive.expect_tx; TMA completes the bytes
+      ptx::mbar_init(&empty_bar[s], 1);  // tcgen05.commit
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);   // tcgen05.commit after the tile's last MMA
+      ptx::mbar_init(&tmem_empty_bar[a], 4);  // one arrival per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kTmemCols>(&tmem_base_slot);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  auto tile_coords = [&](long long t, int& m_blk, int& n_blk, int& kb0, int& kb1) {
+    n_blk = (int)(t % p.n_tiles);
+    t /= p.n_tiles;
+    m_blk = (int)(t % p.m_tiles);
+    const int split = (int)(t / p.m_tiles);
+    kb0 = split * p.kb_per_split;
+    kb1 = kb0 + p.kb_per_split < nk ? kb0 + p.kb_per_split : nk;
+  };
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)kStageABytes + (uint32_t)p.bn * kBK * 2u;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m_blk, n_blk, kb0, kb1;
+        tile_coords(t, m_blk, n_blk, kb0, kb1);
+        const int m0 = m_blk * kBM, n0 = n_blk * p.bn;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          const bool seg2 = kb >= p.nk1;
+          const CUtensorMap* ma = seg2 ? &map_a2 : &map_a1;
+          const CUtensorMap* mb = seg2 ? &map_b2 : &map_b1;
+          const int kk = (seg2 ? kb - p.nk1 : kb) * kBK;
+          unsigned char* sa = smem_a + stage * kStageABytes;
+          unsigned char* sb = smem_b + stage * kStageBBytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], tx);
+          if (p.a_mn) {  // A given reduction-major: two [64 k x 64 m] boxes, m contiguous
+            ptx::tma_load_2d(sa, ma, m0, kk, &full_bar[stage]);
+            ptx::tma_load_2d(sa + kStageABytes / 2, ma, m0 + 64, kk, &full_bar[stage]);
+          } else {
+            ptx::tma_load_2d(sa, ma, kk, m0, &full_bar[stage]);
+          }
+          ptx::tma_load_2d(sb, mb, kk, n0, &full_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16((uint32_t)p.ab_format, (uint32_t)p.a_mn, 0u, (uint32_t)p.bn);
+      int stage = 0;
+      uint32_t phase = 0;
+      long long iter = 0;
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+        int m_blk, n_blk, kb0, kb1;
+        tile_coords(t, m_blk, n_blk, kb0, kb1);
+        const int acc = (int)(iter & 1);
+        const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kBNMax;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_base = ptx::smem_addr(smem_a + stage * kStageABytes);
+          const uint32_t b_base = ptx::smem_addr(smem_b + stage * kStageBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // K-major, 128B swizzle: 8-row atoms 1024 B apart, a 16-element k step is 32 B inside the span.
+            // MN-major A: 64(mn) x 8(k) atoms; 1024 B between k atoms, 64 k-rows * 128 B between mn atoms.
+            const uint64_t a_desc = p.a_mn ? ptx::smem_desc_sw128(a_base + k * 2048, kBK * 128, 1024)
+                                           : ptx::smem_desc_sw128(a_base + k * 32, 0, 1024);
+            const uint64_t b_desc = ptx::smem_desc_sw128(b_base + k * 32, 0, 1024);
+            ptx::umma_f16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);                         // stage reusable once these MMAs retire
+          if (kb == kb1 - 1) ptx::umma_commit(&tmem_full_bar[acc]);    // accumulator complete
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================================================= epilogue (TMEM lanes 32*(warp%4) ..)
+    const int ew = warp - 4;
+    long long iter = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+      int m_blk, n_blk, kb0, kb1;
+      tile_coords(t, m_blk, n_blk, kb0, kb1);
+      const int acc = (int)(iter & 1);
+      const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
+      const long long row = (long long)m_blk * kBM + ew * 32 + lane;
+      const long long n_tile0 = (long long)n_blk * p.bn;
+      const bool add_bias = p.bias != nullptr && kb0 == 0;
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kBNMax;
+      const int chunks = (p.bn + 31) / 32;
+      for (int c = 0; c < chunks; ++c) {
+        const long long n0 = n_tile0 + c * 32;
+        if (n0 >= p.N) break;  // uniform over the warp
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(taddr + (uint32_t)c * 32, raw);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = p.alpha * __uint_as_float(raw[j]);
+          if (add_bias && n0 + j < p.N) v[j] += load_bias(p.bias, p.bias_dtype, n0 + j);
+        }
+        if (p.d_dtype == PSOB200_F32) store_chunk<float>(p, v, row, n0);
+        else if (p.d_dtype == PSOB200_BF16) store_chunk<__nv_bfloat16>(p, v, row, n0);
+        else store_chunk<__half>(p, v, row, n0);
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static std::once_flag once;
+  static EncodeTiledFn fn = nullptr;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+// Tensor map of a row-major [rows, cols] 16-bit matrix with leading dimension ld (elements); box = 64 contiguous
+// elements x box_rows rows, 128-byte swizzle, out-of-bounds elements read as zero.
+static int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
+                    int ab_dtype) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return PSOB200_ERR_DRIVER;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2u};
+  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, ab_dtype == PSOB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                        const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PSOB200_OK : PSOB200_ERR_DRIVER;
+}
+
+static int gemm_sm_count() {
+  static std::atomic<int> cached{0};
+  int v = cached.load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 148;
+  }
+  cached.store(n, std::memory_order_relaxed);
+  return n;
+}
+
+static int choose_bn(long long N) {
+  if (N >= 256) {
+    // widest tile that wastes the fewest columns: 256, or 128-wide tiles when that divides N better
+    const long long w256 = ((N + 255) / 256) * 256 - N, w128 = ((N + 127) / 128) * 128 - N;
+    return w128 < w256 ? 128 : 256;
+  }
+  return (int)(((N + 15) / 16) * 16);
+}
+
+}  // namespace psob200
+
+using namespace psob200;
+
+extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
+  if (args == nullptr) return PSOB200_ERR_INVALID_ARG;
+  const psob200_gemm_args& g = *args;
+  if (g.M <= 0 || g.N <= 0 || g.K1 <= 0 || g.K2 < 0 || !g.a1 || !g.b1 || (!g.d && !g.dt)) return PSOB200_ERR_INVALID_ARG;
+  if (g.K2 > 0 && (!g.a2 || !g.b2)) return PSOB200_ERR_INVALID_ARG;
+  if (g.ab_dtype != PSOB200_BF16 && g.ab_dtype != PSOB200_F16) return PSOB200_ERR_DTYPE;
+  if (!valid_dtype(g.d_dtype) || (g.bias && !valid_dtype(g.bias_dtype))) return PSOB200_ERR_DTYPE;
+  if (g.accumulate && g.d_dtype != PSOB200_F32) return PSOB200_ERR_DTYPE;
+  if (g.a_reduction_major && g.K2 > 0) return PSOB200_ERR_INVALID_ARG;
+  if (g.split_k < 0 || (g.split_k > 1 && !g.accumulate)) return PSOB200_ERR_INVALID_ARG;
+  const void* ptrs[4] = {g.a1, g.b1, g.a2, g.b2};
+  const long long lds[4] = {g.lda1, g.ldb1, g.lda2, g.ldb2};
+  for (int i = 0; i < (g.K2 > 0 ? 4 : 2); ++i) {
+    if (!aligned16(ptrs[i])) return PSOB200_ERR_ALIGNMENT;
+    if (lds[i] <= 0 || (lds[i] % 8) != 0) return PSOB200_ERR_SHAPE;  // TMA: row pitch is a multiple of 16 bytes
+  }
+  if ((g.d && g.ldd < g.N) || (g.dt && g.lddt < g.M)) return PSOB200_ERR_SHAPE;
+  if (g.M > 0x7fffffffLL - 256 || g.N > 0x7fffffffLL - 256 || g.K1 > 0x7fffffffLL - 256 || g.K2 > 0x7fffffffLL - 256)
+    return PSOB200_ERR_SHAPE;
+
+  GemmKernelParams p = {};
+  p.M = g.M; p.N = g.N;
+  p.nk1 = (int)((g.K1 + kBK - 1) / kBK);
+  p.nk2 = (int)((g.K2 + kBK - 1) / kBK);
+  p.bn = g.tune_bn > 0 ? g.tune_bn : choose_bn(g.N);
+  if (p.bn < 16 || p.bn > kBNMax || (p.bn % 16) != 0) return PSOB200_ERR_INVALID_ARG;
+  p.m_tiles = (int)((g.M + kBM - 1) / kBM);
+  p.n_tiles = (int)((g.N + p.bn - 1) / p.bn);
+  const int nk = p.nk1 + p.nk2;
+  const int sms = gemm_sm_count();
+  int splits = g.split_k;
+  if (splits == 0) {  // heuristics: split the reduction only for accumulating launches that cannot fill the GPU
+    splits = 1;
+    if (g.accumulate) {
+      const long long tiles = (long long)p.m_tiles * p.n_tiles;
+      splits = (int)((sms + tiles - 1) / tiles);
+      if (splits > nk) splits = nk;
+      if (splits < 1) splits = 1;
+    }
+  }
+  if (splits > nk) splits = nk;
+  p.kb_per_split = (nk + splits - 1) / splits;
+  p.splits = (nk + p.kb_per_split - 1) / p.kb_per_split;
+  p.d = g.d; p.ldd = g.ldd; p.dt = g.dt; p.lddt = g.lddt; p.bias = g.bias;
+  p.alpha = g.alpha; p.d_dtype = g.d_dtype; p.bias_dtype = g.bias_dtype;
+  p.ab_format = g.ab_dtype == PSOB200_BF16 ? 1 : 0;
+  p.a_mn = g.a_reduction_major ? 1 : 0;
+  p.atomic = g.accumulate ? 1 : 0;
+
+  CUtensorMap ma1, mb1, ma2, mb2;
+  int rc;
+  if (p.a_mn) rc = make_map(&ma1, g.a1, g.K1, g.M, g.lda1, kBK, g.ab_dtype);  // [K, M] row-major: box 64(m) x 64(k)
+  else rc = make_map(&ma1, g.a1, g.M, g.K1, g.lda1, kBM, g.ab_dtype);
+  if (rc != PSOB200_OK) return rc;
+  if ((rc = make_map(&mb1, g.b1, g.N, g.K1, g.ldb1, p.bn, g.ab_dtype)) != PSOB200_OK) return rc;
+  if (g.K2 > 0) {
+    if ((rc = make_map(&ma2, g.a2, g.M, g.K2, g.lda2, kBM, g.ab_dtype)) != PSOB200_OK) return rc;
+    if ((rc = make_map(&mb2, g.b2, g.N, g.K2, g.ldb2, p.bn, g.ab_dtype)) != PSOB200_OK) return rc;
+  } else {
+    ma2 = ma1;
+    mb2 = mb1;
+  }
+
+  static std::atomic<bool> configured{false};
+  if (!configured.load(std::memory_order_acquire)) {
+    const cudaError_t e = cudaFuncSetAttribute(lora_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    if (e != cudaSuccess) return consume_launch_error("configure lora_gemm_kernel", e);
+    configured.store(true, std::memory_order_release);
+  }
+  const long long total = (long long)p.m_tiles * p.n_tiles * p.splits;
+  const unsigned grid = (unsigned)(total < sms ? total : sms);
+  lora_gemm_kernel<<<grid, kGemmThreads, kGemmSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(ma1, mb1, ma2, mb2, p);
+  return consume_launch_error("launch lora_gemm_kernel", cudaSuccess);
+}
