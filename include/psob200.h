@@ -314,6 +314,9 @@ PSOB200_API int psob200_scale_inplace_by_device_scalar(void* data, int64_t count
  * a_reduction_major != 0: A1 is given as [K1, M] row-major (the output-row index contiguous), i.e. the
  *   product A1^T-as-stored: used for the weight-gradient reductions dA = U^T X, dB = dY^T T where the
  *   activations are only available token-major.  Requires K2 == 0.
+ * b_reduction_major != 0: B1 (and B2) are given as [K, N] row-major (the output-column index contiguous):
+ *   lets the backward dX = dY W + U A and U = s dY B consume W [N_out,K_in], lora_A [r,K] and lora_B [N,r]
+ *   in the layout the reference stores them, with no transposed copies.
  * d / dt: row-major output [M,N] (leading dimension ldd) and / or its transpose [N,M] (lddt);
  *   element type d_dtype.  accumulate != 0: fp32 outputs are accumulated with atomic adds (gradient
  *   accumulation into .grad) and the reduction may be split over CTAs (split_k: 0 = heuristics).
@@ -334,6 +337,7 @@ typedef struct psob200_gemm_args {
   int32_t d_dtype;
   int32_t bias_dtype;
   int32_t a_reduction_major;
+  int32_t b_reduction_major;
   int32_t accumulate;
   int32_t split_k;
   int32_t tune_bn;
@@ -341,9 +345,53 @@ typedef struct psob200_gemm_args {
 
 PSOB200_API int psob200_lora_gemm(const psob200_gemm_args* args, void* stream);
 
+/*
+ * The LoRA-wrapped projection as the reference's stack runs it (peft==0.11.1 lora.Linear, created by
+ * unet.add_adapter at T:338-345 / D:361-368 / P:1319-1326 on to_q, to_k, to_v, to_out.0), forward and backward,
+ * each a short sequence of psob200_lora_gemm launches on `stream`:
+ *
+ *   forward   t  = scaling * x A^T               [M,r]  (skinny pass; also tt = t^T when tt != NULL)
+ *             y  = x W^T + bias + t B^T          [M,N]  (ONE pass over W: second K segment = the adapter)
+ *             adapters_enabled == 0 (disable_adapters(), T:790): y = x W^T + bias only
+ *   backward  u  = scaling * dy B                [M,r]  (+ ut = u^T)
+ *             dx = dy W + u A                    [M,K]  (skipped when dx == NULL)
+ *             dA += u^T x  [r,K]   dB += dy^T t  [N,r]  (fp32, accumulated: gradient accumulation T:232)
+ *
+ * x [M,K], w [N,K], lora_a [r,K], lora_b [N,r], dy [M,N] are 16-bit (`dtype`), in the layouts the reference keeps
+ * them (nn.Linear weight [out,in]); no transposed copies are needed.  Leading dimensions are in elements,
+ * multiples of 8 (so lora_b, t, u are stored with ld >= r rounded up to 8).  t/tt (forward) and u/ut (backward)
+ * are caller-provided scratch; tt must be kept for the backward.  r <= 256.
+ */
+typedef struct psob200_lora_linear_args {
+  const void* x;
+  const void* w;
+  const void* bias; /* [N] of bias_dtype, may be NULL */
+  const void* lora_a;
+  const void* lora_b;
+  void* y;
+  void* t;
+  void* tt;
+  const void* dy;
+  void* dx;
+  void* u;
+  void* ut;
+  float* d_lora_a; /* [r, ld_da] fp32, accumulated into; may be NULL */
+  float* d_lora_b; /* [N, ld_db] fp32, accumulated into; may be NULL */
+  int64_t ldx, ldw, lda, ldb, ldy, ldt, ldtt, lddy, lddx, ldu, ldut, ld_da, ld_db;
+  int64_t M, K, N, r;
+  float scaling;
+  int32_t dtype;
+  int32_t bias_dtype;
+  int32_t adapters_enabled;
+} psob200_lora_linear_args;
+
+PSOB200_API int psob200_lora_linear_forward(const psob200_lora_linear_args* args, void* stream);
+PSOB200_API int psob200_lora_linear_backward(const psob200_lora_linear_args* args, void* stream);
+
 /* sizeof() of the argument structs as compiled into the library, for FFI bindings to
  * verify their mirror of this header: which = 0 schedule, 1 online_pso_args,
- * 2 dreambooth_args, 3 step_args, 4 step_bwd_args, 5 gemm_args.  Returns 0 for unknown ids. */
+ * 2 dreambooth_args, 3 step_args, 4 step_bwd_args, 5 gemm_args,
+ * 6 lora_linear_args.  Returns 0 for unknown ids. */
 PSOB200_API size_t psob200_struct_size(int which);
 
 #ifdef __cplusplus

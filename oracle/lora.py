@@ -78,3 +78,23 @@ def attention_forward(hidden_states, encoder_hidden_states, proj, heads: int, re
     if residual_connection:
         o = o + residual
     return o / rescale_output_factor
+
+
+def lora_linear_rounded_flow(x, weight, bias, lora_A, lora_B, grad_y, scaling: float = 1.0, dtype=torch.bfloat16):
+    """The same forward/backward with the 16-bit ROUNDING POINTS of a half-precision run made explicit (fp64 math
+    in between): peft in bf16 materialises ``lora_A(x)`` in bf16 and autograd materialises ``grad @ lora_B`` in
+    bf16; outputs y / dX are 16-bit, the adapter gradients are accumulated in fp32.  This is what the tcgen05 path
+    is compared with: it must agree to 1 ulp of ``dtype`` on y, dX and to fp32 round-off on dA, dB."""
+    rd = lambda t: t.to(dtype).double()
+    x2 = x.double().reshape(-1, x.shape[-1])
+    g2 = grad_y.double().reshape(-1, grad_y.shape[-1])
+    W, A, Bm = weight.double(), rd(lora_A), rd(lora_B)
+    T = rd(scaling * (x2 @ A.t()))
+    y = x2 @ W.t() + T @ Bm.t()
+    if bias is not None:
+        y = y + bias.double()
+    U = rd(scaling * (g2 @ Bm))
+    dX = g2 @ W + U @ A
+    dA = U.t() @ x2
+    dB = g2.t() @ T
+    return {"y": y.reshape(*x.shape[:-1], -1), "dX": dX.reshape(x.shape), "dA": dA, "dB": dB, "T": T, "U": U}

@@ -74,11 +74,23 @@ class GemmArgs(C.Structure):
                 ("lda1", C.c_int64), ("ldb1", C.c_int64), ("lda2", C.c_int64), ("ldb2", C.c_int64),
                 ("ldd", C.c_int64), ("lddt", C.c_int64), ("M", C.c_int64), ("N", C.c_int64), ("K1", C.c_int64),
                 ("K2", C.c_int64), ("alpha", C.c_float), ("ab_dtype", C.c_int32), ("d_dtype", C.c_int32),
-                ("bias_dtype", C.c_int32), ("a_reduction_major", C.c_int32), ("accumulate", C.c_int32),
+                ("bias_dtype", C.c_int32), ("a_reduction_major", C.c_int32), ("b_reduction_major", C.c_int32),
+                ("accumulate", C.c_int32),
                 ("split_k", C.c_int32), ("tune_bn", C.c_int32)]
 
 
-_STRUCTS = {0: Schedule, 1: OnlinePsoArgs, 2: DreamboothArgs, 3: StepArgs, 4: StepBwdArgs, 5: GemmArgs}
+class LoraLinearArgs(C.Structure):
+    _fields_ = [("x", _vp), ("w", _vp), ("bias", _vp), ("lora_a", _vp), ("lora_b", _vp), ("y", _vp), ("t", _vp),
+                ("tt", _vp), ("dy", _vp), ("dx", _vp), ("u", _vp), ("ut", _vp), ("d_lora_a", _fp), ("d_lora_b", _fp),
+                ("ldx", C.c_int64), ("ldw", C.c_int64), ("lda", C.c_int64), ("ldb", C.c_int64), ("ldy", C.c_int64),
+                ("ldt", C.c_int64), ("ldtt", C.c_int64), ("lddy", C.c_int64), ("lddx", C.c_int64),
+                ("ldu", C.c_int64), ("ldut", C.c_int64), ("ld_da", C.c_int64), ("ld_db", C.c_int64),
+                ("M", C.c_int64), ("K", C.c_int64), ("N", C.c_int64), ("r", C.c_int64), ("scaling", C.c_float),
+                ("dtype", C.c_int32), ("bias_dtype", C.c_int32), ("adapters_enabled", C.c_int32)]
+
+
+_STRUCTS = {0: Schedule, 1: OnlinePsoArgs, 2: DreamboothArgs, 3: StepArgs, 4: StepBwdArgs, 5: GemmArgs,
+            6: LoraLinearArgs}
 
 # name -> (restype, argtypes): every symbol include/psob200.h declares
 SIGNATURES = {
@@ -95,6 +107,8 @@ SIGNATURES = {
     "psob200_dmd_x0_from_noise": (C.c_int, [_fp, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64,
                                             C.c_int64, C.c_int32, C.c_int32, C.c_int32, _ip, _vp]),
     "psob200_lora_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "psob200_lora_linear_forward": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
+    "psob200_lora_linear_backward": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
     "psob200_scale": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, C.c_int32, C.c_int32, _vp]),
     "psob200_scale_inplace_by_device_scalar": (C.c_int, [_vp, C.c_int64, C.c_int32, _fp, _vp]),
 }

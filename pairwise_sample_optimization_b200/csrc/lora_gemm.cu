@@ -44,7 +44,7 @@ struct GemmKernelParams {
   void* dt; long long lddt;   // transposed output [N, M] (may be null)
   const void* bias;
   float alpha;
-  int d_dtype, bias_dtype, ab_format, a_mn, atomic;
+  int d_dtype, bias_dtype, ab_format, a_mn, b_mn, atomic;
 };
 
 template <typename T>
@@ -182,7 +182,12 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
           } else {
             ptx::tma_load_2d(sa, ma, kk, m0, &full_bar[stage]);
           }
-          ptx::tma_load_2d(sb, mb, kk, n0, &full_bar[stage]);
+          if (p.b_mn) {  // B given reduction-major: bn/64 boxes of [64 k x 64 n], n contiguous
+            for (int j = 0; j < p.bn / 64; ++j)
+              ptx::tma_load_2d(sb + j * (kBK * 128), mb, n0 + 64 * j, kk, &full_bar[stage]);
+          } else {
+            ptx::tma_load_2d(sb, mb, kk, n0, &full_bar[stage]);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -191,7 +196,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
   } else if (warp == 1) {
     // ================================================================= MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_f16((uint32_t)p.ab_format, (uint32_t)p.a_mn, 0u, (uint32_t)p.bn);
+      const uint32_t idesc = ptx::umma_idesc_f16((uint32_t)p.ab_format, (uint32_t)p.a_mn, (uint32_t)p.b_mn, (uint32_t)p.bn);
       int stage = 0;
       uint32_t phase = 0;
       long long iter = 0;
@@ -211,10 +216,12 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // K-major, 128B swizzle: 8-row atoms 1024 B apart, a 16-element k step is 32 B inside the span.
-            // MN-major A: 64(mn) x 8(k) atoms; 1024 B between k atoms, 64 k-rows * 128 B between mn atoms.
+            // MN-major (reduction-major) operand: 64(mn) x 8(k) atoms; 1024 B between k atoms, 64 k-rows * 128 B
+            // between mn atoms.
             const uint64_t a_desc = p.a_mn ? ptx::smem_desc_sw128(a_base + k * 2048, kBK * 128, 1024)
                                            : ptx::smem_desc_sw128(a_base + k * 32, 0, 1024);
-            const uint64_t b_desc = ptx::smem_desc_sw128(b_base + k * 32, 0, 1024);
+            const uint64_t b_desc = p.b_mn ? ptx::smem_desc_sw128(b_base + k * 2048, kBK * 128, 1024)
+                                           : ptx::smem_desc_sw128(b_base + k * 32, 0, 1024);
             ptx::umma_f16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[stage]);                         // stage reusable once these MMAs retire
@@ -320,7 +327,8 @@ static int gemm_sm_count() {
   return n;
 }
 
-static int choose_bn(long long N) {
+static int choose_bn(long long N, bool b_mn) {
+  if (b_mn && N < 256) return (int)(((N + 63) / 64) * 64);  // reduction-major B: whole 64-column boxes
   if (N >= 256) {
     // widest tile that wastes the fewest columns: 256, or 128-wide tiles when that divides N better
     const long long w256 = ((N + 255) / 256) * 256 - N, w128 = ((N + 127) / 128) * 128 - N;
@@ -357,8 +365,8 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
   p.M = g.M; p.N = g.N;
   p.nk1 = (int)((g.K1 + kBK - 1) / kBK);
   p.nk2 = (int)((g.K2 + kBK - 1) / kBK);
-  p.bn = g.tune_bn > 0 ? g.tune_bn : choose_bn(g.N);
-  if (p.bn < 16 || p.bn > kBNMax || (p.bn % 16) != 0) return PSOB200_ERR_INVALID_ARG;
+  p.bn = g.tune_bn > 0 ? g.tune_bn : choose_bn(g.N, g.b_reduction_major != 0);
+  if (p.bn < 16 || p.bn > kBNMax || (p.bn % (g.b_reduction_major ? 64 : 16)) != 0) return PSOB200_ERR_INVALID_ARG;
   p.m_tiles = (int)((g.M + kBM - 1) / kBM);
   p.n_tiles = (int)((g.N + p.bn - 1) / p.bn);
   const int nk = p.nk1 + p.nk2;
@@ -380,6 +388,7 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
   p.alpha = g.alpha; p.d_dtype = g.d_dtype; p.bias_dtype = g.bias_dtype;
   p.ab_format = g.ab_dtype == PSOB200_BF16 ? 1 : 0;
   p.a_mn = g.a_reduction_major ? 1 : 0;
+  p.b_mn = g.b_reduction_major ? 1 : 0;
   p.atomic = g.accumulate ? 1 : 0;
 
   CUtensorMap ma1, mb1, ma2, mb2;
@@ -387,10 +396,14 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
   if (p.a_mn) rc = make_map(&ma1, g.a1, g.K1, g.M, g.lda1, kBK, g.ab_dtype);  // [K, M] row-major: box 64(m) x 64(k)
   else rc = make_map(&ma1, g.a1, g.M, g.K1, g.lda1, kBM, g.ab_dtype);
   if (rc != PSOB200_OK) return rc;
-  if ((rc = make_map(&mb1, g.b1, g.N, g.K1, g.ldb1, p.bn, g.ab_dtype)) != PSOB200_OK) return rc;
+  if (p.b_mn) rc = make_map(&mb1, g.b1, g.K1, g.N, g.ldb1, kBK, g.ab_dtype);  // [K, N] row-major
+  else rc = make_map(&mb1, g.b1, g.N, g.K1, g.ldb1, p.bn, g.ab_dtype);
+  if (rc != PSOB200_OK) return rc;
   if (g.K2 > 0) {
     if ((rc = make_map(&ma2, g.a2, g.M, g.K2, g.lda2, kBM, g.ab_dtype)) != PSOB200_OK) return rc;
-    if ((rc = make_map(&mb2, g.b2, g.N, g.K2, g.ldb2, p.bn, g.ab_dtype)) != PSOB200_OK) return rc;
+    if (p.b_mn) rc = make_map(&mb2, g.b2, g.K2, g.N, g.ldb2, kBK, g.ab_dtype);
+    else rc = make_map(&mb2, g.b2, g.N, g.K2, g.ldb2, p.bn, g.ab_dtype);
+    if (rc != PSOB200_OK) return rc;
   } else {
     ma2 = ma1;
     mb2 = mb1;
@@ -406,4 +419,80 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
   const unsigned grid = (unsigned)(total < sms ? total : sms);
   lora_gemm_kernel<<<grid, kGemmThreads, kGemmSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(ma1, mb1, ma2, mb2, p);
   return consume_launch_error("launch lora_gemm_kernel", cudaSuccess);
+}
+
+// ---------------------------------------------------------------------------------------------- LoRA-wrapped Linear
+static psob200_gemm_args gemm_defaults(int32_t dtype) {
+  psob200_gemm_args g = {};
+  g.alpha = 1.0f;
+  g.ab_dtype = dtype;
+  g.d_dtype = dtype;
+  return g;
+}
+
+extern "C" int psob200_lora_linear_forward(const psob200_lora_linear_args* args, void* stream) {
+  if (args == nullptr) return PSOB200_ERR_INVALID_ARG;
+  const psob200_lora_linear_args& a = *args;
+  if (!a.x || !a.w || !a.y || a.M <= 0 || a.K <= 0 || a.N <= 0) return PSOB200_ERR_INVALID_ARG;
+  const bool lora = a.adapters_enabled != 0;
+  if (lora && (!a.lora_a || !a.lora_b || !a.t || a.r <= 0 || a.r > kBNMax)) return PSOB200_ERR_INVALID_ARG;
+  int rc;
+  if (lora) {  // t = scaling * x A^T  (+ its transpose, the K-major operand of the dB reduction)
+    psob200_gemm_args g = gemm_defaults(a.dtype);
+    g.a1 = a.x; g.lda1 = a.ldx; g.b1 = a.lora_a; g.ldb1 = a.lda;
+    g.M = a.M; g.N = a.r; g.K1 = a.K;
+    g.alpha = a.scaling;
+    g.d = a.t; g.ldd = a.ldt; g.dt = a.tt; g.lddt = a.ldtt;
+    if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
+  }
+  psob200_gemm_args g = gemm_defaults(a.dtype);
+  g.a1 = a.x; g.lda1 = a.ldx; g.b1 = a.w; g.ldb1 = a.ldw;
+  g.M = a.M; g.N = a.N; g.K1 = a.K;
+  if (lora) { g.a2 = a.t; g.lda2 = a.ldt; g.b2 = a.lora_b; g.ldb2 = a.ldb; g.K2 = a.r; }
+  g.bias = a.bias; g.bias_dtype = a.bias_dtype;
+  g.d = a.y; g.ldd = a.ldy;
+  return psob200_lora_gemm(&g, stream);
+}
+
+extern "C" int psob200_lora_linear_backward(const psob200_lora_linear_args* args, void* stream) {
+  if (args == nullptr) return PSOB200_ERR_INVALID_ARG;
+  const psob200_lora_linear_args& a = *args;
+  if (!a.dy || !a.w || a.M <= 0 || a.K <= 0 || a.N <= 0) return PSOB200_ERR_INVALID_ARG;
+  const bool lora = a.adapters_enabled != 0;
+  if (lora && (!a.lora_a || !a.lora_b || !a.u || a.r <= 0 || a.r > kBNMax)) return PSOB200_ERR_INVALID_ARG;
+  if (lora && a.d_lora_a && (!a.ut || !a.x)) return PSOB200_ERR_INVALID_ARG;
+  if (lora && a.d_lora_b && !a.tt) return PSOB200_ERR_INVALID_ARG;
+  int rc;
+  const bool need_u = lora && (a.dx != nullptr || a.d_lora_a != nullptr);
+  if (need_u) {  // u = scaling * dy B   (B [N,r] consumed reduction-major: no transposed copy)
+    psob200_gemm_args g = gemm_defaults(a.dtype);
+    g.a1 = a.dy; g.lda1 = a.lddy; g.b1 = a.lora_b; g.ldb1 = a.ldb; g.b_reduction_major = 1;
+    g.M = a.M; g.N = a.r; g.K1 = a.N;
+    g.alpha = a.scaling;
+    g.d = a.u; g.ldd = a.ldu; g.dt = a.d_lora_a ? a.ut : nullptr; g.lddt = a.ldut;
+    if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
+  }
+  if (a.dx != nullptr) {  // dx = dy W + u A   (W [N,K], A [r,K] reduction-major)
+    psob200_gemm_args g = gemm_defaults(a.dtype);
+    g.a1 = a.dy; g.lda1 = a.lddy; g.b1 = a.w; g.ldb1 = a.ldw; g.b_reduction_major = 1;
+    g.M = a.M; g.N = a.K; g.K1 = a.N;
+    if (lora) { g.a2 = a.u; g.lda2 = a.ldu; g.b2 = a.lora_a; g.ldb2 = a.lda; g.K2 = a.r; }
+    g.d = a.dx; g.ldd = a.lddx;
+    if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
+  }
+  if (lora && a.d_lora_a != nullptr) {  // dA[r,K] += u^T x : D[K,r] = sum_m x[m,:]^T ut[:,m], written transposed
+    psob200_gemm_args g = gemm_defaults(a.dtype);
+    g.a1 = a.x; g.lda1 = a.ldx; g.a_reduction_major = 1; g.b1 = a.ut; g.ldb1 = a.ldut;
+    g.M = a.K; g.N = a.r; g.K1 = a.M;
+    g.dt = a.d_lora_a; g.lddt = a.ld_da; g.d_dtype = PSOB200_F32; g.accumulate = 1;
+    if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
+  }
+  if (lora && a.d_lora_b != nullptr) {  // dB[N,r] += dy^T t
+    psob200_gemm_args g = gemm_defaults(a.dtype);
+    g.a1 = a.dy; g.lda1 = a.lddy; g.a_reduction_major = 1; g.b1 = a.tt; g.ldb1 = a.ldtt;
+    g.M = a.N; g.N = a.r; g.K1 = a.M;
+    g.d = a.d_lora_b; g.ldd = a.ld_db; g.d_dtype = PSOB200_F32; g.accumulate = 1;
+    if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
+  }
+  return PSOB200_OK;
 }

@@ -1,0 +1,380 @@
+"""LoRA-wrapped attention projections on the tcgen05 GEMM kernels -- host side.
+
+Mirrors the third-party surface the reference's trainers touch:
+
+* ``LoraConfig`` / ``add_adapter(unet, cfg)``: what ``unet.add_adapter(LoraConfig(r=..., lora_alpha=...,
+  init_lora_weights="gaussian", target_modules=["to_k","to_q","to_v","to_out.0"]))`` does
+  (train_online_pso_sdxl_turbo.py:338-345, train_online_pso_sdxl_dmd2.py:361-368,
+  train_pso_sdxl_turbo_dreambooth.py:1319-1326).
+* ``LoRALinear``: the module peft==0.11.1 puts in place of each target ``nn.Linear``: attributes ``base_layer``,
+  ``lora_A[name]``, ``lora_B[name]``, ``scaling[name]``, ``r``, ``lora_alpha``, ``disable_adapters``;
+  ``forward(x) = base_layer(x) + lora_B(lora_A(x)) * scaling``.
+* ``disable_adapters(unet)`` / ``enable_adapters(unet)``: the policy / frozen-reference switch
+  (turbo :790,805; dmd2 :792,807; dreambooth :1897,1918).
+* ``PSOAttnProcessor2_0``: diffusers==0.27.0 ``AttnProcessor2_0.__call__`` signature and data flow.
+* ``LoRAGradBucket``: every adapter gradient lives in ONE flat fp32 buffer, written in place by the
+  weight-gradient kernels (so gradient accumulation costs nothing) and all-reduced with ONE NCCL call
+  (the reference: DDP buckets behind accelerator.prepare, turbo :491, sync gate :858).
+
+The forward is two launches (skinny ``t = s x A^T``; then ``y = x W^T + b + t B^T`` in one pass over W) where the
+reference stack issues five; the backward is four.  There is no PyTorch fallback: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Iterable, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+
+@dataclass
+class LoraConfig:
+    """The subset of ``peft.LoraConfig`` the reference passes."""
+    r: int = 8
+    lora_alpha: int = 8
+    init_lora_weights: object = "gaussian"
+    target_modules: Iterable[str] = field(default_factory=lambda: ["to_k", "to_q", "to_v", "to_out.0"])
+    lora_dropout: float = 0.0
+
+
+def _ceil8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class LoRALinear(nn.Module):
+    """Drop-in for peft ``lora.Linear`` around a frozen ``nn.Linear`` (one adapter, named like peft's)."""
+
+    def __init__(self, base_layer: nn.Linear, r: int, lora_alpha: int, init_lora_weights="gaussian",
+                 adapter_name: str = "default", lora_dtype: torch.dtype = torch.float32):
+        super().__init__()
+        if r <= 0 or r > 256:
+            raise ValueError(f"LoRA rank must be in [1, 256], got {r}")
+        self.base_layer = base_layer
+        self.in_features, self.out_features = base_layer.in_features, base_layer.out_features
+        self.active_adapter = adapter_name
+        self.r = {adapter_name: r}
+        self.lora_alpha = {adapter_name: lora_alpha}
+        self.scaling = {adapter_name: lora_alpha / r}
+        dev = base_layer.weight.device
+        a = nn.Linear(self.in_features, r, bias=False, device=dev, dtype=lora_dtype)
+        b = nn.Linear(r, self.out_features, bias=False, device=dev, dtype=lora_dtype)
+        if init_lora_weights == "gaussian":  # peft: normal_(A, std=1/r), zeros_(B)
+            nn.init.normal_(a.weight, std=1.0 / r)
+        elif init_lora_weights:
+            nn.init.kaiming_uniform_(a.weight, a=math.sqrt(5))
+        nn.init.zeros_(b.weight)
+        self.lora_A = nn.ModuleDict({adapter_name: a})
+        self.lora_B = nn.ModuleDict({adapter_name: b})
+        self._disable_adapters = False
+        self._op_cache = {}  # 16-bit, TMA-friendly copies of the adapter weights, keyed by parameter version
+        base_layer.weight.requires_grad_(False)
+        if base_layer.bias is not None:
+            base_layer.bias.requires_grad_(False)
+
+    # ---- peft surface
+    @property
+    def disable_adapters(self) -> bool:
+        return self._disable_adapters
+
+    def enable_adapters(self, enabled: bool) -> None:
+        self._disable_adapters = not enabled
+
+    @property
+    def weight(self):
+        return self.base_layer.weight
+
+    @property
+    def bias(self):
+        return self.base_layer.bias
+
+    # ---- operands
+    def _operand(self, which: str, dtype: torch.dtype) -> torch.Tensor:
+        """The adapter matrix as a 16-bit tensor whose row pitch is a multiple of 16 bytes (A: [r,K]; B: [N,r] in a
+        [N, ceil8(r)] buffer).  Re-made only when the parameter changed (optimizer step)."""
+        p = (self.lora_A if which == "a" else self.lora_B)[self.active_adapter].weight
+        ok = p.dtype == dtype and p.is_contiguous() and p.shape[1] % 8 == 0 and p.data_ptr() % 16 == 0
+        if ok:
+            return p.detach()
+        key = (which, dtype)
+        hit = self._op_cache.get(key)
+        if hit is not None and hit[0] == p._version and hit[1] == p.data_ptr():
+            return hit[2]
+        cols = p.shape[1]
+        buf = torch.zeros(p.shape[0], _ceil8(cols), dtype=dtype, device=p.device)
+        buf[:, :cols].copy_(p.detach())
+        view = buf[:, :cols]
+        self._op_cache[key] = (p._version, p.data_ptr(), view)
+        return view
+
+    def forward(self, x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        n = self.active_adapter
+        # the adapter matrices are passed so that autograd knows the output depends on them (their gradients are
+        # accumulated in place by the kernels; the Function returns None for them)
+        return _LoraLinearFn.apply(x, self, self.lora_A[n].weight, self.lora_B[n].weight, torch.is_grad_enabled())
+
+
+class _LoraLinearFn(torch.autograd.Function):
+    """psob200_lora_linear_forward / _backward.  Gradients of the adapter matrices are ACCUMULATED IN PLACE into
+    ``param.grad`` (fp32 views of the flat bucket when one is attached), so autograd receives only ``dx``."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, layer: LoRALinear, _pa, _pb, grad_mode: bool):
+        w = layer.base_layer.weight
+        dev = _lib.require_cuda(x, w)
+        dtype = w.dtype
+        if dtype not in (torch.bfloat16, torch.float16):
+            raise _lib.Psob200Error(f"the tcgen05 LoRA path needs bf16/fp16 base weights, got {dtype}")
+        K, N = layer.in_features, layer.out_features
+        if x.shape[-1] != K:
+            raise _lib.Psob200Error(f"input feature size {x.shape[-1]} != in_features {K}")
+        x2 = x.detach().reshape(-1, K)
+        if x2.dtype != dtype:
+            x2 = x2.to(dtype)
+        if not x2.is_contiguous() or x2.data_ptr() % 16:
+            x2 = x2.contiguous()
+        if K % 8 or w.stride(0) != K or w.data_ptr() % 16:
+            raise _lib.Psob200Error("base weight must be contiguous with in_features a multiple of 8")
+        M = x2.shape[0]
+        enabled = not layer._disable_adapters
+        name = layer.active_adapter
+        r = layer.r[name]
+        a = _lib.LoraLinearArgs()
+        y = torch.empty(M, N, dtype=dtype, device=dev)
+        a.x, a.ldx, a.w, a.ldw, a.y, a.ldy = x2.data_ptr(), K, w.data_ptr(), K, y.data_ptr(), N
+        bias = layer.base_layer.bias
+        if bias is not None:
+            a.bias, a.bias_dtype = bias.data_ptr(), _lib.dtype_code(bias)
+        a.M, a.K, a.N, a.r = M, K, N, r
+        a.dtype = _lib.dtype_code(x2)
+        a.adapters_enabled = int(enabled)
+        want_wgrad = enabled and grad_mode and _pa.requires_grad  # False under no_grad (the frozen-reference pass)
+        t = tt = None
+        if enabled:
+            la, lb = layer._operand("a", dtype), layer._operand("b", dtype)
+            r8 = _ceil8(r)
+            t = torch.empty(M, r8, dtype=dtype, device=dev)
+            a.lora_a, a.lda, a.lora_b, a.ldb = la.data_ptr(), la.stride(0), lb.data_ptr(), lb.stride(0)
+            a.t, a.ldt = t.data_ptr(), r8
+            a.scaling = float(layer.scaling[name])
+            if want_wgrad:
+                tt = torch.empty(r, _ceil8(M), dtype=dtype, device=dev)
+                a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
+        rc = _lib.lib().psob200_lora_linear_forward(C.byref(a), _lib.current_stream(dev))
+        _lib.check(rc, "psob200_lora_linear_forward")
+        ctx.layer, ctx.enabled, ctx.x_shape, ctx.x_dtype, ctx.want_wgrad = layer, enabled, x.shape, x.dtype, want_wgrad
+        ctx.save_for_backward(x2, tt)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        layer: LoRALinear = ctx.layer
+        x2, tt = ctx.saved_tensors
+        w = layer.base_layer.weight
+        dev, dtype = w.device, w.dtype
+        K, N = layer.in_features, layer.out_features
+        M = x2.shape[0]
+        dy2 = dy.reshape(-1, N)
+        if dy2.dtype != dtype:
+            dy2 = dy2.to(dtype)
+        if not dy2.is_contiguous() or dy2.data_ptr() % 16:
+            dy2 = dy2.contiguous()
+        name = layer.active_adapter
+        r = layer.r[name]
+        a = _lib.LoraLinearArgs()
+        a.dy, a.lddy, a.w, a.ldw, a.x, a.ldx = dy2.data_ptr(), N, w.data_ptr(), K, x2.data_ptr(), K
+        a.M, a.K, a.N, a.r = M, K, N, r
+        a.dtype = _lib.dtype_code(dy2)
+        a.adapters_enabled = int(ctx.enabled)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, dtype=dtype, device=dev)
+            a.dx, a.lddx = dx.data_ptr(), K
+        keep = []
+        if ctx.enabled:
+            pa, pb = layer.lora_A[name].weight, layer.lora_B[name].weight
+            la, lb = layer._operand("a", dtype), layer._operand("b", dtype)
+            a.lora_a, a.lda, a.lora_b, a.ldb = la.data_ptr(), la.stride(0), lb.data_ptr(), lb.stride(0)
+            a.scaling = float(layer.scaling[name])
+            r8 = _ceil8(r)
+            u = torch.empty(M, r8, dtype=dtype, device=dev)
+            a.u, a.ldu = u.data_ptr(), r8
+            keep.append(u)
+            if ctx.want_wgrad:
+                ga, gb = _grad_buffer(pa), _grad_buffer(pb)
+                ut = torch.empty(r, _ceil8(M), dtype=dtype, device=dev)
+                a.ut, a.ldut = ut.data_ptr(), ut.stride(0)
+                a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
+                a.d_lora_a, a.ld_da = ga.data_ptr(), ga.stride(0)
+                a.d_lora_b, a.ld_db = gb.data_ptr(), gb.stride(0)
+                keep += [ut, ga, gb]
+        if dx is not None or (ctx.enabled and a.d_lora_a):
+            rc = _lib.lib().psob200_lora_linear_backward(C.byref(a), _lib.current_stream(dev))
+            _lib.check(rc, "psob200_lora_linear_backward")
+        del keep
+        if dx is not None:
+            dx = dx.view(ctx.x_shape)
+            if dx.dtype != ctx.x_dtype:
+                dx = dx.to(ctx.x_dtype)
+        return dx, None, None, None, None
+
+
+def _grad_buffer(p: torch.nn.Parameter) -> torch.Tensor:
+    """fp32 accumulation target of a LoRA parameter: ``p.grad`` itself for fp32 parameters (a view of the flat
+    bucket once ``LoRAGradBucket`` is attached), else a side buffer ``p.grad32`` folded in by ``finalize_grads``."""
+    if p.dtype == torch.float32:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+        return p.grad
+    g = getattr(p, "grad32", None)
+    if g is None:
+        g = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+        p.grad32 = g
+    return g
+
+
+# ----------------------------------------------------------------------------------------------- model-level API
+def lora_layers(model: nn.Module):
+    return [m for m in model.modules() if isinstance(m, LoRALinear)]
+
+
+def add_adapter(model: nn.Module, config: LoraConfig, adapter_name: str = "default",
+                lora_dtype: torch.dtype = torch.float32) -> list:
+    """``unet.add_adapter(cfg)``: wrap every ``nn.Linear`` whose qualified name ends with one of
+    ``config.target_modules`` (peft matches by suffix, so "to_out.0" hits ``...attn{1,2}.to_out.0`` only).
+    ``lora_dtype=float32`` is what the shipped fp16 recipes train (turbo :346-350); pass the base dtype to mimic the
+    bf16 recipes, where peft leaves the adapters in the base dtype."""
+    targets = list(config.target_modules)
+    wrapped = []
+    for parent_name, parent in list(model.named_modules()):
+        for child_name, child in list(parent.named_children()):
+            full = f"{parent_name}.{child_name}" if parent_name else child_name
+            if isinstance(child, nn.Linear) and any(full == t or full.endswith("." + t) for t in targets):
+                new = LoRALinear(child, config.r, config.lora_alpha, config.init_lora_weights, adapter_name, lora_dtype)
+                setattr(parent, child_name, new)
+                wrapped.append(new)
+    if not wrapped:
+        raise ValueError(f"no nn.Linear matches target_modules={targets}")
+    return wrapped
+
+
+def disable_adapters(model: nn.Module) -> None:
+    for m in lora_layers(model):
+        m.enable_adapters(False)
+
+
+def enable_adapters(model: nn.Module) -> None:
+    for m in lora_layers(model):
+        m.enable_adapters(True)
+
+
+def lora_parameters(model: nn.Module):
+    out = []
+    for m in lora_layers(model):
+        n = m.active_adapter
+        out += [m.lora_A[n].weight, m.lora_B[n].weight]
+    return out
+
+
+class LoRAGradBucket:
+    """All adapter gradients in one flat fp32 buffer.
+
+    ``param.grad`` of every fp32 adapter matrix becomes a view of ``self.flat``; the dA / dB kernels accumulate
+    into those views directly.  ``all_reduce()`` is the data-parallel exchange of the whole training step: one
+    collective over the flat buffer, averaged over ranks (what DDP does for the reference, bucket by bucket).
+    ``clip_grad_norm_`` is accelerate's ``clip_grad_norm_`` (turbo :859) on the flat buffer: one norm, one scale."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable LoRA parameters")
+        dev = self.params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]  # keep every view 16-byte aligned
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.views = []
+        off = 0
+        for p, n in zip(self.params, sizes):
+            v = self.flat[off:off + p.numel()].view(p.shape)
+            off += n
+            self.views.append(v)
+            if p.dtype == torch.float32:
+                p.grad = v
+            else:
+                p.grad32 = v
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce(self, group=None, async_op: bool = False):
+        """Average the flat gradient over the data-parallel ranks with ONE collective."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        op = dist.ReduceOp.AVG if dist.get_backend(group) == "nccl" else dist.ReduceOp.SUM
+        work = dist.all_reduce(self.flat, op=op, group=group, async_op=async_op)
+        if op == dist.ReduceOp.SUM:
+            if async_op:
+                work.wait()
+                work = None
+            self.flat.div_(dist.get_world_size(group))
+        return work
+
+    def clip_grad_norm_(self, max_norm: float) -> torch.Tensor:
+        norm = torch.linalg.vector_norm(self.flat)
+        self.flat.mul_(torch.clamp(max_norm / (norm + 1e-6), max=1.0))
+        return norm
+
+    def finalize_grads(self) -> None:
+        """For 16-bit adapter parameters: publish the fp32 accumulators as ``param.grad`` in the parameter dtype."""
+        for p, v in zip(self.params, self.views):
+            if p.dtype != torch.float32:
+                p.grad = v.to(p.dtype)
+
+
+# ----------------------------------------------------------------------------------------------- attention processor
+class PSOAttnProcessor2_0:
+    """diffusers==0.27.0 ``AttnProcessor2_0``: same ``__call__`` signature, same data flow; the four projections run
+    on the tcgen05 path when they are ``LoRALinear`` (the attention core stays ``F.scaled_dot_product_attention``,
+    which is outside the PSO hot path)."""
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0):
+        residual = hidden_states
+        if getattr(attn, "spatial_norm", None) is not None:
+            hidden_states = attn.spatial_norm(hidden_states, temb)
+        input_ndim = hidden_states.ndim
+        if input_ndim == 4:
+            bsz, ch, h, w = hidden_states.shape
+            hidden_states = hidden_states.view(bsz, ch, h * w).transpose(1, 2)
+        bsz = hidden_states.shape[0]
+        if getattr(attn, "group_norm", None) is not None:
+            hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+        query = attn.to_q(hidden_states)
+        if encoder_hidden_states is None:
+            encoder_hidden_states = hidden_states
+        elif getattr(attn, "norm_cross", None):
+            encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
+        key = attn.to_k(encoder_hidden_states)
+        value = attn.to_v(encoder_hidden_states)
+        inner = key.shape[-1]
+        hd = inner // attn.heads
+        query = query.view(bsz, -1, attn.heads, hd).transpose(1, 2)
+        key = key.view(bsz, -1, attn.heads, hd).transpose(1, 2)
+        value = value.view(bsz, -1, attn.heads, hd).transpose(1, 2)
+        if attention_mask is not None and hasattr(attn, "prepare_attention_mask"):
+            attention_mask = attn.prepare_attention_mask(attention_mask, key.shape[2], bsz)
+            attention_mask = attention_mask.view(bsz, attn.heads, -1, attention_mask.shape[-1])
+        hidden_states = F.scaled_dot_product_attention(query, key, value, attn_mask=attention_mask, dropout_p=0.0,
+                                                       is_causal=False)
+        hidden_states = hidden_states.transpose(1, 2).reshape(bsz, -1, attn.heads * hd).to(query.dtype)
+        hidden_states = attn.to_out[0](hidden_states)
+        hidden_states = attn.to_out[1](hidden_states)
+        if input_ndim == 4:
+            hidden_states = hidden_states.transpose(-1, -2).reshape(bsz, ch, h, w)
+        if getattr(attn, "residual_connection", False):
+            hidden_states = hidden_states + residual
+        return hidden_states / getattr(attn, "rescale_output_factor", 1.0)
