@@ -341,6 +341,8 @@ typedef struct psob200_gemm_args {
   int32_t accumulate;
   int32_t split_k;
   int32_t tune_bn;
+  int32_t diag; /* timing experiments only (results are then wrong): bit 0 skip the MMAs, bit 1 skip the stores,
+                   bit 2 skip the B loads */
 } psob200_gemm_args;
 
 PSOB200_API int psob200_lora_gemm(const psob200_gemm_args* args, void* stream);

@@ -28,7 +28,8 @@ namespace psob200 {
 constexpr int kBM = 128;            // UMMA M: rows of an output tile
 constexpr int kBNMax = 256;         // widest UMMA N
 constexpr int kBK = 64;             // reduction elements per stage = one 128-byte swizzle span of a 16-bit type
-constexpr int kStages = 4;
+constexpr int kStages = 4;          // with the widest tile; narrower tiles get more (up to kMaxStages)
+constexpr int kMaxStages = 8;
 constexpr int kGemmThreads = 256;
 constexpr int kStageABytes = kBM * kBK * 2;      // 16 KB
 constexpr int kStageBBytes = kBNMax * kBK * 2;   // 32 KB
@@ -44,7 +45,8 @@ struct GemmKernelParams {
   void* dt; long long lddt;   // transposed output [N, M] (may be null)
   const void* bias;
   float alpha;
-  int d_dtype, bias_dtype, ab_format, a_mn, b_mn, atomic;
+  int d_dtype, bias_dtype, ab_format, a_mn, b_mn, atomic, diag;
+  int stages;             // even; stage = 16 KB of A + bn*128 B of B
 };
 
 template <typename T>
@@ -53,25 +55,42 @@ template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v;
 template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
 
-__device__ __forceinline__ float load_bias(const void* bias, int dt, long long n) {
-  if (dt == PSOB200_F32) return __ldg(reinterpret_cast<const float*>(bias) + n);
-  if (dt == PSOB200_BF16) return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(bias) + n));
-  return __half2float(__ldg(reinterpret_cast<const __half*>(bias) + n));
+// bias[n0 .. n0+32) as fp32, zero beyond N.  One uniform branch per chunk, 128-bit loads for whole chunks.
+template <typename TB>
+__device__ __forceinline__ void load_bias32(const void* bias, long long n0, long long N, float (&b)[32]) {
+  const TB* src = reinterpret_cast<const TB*>(bias) + n0;
+  if (n0 + 32 <= N && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float t[8];
+      if constexpr (sizeof(TB) == 4) {
+        const float4 lo = __ldg(reinterpret_cast<const float4*>(src + j)), hi = __ldg(reinterpret_cast<const float4*>(src + j + 4));
+        t[0] = lo.x; t[1] = lo.y; t[2] = lo.z; t[3] = lo.w; t[4] = hi.x; t[5] = hi.y; t[6] = hi.z; t[7] = hi.w;
+      } else {
+        const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(src + j));
+        typename Vec8<TB>::Raw raw{w4};
+        Vec8<TB>::decode(raw, t);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) b[j + i] = t[i];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = (n0 + j < N) ? Vec8<TB>::load1(src + j) : 0.f;
+  }
 }
 
 // One 32-column chunk of one accumulator row: v[j] belongs to (row, n0 + j).
-template <typename TD>
+template <typename TD, bool kAtomic>
 __device__ __forceinline__ void store_chunk(const GemmKernelParams& p, const float (&v)[32], long long row, long long n0) {
-  const bool row_ok = row < p.M;
+  if (row >= p.M) return;
   const long long nleft = p.N - n0;  // columns of this chunk that exist
-  if (p.d != nullptr && row_ok) {
+  if (p.d != nullptr) {
     TD* dst = reinterpret_cast<TD*>(p.d) + row * p.ldd + n0;
-    if (p.atomic) {
-      if constexpr (sizeof(TD) == 4) {
+    if constexpr (kAtomic) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nleft) atomicAdd(reinterpret_cast<float*>(dst) + j, v[j]);
-      }
+      for (int j = 0; j < 32; ++j)
+        if (j < nleft) atomicAdd(reinterpret_cast<float*>(dst) + j, v[j]);
     } else if (nleft >= 32 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
       if constexpr (sizeof(TD) == 4) {
 #pragma unroll
@@ -90,19 +109,52 @@ __device__ __forceinline__ void store_chunk(const GemmKernelParams& p, const flo
         if (j < nleft) dst[j] = cvt_out<TD>(v[j]);
     }
   }
-  if (p.dt != nullptr && row_ok) {  // lanes hold consecutive rows: every column is a coalesced store
+  if (p.dt != nullptr) {  // lanes hold consecutive rows: every column is a coalesced store
     TD* dst = reinterpret_cast<TD*>(p.dt) + n0 * p.lddt + row;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       if (j < nleft) {
-        if (p.atomic) {
-          if constexpr (sizeof(TD) == 4) atomicAdd(reinterpret_cast<float*>(dst) + (long long)j * p.lddt, v[j]);
-        } else {
-          dst[(long long)j * p.lddt] = cvt_out<TD>(v[j]);
-        }
+        if constexpr (kAtomic) atomicAdd(reinterpret_cast<float*>(dst) + (long long)j * p.lddt, v[j]);
+        else dst[(long long)j * p.lddt] = cvt_out<TD>(v[j]);
       }
     }
   }
+}
+
+// Drain one accumulator tile: TMEM -> registers (the load of chunk c+1 is in flight while chunk c is converted and
+// stored) -> alpha, bias -> global.
+template <typename TD, bool kAtomic>
+__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_t taddr, long long row, long long n_tile0,
+                                              bool add_bias) {
+  const int chunks = (p.bn + 31) / 32;
+  uint32_t raw[2][32];
+  ptx::tmem_ld_32x32(taddr, raw[0]);
+#pragma unroll 1
+  for (int c = 0; c < chunks; c += 2) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cc = c + h;
+      const long long n0 = n_tile0 + (long long)cc * 32;
+      if (cc < chunks && n0 < p.N) {  // uniform over the warp
+        ptx::tmem_ld_wait();
+        if (cc + 1 < chunks) ptx::tmem_ld_32x32(taddr + (uint32_t)(cc + 1) * 32, raw[h ^ 1]);
+        float v[32];
+        if (add_bias) {
+          float b[32];
+          if (p.bias_dtype == PSOB200_F32) load_bias32<float>(p.bias, n0, p.N, b);
+          else if (p.bias_dtype == PSOB200_BF16) load_bias32<__nv_bfloat16>(p.bias, n0, p.N, b);
+          else load_bias32<__half>(p.bias, n0, p.N, b);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(p.alpha, __uint_as_float(raw[h][j]), b[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(raw[h][j]);
+        }
+        if (!(p.diag & 2)) store_chunk<TD, kAtomic>(p, v, row, n0);
+      }
+    }
+  }
+  ptx::tmem_ld_wait();
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -110,12 +162,16 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                  const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
                  const GemmKernelParams p) {
   extern __shared__ unsigned char gemm_smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar[2], tmem_empty_bar[2];
+  // one "full" barrier per stage, one "empty" barrier per PAIR of stages: tcgen05.commit costs several hundred
+  // cycles of tensor-pipe command time, so the MMA warp commits every second k-block only
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages / 2], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_a = smem;
-  unsigned char* smem_b = smem + kStages * kStageABytes;
+  const int n_stages = p.stages;
+  const int stage_b_bytes = p.bn * kBK * 2;
+  unsigned char* smem_b = smem + n_stages * kStageABytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = p.nk1 + p.nk2;
@@ -131,10 +187,9 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);   // producer's arrive.expect_tx; TMA completes the bytes
-      ptx::mbar_init(&empty_bar[s], 1);  // tcgen05.commit
-    }
+    for (int s = 0; s < kMaxStages; ++s) ptx::mbar_init(&full_bar[s], 1);  // producer's arrive.expect_tx; TMA completes the bytes
+#pragma unroll
+    for (int s = 0; s < kMaxStages / 2; ++s) ptx::mbar_init(&empty_bar[s], 1);  // tcgen05.commit
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);   // tcgen05.commit after the tile's last MMA
@@ -157,80 +212,88 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     kb1 = kb0 + p.kb_per_split < nk ? kb0 + p.kb_per_split : nk;
   };
 
+  // The producer and MMA loops run WARP-UNIFORMLY (all 32 lanes keep the loop state) and only the issuing
+  // instructions are predicated on elect.sync: UTMALDG / UTCHMMA take uniform-register operands, and a loop that
+  // only lane 0 executes makes ptxas wrap every one of them in an ELECT / R2UR.BROADCAST waterfall (measured:
+  // ~450 cycles per k-block, more than the MMAs themselves).
   if (warp == 0) {
     // ================================================================= TMA producer
-    if (lane == 0) {
-      const uint32_t tx = (uint32_t)kStageABytes + (uint32_t)p.bn * kBK * 2u;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int m_blk, n_blk, kb0, kb1;
-        tile_coords(t, m_blk, n_blk, kb0, kb1);
-        const int m0 = m_blk * kBM, n0 = n_blk * p.bn;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-          const bool seg2 = kb >= p.nk1;
-          const CUtensorMap* ma = seg2 ? &map_a2 : &map_a1;
-          const CUtensorMap* mb = seg2 ? &map_b2 : &map_b1;
-          const int kk = (seg2 ? kb - p.nk1 : kb) * kBK;
-          unsigned char* sa = smem_a + stage * kStageABytes;
-          unsigned char* sb = smem_b + stage * kStageBBytes;
+    const uint32_t tx = ((p.diag & 8) ? 0u : (uint32_t)kStageABytes) + ((p.diag & 4) ? 0u : (uint32_t)p.bn * kBK * 2u);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int m_blk, n_blk, kb0, kb1;
+      tile_coords(t, m_blk, n_blk, kb0, kb1);
+      const int m0 = m_blk * kBM, n0 = n_blk * p.bn;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if ((stage & 1) == 0) ptx::mbar_wait(&empty_bar[stage >> 1], phase ^ 1u);  // the pair (stage, stage+1) is free
+        const bool seg2 = kb >= p.nk1;
+        const CUtensorMap* ma = seg2 ? &map_a2 : &map_a1;
+        const CUtensorMap* mb = seg2 ? &map_b2 : &map_b1;
+        const int kk = (seg2 ? kb - p.nk1 : kb) * kBK;
+        unsigned char* sa = smem_a + stage * kStageABytes;
+        unsigned char* sb = smem_b + stage * stage_b_bytes;
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full_bar[stage], tx);
-          if (p.a_mn) {  // A given reduction-major: two [64 k x 64 m] boxes, m contiguous
+          if (p.diag & 8) {
+          } else if (p.a_mn) {  // A given reduction-major: two [64 k x 64 m] boxes, m contiguous
             ptx::tma_load_2d(sa, ma, m0, kk, &full_bar[stage]);
             ptx::tma_load_2d(sa + kStageABytes / 2, ma, m0 + 64, kk, &full_bar[stage]);
           } else {
             ptx::tma_load_2d(sa, ma, kk, m0, &full_bar[stage]);
           }
-          if (p.b_mn) {  // B given reduction-major: bn/64 boxes of [64 k x 64 n], n contiguous
+          if (p.diag & 4) {
+          } else if (p.b_mn) {  // B given reduction-major: bn/64 boxes of [64 k x 64 n], n contiguous
             for (int j = 0; j < p.bn / 64; ++j)
               ptx::tma_load_2d(sb + j * (kBK * 128), mb, n0 + 64 * j, kk, &full_bar[stage]);
           } else {
             ptx::tma_load_2d(sb, mb, kk, n0, &full_bar[stage]);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ================================================================= MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_f16((uint32_t)p.ab_format, (uint32_t)p.a_mn, (uint32_t)p.b_mn, (uint32_t)p.bn);
-      int stage = 0;
-      uint32_t phase = 0;
-      long long iter = 0;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
-        int m_blk, n_blk, kb0, kb1;
-        tile_coords(t, m_blk, n_blk, kb0, kb1);
-        const int acc = (int)(iter & 1);
-        const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
-        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
+    const uint32_t idesc = ptx::umma_idesc_f16((uint32_t)p.ab_format, (uint32_t)p.a_mn, (uint32_t)p.b_mn, (uint32_t)p.bn);
+    // per-k-step advance of the descriptor start address (>> 4) and the constant upper halves:
+    //   K-major, 128B swizzle: 8-row atoms 1024 B apart (SBO); a 16-element k step is 32 B inside the swizzle span.
+    //   reduction-major ("MN-major"): 64(mn) x 8(k) atoms, 1024 B between k atoms (SBO), 64 k-rows * 128 B between
+    //   mn atoms (LBO); a 16-row k step is 2048 B.
+    const uint64_t a_hi = ptx::smem_desc_sw128(0, p.a_mn ? kBK * 128 : 0, 1024);
+    const uint64_t b_hi = ptx::smem_desc_sw128(0, p.b_mn ? kBK * 128 : 0, 1024);
+    const uint32_t a_step = p.a_mn ? 2048u >> 4 : 32u >> 4, b_step = p.b_mn ? 2048u >> 4 : 32u >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    long long iter = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+      int m_blk, n_blk, kb0, kb1;
+      tile_coords(t, m_blk, n_blk, kb0, kb1);
+      const int acc = (int)(iter & 1);
+      const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
+      ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
+      ptx::tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * kBNMax;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kBNMax;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after_sync();
-          const uint32_t a_base = ptx::smem_addr(smem_a + stage * kStageABytes);
-          const uint32_t b_base = ptx::smem_addr(smem_b + stage * kStageBBytes);
+        const uint64_t a_desc = a_hi | (uint64_t)((ptx::smem_addr(smem_a + stage * kStageABytes) >> 4) & 0x3FFFu);
+        const uint64_t b_desc = b_hi | (uint64_t)((ptx::smem_addr(smem_b + stage * stage_b_bytes) >> 4) & 0x3FFFu);
+        if (ptx::elect_one()) {
+          if (!(p.diag & 1)) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // K-major, 128B swizzle: 8-row atoms 1024 B apart, a 16-element k step is 32 B inside the span.
-            // MN-major (reduction-major) operand: 64(mn) x 8(k) atoms; 1024 B between k atoms, 64 k-rows * 128 B
-            // between mn atoms.
-            const uint64_t a_desc = p.a_mn ? ptx::smem_desc_sw128(a_base + k * 2048, kBK * 128, 1024)
-                                           : ptx::smem_desc_sw128(a_base + k * 32, 0, 1024);
-            const uint64_t b_desc = p.b_mn ? ptx::smem_desc_sw128(b_base + k * 2048, kBK * 128, 1024)
-                                           : ptx::smem_desc_sw128(b_base + k * 32, 0, 1024);
-            ptx::umma_f16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k)
+              ptx::umma_f16(d_tmem, a_desc + (uint64_t)(k * a_step), b_desc + (uint64_t)(k * b_step), idesc,
+                            (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);                         // stage reusable once these MMAs retire
-          if (kb == kb1 - 1) ptx::umma_commit(&tmem_full_bar[acc]);    // accumulator complete
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (stage & 1) ptx::umma_commit(&empty_bar[stage >> 1]);   // the pair is reusable once these MMAs retire
+          if (kb == kb1 - 1) ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete
         }
+        __syncwarp();
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ================================================================= epilogue (TMEM lanes 32*(warp%4) ..)
     const int ew = warp - 4;
@@ -246,23 +309,10 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kBNMax;
-      const int chunks = (p.bn + 31) / 32;
-      for (int c = 0; c < chunks; ++c) {
-        const long long n0 = n_tile0 + c * 32;
-        if (n0 >= p.N) break;  // uniform over the warp
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(taddr + (uint32_t)c * 32, raw);
-        ptx::tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = p.alpha * __uint_as_float(raw[j]);
-          if (add_bias && n0 + j < p.N) v[j] += load_bias(p.bias, p.bias_dtype, n0 + j);
-        }
-        if (p.d_dtype == PSOB200_F32) store_chunk<float>(p, v, row, n0);
-        else if (p.d_dtype == PSOB200_BF16) store_chunk<__nv_bfloat16>(p, v, row, n0);
-        else store_chunk<__half>(p, v, row, n0);
-      }
+      if (p.atomic) epilogue_tile<float, true>(p, taddr, row, n_tile0, add_bias);
+      else if (p.d_dtype == PSOB200_F32) epilogue_tile<float, false>(p, taddr, row, n_tile0, add_bias);
+      else if (p.d_dtype == PSOB200_BF16) epilogue_tile<__nv_bfloat16, false>(p, taddr, row, n_tile0, add_bias);
+      else epilogue_tile<__half, false>(p, taddr, row, n_tile0, add_bias);
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
@@ -390,6 +440,11 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
   p.a_mn = g.a_reduction_major ? 1 : 0;
   p.b_mn = g.b_reduction_major ? 1 : 0;
   p.atomic = g.accumulate ? 1 : 0;
+  p.diag = g.diag;
+  p.stages = (kStages * (kStageABytes + kStageBBytes)) / (kStageABytes + p.bn * kBK * 2);
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.stages &= ~1;
+  if ((g.diag >> 8) & 15) p.stages = (g.diag >> 8) & 14;
 
   CUtensorMap ma1, mb1, ma2, mb2;
   int rc;
