@@ -1,0 +1,76 @@
+"""One online-PSO training micro-step on the SDXL-architecture fixture, written the way the reference's trainers
+write it (train_online_pso_sdxl_turbo.py:771-861), once against the product API (CUDA) and once against the oracle
+(CPU).  FIXTURE code shared by tests/ and bench.py; the oracle variant is test / baseline infrastructure only."""
+from __future__ import annotations
+
+import types
+
+import torch
+
+TURBO_TS = [999, 749, 499]  # trained timesteps: first 3 of the 4-step trailing schedule (turbo :617)
+
+
+def synth_batch(B, latent_hw, cross_dim, pooled_dim, seed, sigmas, dtype=torch.float32, device="cpu"):
+    """Synthetic stored trajectories of one micro-step: per pair and branch the current latent
+    (sigma-scaled noise), the UNet input (latent / sqrt(sigma^2+1), turbo :121), the stored next latent, one trained
+    timestep per pair, prompt embeddings and the reward sign."""
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randint(0, len(TURBO_TS), (B,), generator=g)
+    ts = torch.tensor(TURBO_TS)[idx]
+    sig = sigmas[idx].float()
+    sig_next = sigmas[idx + 1].float()
+    out = {"timesteps": ts, "step_index": idx}
+    for k in (0, 1):
+        lat = torch.randn(B, 4, latent_hw, latent_hw, generator=g) * sig[:, None, None, None]
+        out[f"latents_{k}"] = lat
+        out[f"input_latents_{k}"] = lat / (sig[:, None, None, None] ** 2 + 1) ** 0.5
+        out[f"next_latents_{k}"] = torch.randn(B, 4, latent_hw, latent_hw, generator=g) * sig_next[:, None, None, None]
+    out["prompt_embeds"] = torch.randn(B, 77, cross_dim, generator=g)
+    out["text_embeds"] = torch.randn(B, pooled_dim, generator=g)
+    out["time_ids"] = torch.tensor([[512.0, 512.0, 0.0, 0.0, 512.0, 512.0]]).repeat(B, 1)
+    sign = torch.randint(0, 2, (B,), generator=g).float() * 2 - 1
+    out["human_prefer"] = torch.stack([-sign, sign], 1)
+    cast = lambda t: t.to(device=device, dtype=dtype) if t.is_floating_point() else t.to(device)
+    return {k: (cast(v) if k not in ("human_prefer", "time_ids") else v.to(device)) for k, v in out.items()}
+
+
+def _unet_call(unet, x, ts, batch):
+    return unet(x, ts, batch["prompt_embeds"], added_cond_kwargs={"text_embeds": batch["text_embeds"],
+                                                                  "time_ids": batch["time_ids"].to(x.dtype)}).sample
+
+
+def product_micro_step(pso, lora, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0):
+    """Product path: 2 policy forwards with grad, 2 adapter-disabled forwards without (turbo :775-805), the fused
+    loss+grad kernel in place of the four step calls + inline loss (:810-850), backward (:857)."""
+    ts = batch["timesteps"]
+    p0 = _unet_call(unet, batch["input_latents_0"], ts, batch)
+    p1 = _unet_call(unet, batch["input_latents_1"], ts, batch)
+    lora.disable_adapters(unet)
+    with torch.no_grad():
+        r0 = _unet_call(unet, batch["input_latents_0"], ts, batch)
+        r1 = _unet_call(unet, batch["input_latents_1"], ts, batch)
+    lora.enable_adapters(unet)
+    loss = pso.pso_pair_loss(p0, p1, r0, r1, batch["latents_0"], batch["latents_1"],
+                             batch["next_latents_0"], batch["next_latents_1"], ts, ts, batch["human_prefer"],
+                             scheduler=sched, kind="turbo", beta=beta, eps=eps, loss_scale=loss_scale)
+    loss.backward()
+    return loss
+
+
+def oracle_micro_step(olora, olosses, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0):
+    """The reference's flow restated with the oracle pieces (CPU): same four forwards, four step-with-logprob calls,
+    inline loss, autograd backward."""
+    ts = batch["timesteps"]
+    p0 = _unet_call(unet, batch["input_latents_0"], ts, batch)
+    p1 = _unet_call(unet, batch["input_latents_1"], ts, batch)
+    olora.oracle_set_adapters(unet, False)
+    with torch.no_grad():
+        r0 = _unet_call(unet, batch["input_latents_0"], ts, batch)
+        r1 = _unet_call(unet, batch["input_latents_1"], ts, batch)
+    olora.oracle_set_adapters(unet, True)
+    loss, _ = olosses.online_micro_step("turbo", sched, [p0.float(), p1.float()], [r0.float(), r1.float()],
+                                        [batch["latents_0"].float(), batch["latents_1"].float()],
+                                        [batch["next_latents_0"].float(), batch["next_latents_1"].float()], [ts, ts],
+                                        batch["human_prefer"], beta, eps)
+    (loss * loss_scale).backward()
+    return loss * loss_scale

@@ -98,3 +98,49 @@ def lora_linear_rounded_flow(x, weight, bias, lora_A, lora_B, grad_y, scaling: f
     dA = U.t() @ x2
     dB = g2.t() @ T
     return {"y": y.reshape(*x.shape[:-1], -1), "dX": dX.reshape(x.shape), "dA": dA, "dB": dB, "T": T, "U": U}
+
+
+class OracleLoRALinear(torch.nn.Module):
+    """peft==0.11.1 ``lora.Linear`` restated as a plain torch module (CPU oracle / reference arm): same attribute
+    names as the real one (``base_layer``, ``lora_A``, ``lora_B``, ``scaling``, ``disable_adapters``)."""
+
+    def __init__(self, base_layer: torch.nn.Linear, r: int, lora_alpha: int, adapter_name: str = "default"):
+        super().__init__()
+        self.base_layer = base_layer
+        self.active_adapter = adapter_name
+        self.r, self.lora_alpha, self.scaling = {adapter_name: r}, {adapter_name: lora_alpha}, {adapter_name: lora_alpha / r}
+        dev, dt = base_layer.weight.device, torch.float32
+        a = torch.nn.Linear(base_layer.in_features, r, bias=False, device=dev, dtype=dt)
+        b = torch.nn.Linear(r, base_layer.out_features, bias=False, device=dev, dtype=dt)
+        torch.nn.init.normal_(a.weight, std=1.0 / r)
+        torch.nn.init.zeros_(b.weight)
+        self.lora_A = torch.nn.ModuleDict({adapter_name: a})
+        self.lora_B = torch.nn.ModuleDict({adapter_name: b})
+        self.disable_adapters = False
+        base_layer.weight.requires_grad_(False)
+        if base_layer.bias is not None:
+            base_layer.bias.requires_grad_(False)
+
+    def forward(self, x):
+        n = self.active_adapter
+        return lora_linear(x, self.base_layer.weight, self.base_layer.bias, self.lora_A[n].weight, self.lora_B[n].weight,
+                           self.scaling[n], adapters_enabled=not self.disable_adapters)
+
+
+def oracle_add_adapter(model, r, lora_alpha, target_modules=("to_k", "to_q", "to_v", "to_out.0")):
+    """``unet.add_adapter(LoraConfig(...))`` with the restated module; suffix matching like peft."""
+    wrapped = []
+    for parent_name, parent in list(model.named_modules()):
+        for child_name, child in list(parent.named_children()):
+            full = f"{parent_name}.{child_name}" if parent_name else child_name
+            if isinstance(child, torch.nn.Linear) and any(full == t or full.endswith("." + t) for t in target_modules):
+                new = OracleLoRALinear(child, r, lora_alpha)
+                setattr(parent, child_name, new)
+                wrapped.append(new)
+    return wrapped
+
+
+def oracle_set_adapters(model, enabled: bool):
+    for m in model.modules():
+        if isinstance(m, OracleLoRALinear):
+            m.disable_adapters = not enabled

@@ -1,0 +1,98 @@
+"""Host-side logic of the LoRA path that needs no GPU: adapter injection by peft-style suffix matching, the flat
+gradient bucket and its single all-reduce (gloo, world_size 2), the fixture's SDXL inventory, the oracle micro-step."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fixtures import micro_step, sdxl_unet
+from oracle import lora as olora, losses as olosses, schedules
+
+
+def test_sdxl_architecture_inventory():
+    """The scaffold reproduces the counts SURVEY.md derives for the real SDXL UNet."""
+    with torch.device("meta"):
+        big = sdxl_unet.UNet2DConditionModel(sdxl_unet.sdxl_config())
+    assert sdxl_unet.count_lora_targets(big) == 560
+    assert sum(1 for m in big.modules() if isinstance(m, sdxl_unet.BasicTransformerBlock)) == 70
+    tot = sum(m.in_features + m.out_features for n, m in big.named_modules() if isinstance(m, torch.nn.Linear) and
+              any(n.endswith(s) for s in (".to_q", ".to_k", ".to_v", ".to_out.0")))
+    assert tot == 1451520  # x rank = trainable parameters
+    assert abs(sum(p.numel() for p in big.parameters()) / 1e9 - 2.567) < 0.01
+
+
+def test_add_adapter_matches_peft_suffix_rules(built_lib):
+    from pairwise_sample_optimization_b200 import _lib, lora
+    unet = sdxl_unet.UNet2DConditionModel(sdxl_unet.tiny_config())
+    wrapped = lora.add_adapter(unet, lora.LoraConfig(r=4, lora_alpha=4))
+    assert len(wrapped) == 96
+    names = [n for n, m in unet.named_modules() if isinstance(m, lora.LoRALinear)]
+    assert all(n.endswith((".to_q", ".to_k", ".to_v", ".to_out.0")) for n in names)
+    assert not any(".ff." in n or "proj_in" in n or "proj_out" in n for n in names)
+    m = wrapped[0]
+    assert m.scaling["default"] == 1.0 and m.r["default"] == 4 and not m.disable_adapters
+    assert float(m.lora_B["default"].weight.detach().abs().sum()) == 0.0  # peft gaussian init: B = 0
+    assert abs(float(m.lora_A["default"].weight.detach().std()) - 0.25) < 0.1  # std = 1/r
+    trainable = [p for p in unet.parameters() if p.requires_grad]
+    frozen_targets = [m.base_layer.weight.requires_grad for m in wrapped]
+    assert not any(frozen_targets) and len(lora.lora_parameters(unet)) == 192
+    lora.disable_adapters(unet)
+    assert all(w.disable_adapters for w in wrapped)
+    lora.enable_adapters(unet)
+    assert not any(w.disable_adapters for w in wrapped)
+    with pytest.raises(_lib.Psob200Error):  # no CPU fallback
+        m(torch.zeros(2, m.in_features))
+    with pytest.raises(ValueError):
+        lora.add_adapter(torch.nn.Sequential(torch.nn.Linear(4, 4)), lora.LoraConfig(target_modules=["to_q"]))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pairwise_sample_optimization_b200 import lora
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(4, 6)), torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(2, 2))]
+    bucket = lora.LoRAGradBucket(params)
+    for i, p in enumerate(params):  # what the dA / dB kernels do: accumulate into the views in place
+        p.grad.add_(torch.full_like(p, float((rank + 1) * (i + 1))))
+    bucket.all_reduce()
+    want = [(1 + 2) / 2 * (i + 1) for i in range(3)]
+    ok = all(torch.allclose(p.grad, torch.full_like(p, w)) for p, w in zip(params, want))
+    ok = ok and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, bucket.views))
+    norm = bucket.clip_grad_norm_(1.0)
+    ok = ok and abs(float(torch.linalg.vector_norm(bucket.flat)) - 1.0) < 1e-4 and float(norm) > 1.0
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_single_allreduce_gloo_world2(built_lib):
+    world = 2
+    with mp.Manager() as man:
+        out = man.dict()
+        mp.spawn(_bucket_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
+
+
+def test_oracle_micro_step_on_tiny_unet_cpu():
+    torch.manual_seed(0)
+    cfg = sdxl_unet.tiny_config()
+    unet = sdxl_unet.UNet2DConditionModel(cfg)
+    wrapped = olora.oracle_add_adapter(unet, 4, 4)
+    for m in wrapped:
+        torch.nn.init.normal_(m.lora_B["default"].weight, std=0.02)
+    sched = schedules.turbo_scheduler(4)
+    batch = micro_step.synth_batch(2, 32, cfg.cross_attention_dim, 32, 3, sched.sigmas)
+    loss = micro_step.oracle_micro_step(olora, olosses, unet, batch, sched, beta=5.0, eps=0.9)
+    assert torch.isfinite(loss)
+    g = torch.cat([m.lora_A["default"].weight.grad.flatten() for m in wrapped])
+    assert torch.isfinite(g).all() and g.abs().max() > 0
+    assert all(m.base_layer.weight.grad is None for m in wrapped)
