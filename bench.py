@@ -1,26 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- PSO train pairs/sec on synthetic SDXL-shaped latents (BASELINE.json metric).
+"""bench.py -- PSO train pairs/sec on synthetic SDXL-shaped data (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--pairs B]
 
-Workload (config.workload): the online-PSO hot path of one training micro-step on DMD2-shaped data
-(4x128x128 latents, bf16), B pairs per GPU:
-    2 sampler-update launches  (distilled_step_with_logprob, sampling mode: next latents of both branches)
-    1 fused loss+grad launch   (pso_pair_loss: four log-probs + pairwise log-sigmoid loss + grad into the
-                                two policy predictions)
-    loss.backward()            (hands the fused gradients to autograd; 2 device-side no-op scale launches)
-One rank per GPU; pairs shard across ranks with no data-path collective (weak scaling).
+Workload (config.workload) = BASELINE configs[1]: SDXL-Turbo online PSO, LoRA rank 8, 512x512 (64x64 latents), bf16,
+on a random-init SDXL-ARCHITECTURE UNet (fixtures/sdxl_unet.py: 2.57 B parameters, 70 transformer blocks, 560 LoRA-wrapped
+attention projections; diffusers is not installed here).  A "step" is one training micro-step over B pairs, written as the
+reference writes it (train_online_pso_sdxl_turbo.py:771-861):
 
-Numbers:
-  value / ms_per_step : K CUDA-graph replays of the step, inputs resident in HBM, CUDA events, max over ranks.
-  roofline            : the fused loss+grad kernel, one CUDA-event pair around every launch in a second pass of
-                        K direct launches on the same (larger-than-L2) inputs; algorithmic bytes = 10*N*2 per pair.
-  e2e                 : the same step through the public API from pinned host buffers: H2D of the step's inputs,
-                        the step, D2H of the loss, every step, inside the timed region.
-  cpu_baseline        : the oracle port of the reference's PyTorch path (oracle/), timed on this box's host cores
-                        on a bounded sample (N=1, rank 0 only).
-`--impl reference` times that oracle port as the reference arm (the reference is pure Python and cannot be
-installed on the GPU box: diffusers/peft/accelerate are absent).
+    2 UNet forwards with grad (policy) + 2 adapter-disabled forwards without (frozen reference), gradient checkpointing on
+    fused PSO loss+grad kernel  (replaces 4 x turbo_step_with_logprob + the inline loss + its backward)
+    backward through the UNet   (LoRA dX / dA / dB on the tcgen05 GEMM path, accumulated into ONE flat fp32 buffer)
+    every `accum` = GA x T = 6 steps: all-reduce of the flat LoRA gradient (NCCL, N > 1), clip-norm, AdamW
+
+The 560 projections (forward + backward) and the loss run on this repo's sm_100a kernels; convolutions, norms and the
+attention core are stock torch kernels (outside the PSO hot path).  One rank per GPU, pairs sharded
+over ranks (weak scaling); the only collective is the LoRA-gradient all-reduce.
+
+Numbers on the JSON line:
+  value / ms_per_step : exactly K steps, inputs resident in HBM, CUDA events, max over ranks.
+  e2e                 : the same K steps with the step's inputs copied from pinned host memory and the loss read back,
+                        every step, inside the timed region.
+  roofline            : the dominant kernel of OURS in this step (lora_gemm_kernel, tensor-bound), timed with one CUDA-event
+                        pair around every projection call in a separate instrumented pass; peak = sustained bf16 TF/s.
+  loss_kernel_roofline / lora_gemm_large : the two kernel-level figures of BASELINE config 5 (fused loss+grad kernel at 256
+                        pairs x 128x128 latents against the HBM roofline; the fused base+LoRA GEMM at M = 18944).
+  cpu_baseline        : the oracle port of the reference's PyTorch path (fp32, same UNet architecture) on this box's host
+                        cores, one micro-step of ONE pair (bounded sample), N = 1 / rank 0 only.
+`--impl reference` times that oracle port as the reference arm (the reference is Python that needs diffusers / peft /
+accelerate and /root/reference; none exist on the GPU box -- DESIGN.md).
 """
 from __future__ import annotations
 
@@ -40,18 +48,17 @@ if ROOT not in sys.path:
 
 METRIC = "pso_train_pairs_per_sec"
 UNIT = "pairs/s"
-SHAPE = (4, 128, 128)
-N_ELEM = 4 * 128 * 128
-DMD_TS = [999, 749, 499]
-STEP_RATIO = 250
+LATENT_HW = 64
+RANK = 8
+ACCUM = 6  # gradient_accumulation_steps (2) x trained timesteps (3): turbo trainer :232
+WORKLOAD = ("BASELINE configs[1]: SDXL-Turbo online PSO micro-step (2 policy + 2 frozen-reference UNet forwards, fused PSO "
+            "loss+grad, backward), random-init SDXL-architecture UNet (2.57 B params, 560 LoRA projections), LoRA rank 8, "
+            "64x64 latents, bf16, gradient checkpointing, optimizer step every 6 micro-steps")
 
 
 # ----------------------------------------------------------------------------------------------- utilities
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
 class ClockSampler:
@@ -113,77 +120,157 @@ def measured_peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+        return {"hbm": float(p["hbm_gbs"]), "tf_burst": float(p["bf16_tflops"]),
+                "tf_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-# ----------------------------------------------------------------------------------------------- synthetic data
-def make_host_inputs(B: int, seed: int, pin: bool):
-    """Synthetic step inputs on the host: x ~ N(0,1), eps_ref ~ N(0,1),
-    eps_policy = eps_ref + 0.02 N(0,1) (keeps exp(delta) inside the clamp), timesteps uniform over the trained
-    ones, preferences uniform with 5% ties."""
-    g = torch.Generator().manual_seed(seed)
-    out = {}
-    for k in (0, 1):
-        out[f"x{k}"] = torch.randn(B, *SHAPE, generator=g).bfloat16()
-        ref = torch.randn(B, *SHAPE, generator=g)
-        out[f"ref{k}"] = ref.bfloat16()
-        out[f"pred{k}"] = (ref + 0.02 * torch.randn(B, *SHAPE, generator=g)).bfloat16()
-    tsel = torch.randint(0, len(DMD_TS), (B,), generator=g)
-    out["ts"] = torch.tensor(DMD_TS)[tsel]
-    sign = torch.randint(0, 2, (B,), generator=g).float() * 2 - 1
-    h = torch.stack([-sign, sign], 1)
-    h[torch.rand(B, generator=g) < 0.05] = 0.0
-    out["h"] = h
-    if pin:
-        out = {k: v.pin_memory() for k, v in out.items()}
-    return out
-
-
-def alphas_cumprod() -> torch.Tensor:
-    """SDXL scaled_linear schedule (diffusers scheduler config; restated, see oracle/schedules.py)."""
+def turbo_scheduler():
+    """SDXL-Turbo EulerAncestral schedule, 4 trailing steps (restated; see oracle/schedules.py for the anchored copy)."""
+    import types
     betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2
-    return torch.cumprod(1.0 - betas, dim=0)
+    ac = torch.cumprod(1.0 - betas, dim=0)
+    ts = torch.tensor([999, 749, 499, 249])
+    sig = ((1 - ac) / ac) ** 0.5
+    return types.SimpleNamespace(timesteps=ts.float(), sigmas=torch.cat([sig[ts], torch.zeros(1)]).float())
+
+
+def graph_timed(fn, reps, per_graph=2):
+    """Mean device time (ms) of one ``fn()`` call: calls captured in a CUDA graph, one event pair per replay."""
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for _ in range(per_graph):
+            fn()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record()
+        graph.replay()
+        b.record()
+    torch.cuda.synchronize()
+    return statistics.mean(a.elapsed_time(b) for a, b in evs) / per_graph
+
+
+# ----------------------------------------------------------------------------------------------- kernel-level figures
+def loss_kernel_roofline(pso, dev, peaks, ncu_traffic):
+    """Fused loss+grad kernel alone at the top of the config-5 sweep: 256 pairs of 4x128x128 bf16 latents (DMD2 shapes);
+    inputs (336 MB) exceed L2.  Algorithmic bytes = 10 N sizeof(bf16) per pair."""
+    import types
+    B, n = 256, 4 * 128 * 128
+    g = torch.Generator(device=dev).manual_seed(7)
+    mk = lambda: torch.randn(B, 4, 128, 128, device=dev, generator=g).bfloat16()
+    x0, x1, r0, r1, n0, n1 = mk(), mk(), mk(), mk(), mk(), mk()
+    p0 = (r0.float() + 0.02 * torch.randn_like(r0, dtype=torch.float32)).bfloat16()
+    p1 = (r1.float() + 0.02 * torch.randn_like(r1, dtype=torch.float32)).bfloat16()
+    ts = torch.tensor([999, 749, 499], device=dev)[torch.randint(0, 3, (B,), device=dev)]
+    h = torch.tensor([[-1.0, 1.0]], device=dev).repeat(B, 1)
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2
+    sched = types.SimpleNamespace(alphas_cumprod=torch.cumprod(1.0 - betas, dim=0).to(dev))
+
+    def call():
+        with torch.no_grad():
+            pso.pso_pair_loss(p0, p1, r0, r1, x0, x1, n0, n1, ts, ts, h, scheduler=sched, kind="dmd", step_ratio=250)
+    ms = graph_timed(call, 20, per_graph=1)
+    alg = 10 * n * 2 * B
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"kernel": "pair_loss_grad_tma_kernel<bf16,bf16,ref>", "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"],
+            "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4), "traffic": ncu_traffic,
+            "workload": "256 pairs x 4x128x128 bf16 (BASELINE config 5 top of sweep)", "algorithmic_bytes_per_launch": alg,
+            "avg_launch_us": round(ms * 1e3, 2), "peak_source": peaks["source"]}
+
+
+def lora_gemm_large(dev, peaks):
+    """Fused base+LoRA projection y = x W^T + b + t B^T (one launch) at M = 18944 (148 row tiles), K = N = 1280, r = 64."""
+    from pairwise_sample_optimization_b200 import gemm
+    M, K, N, r = 18944, 1280, 1280, 64
+    g = torch.Generator(device=dev).manual_seed(3)
+    rn = lambda *s, sc=1.0: (torch.randn(*s, device=dev, generator=g) * sc).bfloat16()
+    x, w, b, A, Bm = rn(M, K), rn(N, K, sc=K ** -0.5), rn(N), rn(r, K, sc=1 / r), rn(N, r, sc=0.05)
+    T, _ = gemm.lora_gemm(x, A)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ms = graph_timed(lambda: gemm.lora_gemm(x, w, T, Bm, bias=b, out=out), 20)
+    fl = 2.0 * M * N * (K + r)
+    ach = fl / (ms * 1e-3) / 1e12
+    return {"kernel": "lora_gemm_kernel (x W^T + b + t B^T)", "bound": "tensor", "achieved": round(ach, 1),
+            "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_burst"], 4),
+            "shape": {"M": M, "K": K, "N": N, "r": r}, "avg_launch_us": round(ms * 1e3, 2), "peak_source": peaks["source"]}
 
 
 # ----------------------------------------------------------------------------------------------- b200 arm
 def run_b200(args):
-    import types
-
     import pairwise_sample_optimization_b200 as pso
-    from pairwise_sample_optimization_b200 import _lib
+    from fixtures import micro_step, sdxl_unet
+    from pairwise_sample_optimization_b200 import _lib, lora
 
     rank, world, local = dist_env()
     if args.gpus != world and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the b200 arm")
-    _lib.lib()  # fail loudly if the CUDA library is missing
+    L = _lib.lib()  # fail loudly if the CUDA library is missing
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    B, K, W = args.pairs, args.steps, args.warmup
-    host = make_host_inputs(B, 1234 + rank, pin=True)
-    d = {k: v.to(dev) for k, v in host.items()}
-    sched = types.SimpleNamespace(alphas_cumprod=alphas_cumprod().to(dev))
-    torch.cuda.manual_seed(99 + rank)  # sampler noise comes from the default CUDA generator (graph-capturable)
-    launches_per_step = 5
+    B, K, W = args.pairs, args.steps, max(args.warmup, 3)
+    peaks = measured_peaks()
 
-    def step(t):
-        """One pass of the hot path over B pairs through the public API."""
-        ts, tp = t["ts"], t["ts"] - STEP_RATIO
-        nxt = []
-        for k in (0, 1):  # sampler update under the frozen reference policy -> stored next latents
-            xn, _ = pso.distilled_step_with_logprob(sched, t[f"ref{k}"], ts, tp, t[f"x{k}"])
-            nxt.append(xn)
-        # fresh autograd leaves every step (what a UNet forward would hand over)
-        p0, p1 = t["pred0"].detach().requires_grad_(True), t["pred1"].detach().requires_grad_(True)
-        loss = pso.pso_pair_loss(p0, p1, t["ref0"], t["ref1"], t["x0"], t["x1"], nxt[0], nxt[1],
-                                 ts, ts, t["h"], scheduler=sched, kind="dmd", beta=50.0, eps=0.1, step_ratio=STEP_RATIO)
-        loss.backward()
-        return loss, nxt, (p0.grad, p1.grad)
+    # ---- model: random-init SDXL-architecture UNet in bf16, LoRA rank 8 on to_q/to_k/to_v/to_out.0
+    torch.manual_seed(1234)  # same base weights on every rank (as a checkpoint would give)
+    cfg = sdxl_unet.tiny_config() if args.tiny else sdxl_unet.sdxl_config()
+    with torch.device(dev):
+        unet = sdxl_unet.UNet2DConditionModel(cfg)
+    unet = unet.to(torch.bfloat16).requires_grad_(False)
+    wrapped = lora.add_adapter(unet, lora.LoraConfig(r=RANK, lora_alpha=RANK))
+    for m in wrapped:  # the reference starts from B = 0; use a small non-zero B so every adapter GEMM does real work
+        torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
+    unet.set_attn_processor(lora.PSOAttnProcessor2_0())
+    unet.train()
+    unet.enable_gradient_checkpointing()  # turbo trainer :358
+    params = lora.lora_parameters(unet)
+    bucket = lora.LoRAGradBucket(params)
+    opt = torch.optim.AdamW(params, lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-4, eps=1e-8, fused=True)
+    sched = turbo_scheduler()
+    pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
+    host = micro_step.synth_batch(B, LATENT_HW, cfg.cross_attention_dim, pooled, 100 + rank, sched.sigmas, dtype=torch.bfloat16)
+    if not args.separate_forwards:
+        host = micro_step.batched_view(host)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    d = {k: v.to(dev) for k, v in host.items()}
+    fwd_bwd = micro_step.product_micro_step if args.separate_forwards else micro_step.product_micro_step_batched
+
+    def micro(batch):
+        return fwd_bwd(pso, lora, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM)
+
+    def optimizer_boundary(i):
+        if (i + 1) % ACCUM == 0:  # turbo trainer :858-861 (sync_gradients)
+            bucket.all_reduce()
+            bucket.clip_grad_norm_(1.0)
+            opt.step()
+            lora.refresh_operands(unet)
+            bucket.zero_()
+
+    graph = None
+    static_loss = None
+    launches_per_micro = 0
+
+    def step(i, batch):
+        if graph is not None:
+            graph.replay()  # the captured micro-step reads the static device batch `d`
+            loss = static_loss
+        else:
+            loss = micro(batch)
+        optimizer_boundary(i)
+        return loss
 
     def barrier():
         if world > 1:
@@ -199,111 +286,125 @@ def run_b200(args):
             return float(t.item())
         return ms
 
-    # ---- warm-up (eager), then capture one step in a CUDA graph on a side stream
-    side = torch.cuda.Stream(dev)
-    with torch.cuda.stream(side):
-        for _ in range(max(W, 3)):
-            loss, nxt, grads = step(d)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph, stream=side):
-        g_loss, g_nxt, g_grads = step(d)
-    for _ in range(max(W, 3)):
-        graph.replay()
+    if not args.no_graph:
+        # warm up eagerly on a side stream (also fills every host-side cache), then capture ONE micro-step: forward(s),
+        # fused loss+grad kernel, backward with in-place accumulation into the flat bucket.  Replays need no Python.
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(3):
+                micro(d)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        pso.check_status(dev)
+        bucket.zero_()
+        graph = torch.cuda.CUDAGraph()
+        n0 = L.psob200_launch_count()
+        with torch.cuda.graph(graph, stream=side):
+            static_loss = micro(d)
+        launches_per_micro = L.psob200_launch_count() - n0  # kernels of this library inside the captured micro-step
+        bucket.zero_()
+    for i in range(W):
+        loss = step(i, d)
+    optimizer_boundary(ACCUM - 1)  # one untimed optimizer boundary: AdamW state allocation, first NCCL all-reduce
     pso.check_status(dev)
+    bucket.zero_()
 
-    # ---- timed region: exactly K steps
+    # ---- timed region: exactly K steps, inputs resident in HBM
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launches0 = L.psob200_launch_count()
     with ClockSampler(local) as clocks:
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
         ev0.record()
-        for _ in range(K):
-            graph.replay()
+        marks[0].record()
+        for i in range(K):
+            loss = step(i, d)
+            marks[i + 1].record()
         ev1.record()
         barrier()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    ms_per_step = ms_total / K
+    launches = L.psob200_launch_count() - launches0 + K * launches_per_micro
+    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(K)]
+    ms_per_step = max_over_ranks(ev0.elapsed_time(ev1)) / K
     value = world * B / (ms_per_step * 1e-3)
-    loss_value = float(g_loss.item())
+    loss_value = float(loss.item()) * ACCUM
 
-    # ---- roofline pass: the fused loss+grad kernel alone, one event pair per launch
-    nxt = [t.detach() for t in g_nxt]
-    ts = d["ts"]
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-
-    def loss_only(tune=(0, 0)):
-        with torch.no_grad():
-            return pso.pso_pair_loss(d["pred0"].detach(), d["pred1"].detach(), d["ref0"], d["ref1"], d["x0"], d["x1"],
-                                     nxt[0], nxt[1], ts, ts, d["h"], scheduler=sched, kind="dmd", beta=50.0, eps=0.1,
-                                     step_ratio=STEP_RATIO, tune=tune)
-    # the Python/ctypes cost of one call exceeds the kernel's run time, so the launch is captured in a CUDA graph:
-    # the host then runs ahead of the GPU and each event pair brackets device time only
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            loss_only()
-    torch.cuda.synchronize()
-    kgraph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(kgraph, stream=side):
-        loss_only()
-    for _ in range(3):
-        kgraph.replay()
-    torch.cuda.synchronize()
-    for a, b in evs:
-        a.record()
-        kgraph.replay()
-        b.record()
-    torch.cuda.synchronize()
-    kern_ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
-    alg_bytes = 10 * N_ELEM * 2 * B
-    peak, peak_src = measured_peaks()
-    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    roofline = {"kernel": "pair_loss_grad_kernel<bf16,bf16,ref,vec8>", "bound": "hbm", "achieved": round(achieved, 1),
-                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": args.ncu_traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "avg_launch_us": round(kern_ms * 1e3, 2)}
-
-    # ---- end-to-end: pinned host buffers -> H2D -> step -> D2H loss, every step
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, every step
     loss_pinned = torch.empty((), dtype=torch.float32).pin_memory()
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
-    def e2e_step():
-        with torch.no_grad():
-            for k, v in host.items():
-                d[k].copy_(v, non_blocking=True)
-        loss, _, _ = step(d)
+    def e2e_step(i):
+        for k, v in host.items():
+            d[k].copy_(v, non_blocking=True)
+        loss = step(i, d)
         loss_pinned.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_pinned)
-    for _ in range(2):
-        e2e_step()
+    bucket.zero_()
+    e2e_step(0)
+    bucket.zero_()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        e2e_step()
+    for i in range(K):
+        e2e_step(i)
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     barrier()
-    e2e = {"value": round(world * B * K / (e2e_ms * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-           "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms / K, 4)}
+    e2e = {"value": round(world * B * K / (e2e_ms * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+           "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms / K, 3)}
 
+    # ---- roofline of the dominant kernel of ours (lora_gemm_kernel): instrumented pass, one event pair per projection call
+    bucket.zero_()
+    sink = []
+    lora.set_timing_sink(sink)
+    n_inst = 2
+    for i in range(n_inst):
+        micro(d)  # eager (the event pairs are host-side objects), same kernels as the captured step
+    lora.set_timing_sink(None)
+    torch.cuda.synchronize()
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in sink)
+    gemm_flops = sum(f for _, _, f, _ in sink)
+    gemm_launches = sum(n for _, _, _, n in sink)
+    ach = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"kernel": "lora_gemm_kernel (560 LoRA-wrapped projections, forward + backward)", "bound": "tensor",
+                "achieved": round(ach, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": round(ach / peaks["tf_sustained"], 4), "traffic": None,
+                "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "launches_per_step": gemm_launches // n_inst, "avg_launch_us": round(gemm_ms * 1e3 / max(gemm_launches, 1), 2),
+                "share_of_step": round(gemm_ms / n_inst / ms_per_step, 4),
+                "flops_per_step": gemm_flops / n_inst,
+                "how": "CUDA-event pair around every psob200_lora_linear_forward/backward call in 2 extra instrumented "
+                       "steps (each pair brackets 1-4 back-to-back launches of this kernel and nothing else)"}
+    bucket.zero_()
+
+    extra = {}
+    if rank == 0 and not args.no_kernel_figures:
+        extra["loss_kernel_roofline"] = loss_kernel_roofline(pso, dev, peaks, args.ncu_traffic)
+        extra["lora_gemm_large"] = lora_gemm_large(dev, peaks)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference(args.cpu_pairs, budget_s=args.cpu_seconds)
+        del unet, opt, bucket
+        torch.cuda.empty_cache()
+        cpu = cpu_reference(args, reps=1, warmup=0)
     if rank == 0:
         line = {
-            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
-            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 storage / fp32 math", "data": "synthetic",
-            "config": {"workload": "online-PSO loss hot path, SDXL-DMD2 shapes (BASELINE configs[2] per-GPU slice): "
-                                   "2 sampler-update launches + 1 fused loss+grad launch + backward hand-off; "
-                                   "LoRA GEMMs not in this step",
-                       "pairs_per_gpu": B, "latent_shape": list(SHAPE), "beta": 50.0, "eps": 0.1,
-                       "trained_timesteps": DMD_TS, "parallelism": f"dp{world} (pairs sharded, no collective)",
-                       "l2_policy": f"inputs larger than L2 ({alg_bytes / 1e6:.0f} MB touched per step vs 126 MB L2)",
-                       "timing": "CUDA-graph replay of the step; CUDA events; max over ranks"},
-            "gpu_launches": launches_per_step * K, "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(ms_per_step, 3), "ms_per_step_each": [round(v, 1) for v in per_step],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD if not args.tiny else "TINY fixture (debug run, not the benchmark)",
+                       "pairs_per_gpu_per_step": B, "latent_shape": [4, LATENT_HW, LATENT_HW], "lora_rank": RANK,
+                       "beta": 50.0, "eps": 0.1, "accum": ACCUM,
+                       "parallelism": f"dp{world} (pairs sharded; one all-reduce of the flat LoRA gradient per {ACCUM} steps)",
+                       "l2_policy": "working set larger than L2 (5.1 GB of bf16 weights streamed every forward)",
+                       "forwards": "4 separate (as the reference)" if args.separate_forwards else
+                                   "win+lose batched: 1 policy + 1 reference forward of batch 2B",
+                       "timing": ("eager launches" if args.no_graph else "micro-step replayed from one CUDA graph; optimizer "
+                                  "boundary eager") + ", CUDA events around K steps, max over ranks"},
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
             "loss": round(loss_value, 6),
         }
+        line.update(extra)
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -312,81 +413,100 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-# ----------------------------------------------------------------------------------------------- reference arm
-def _make_cpu_step(pairs: int):
-    """One micro-step of the reference's PyTorch path as restated in oracle/ (checker code, executed here only as
-    the reported CPU baseline / reference arm): two sampling-mode step calls, four scoring-mode step calls, the
-    inline loss and loss.backward(); fp32, all host threads."""
-    from oracle import losses, schedules, steps
+# ----------------------------------------------------------------------------------------------- reference arm (CPU)
+def _make_cpu_step(args, pairs):
+    """The reference's micro-step restated with the oracle pieces (oracle/ is checker code; it is executed here only as
+    the reported CPU baseline / reference arm): fp32, same UNet architecture, oracle LoRA modules (peft forward restated),
+    four step-with-logprob calls, the inline loss, autograd backward; all host threads."""
+    from fixtures import micro_step, sdxl_unet
+    from oracle import lora as olora, losses as olosses, schedules
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sched = schedules.dmd_scheduler()
-    h = make_host_inputs(pairs, 4321, pin=False)
-    x = [h["x0"].float(), h["x1"].float()]
-    ref = [h["ref0"].float(), h["ref1"].float()]
-    ts = h["ts"]
-    gen = torch.Generator().manual_seed(5)
+    cfg = sdxl_unet.tiny_config() if args.tiny else sdxl_unet.sdxl_config()
+    with torch.device("meta"):
+        unet = sdxl_unet.UNet2DConditionModel(cfg)
+    unet = unet.to_empty(device="cpu")
+    g = torch.Generator().manual_seed(0)
+    pool = torch.randn(1 << 22, generator=g) * 0.02  # cheap random init: values only need to be finite and small
+    with torch.no_grad():
+        for prm in unet.parameters():
+            n = prm.numel()
+            flat = prm.view(-1)
+            for off in range(0, n, pool.numel()):
+                m = min(pool.numel(), n - off)
+                flat[off:off + m] = pool[:m]
+            if prm.dim() == 1:
+                prm.zero_()
+        for mod in unet.modules():
+            if isinstance(mod, (torch.nn.GroupNorm, torch.nn.LayerNorm)):
+                mod.weight.fill_(1.0)
+                mod.bias.zero_()
+    unet.requires_grad_(False)
+    wrapped = olora.oracle_add_adapter(unet, RANK, RANK)
+    for m in wrapped:
+        torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
+    unet.train()
+    unet.enable_gradient_checkpointing()
+    sched = schedules.turbo_scheduler(4)
+    pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
+    batch = micro_step.synth_batch(pairs, LATENT_HW, cfg.cross_attention_dim, pooled, 100, sched.sigmas)
 
     def one():
-        pred = [h["pred0"].float().requires_grad_(True), h["pred1"].float().requires_grad_(True)]
-        nxt = []
-        with torch.no_grad():
-            for k in (0, 1):
-                xn, _ = steps.distilled_step(sched, ref[k], ts, ts - STEP_RATIO, x[k], generator=gen)
-                nxt.append(xn)
-        loss, _ = losses.online_micro_step("dmd", sched, pred, ref, x, nxt, [ts, ts], h["h"], 50.0, 0.1,
-                                           step_ratio=STEP_RATIO)
-        loss.backward()
-        return float(loss.detach())
+        loss = micro_step.oracle_micro_step(olora, olosses, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM)
+        for m in wrapped:
+            m.lora_A["default"].weight.grad = None
+            m.lora_B["default"].weight.grad = None
+        return float(loss.detach()) * ACCUM
     return one, threads
 
 
-def cpu_reference(pairs: int, budget_s: float = 15.0, min_reps: int = 3):
-    """The reference's path on the host cores (the reference itself is Python that needs diffusers/peft/accelerate
-    and /root/reference, neither of which exists on the GPU box, so the oracle port is what runs)."""
-    one, threads = _make_cpu_step(pairs)
-    one()
+def cpu_reference(args, reps, warmup):
+    pairs = args.cpu_pairs
+    one, threads = _make_cpu_step(args, pairs)
+    for _ in range(warmup):
+        one()
     times = []
-    t_start = time.perf_counter()
-    while len(times) < min_reps or (time.perf_counter() - t_start) < budget_s:
+    for _ in range(reps):
         t0 = time.perf_counter()
         one()
         times.append(time.perf_counter() - t0)
-        if len(times) >= 200:
-            break
     med = statistics.median(times)
-    return {"value": round(pairs / med, 1), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{pairs} pairs x {len(times)} reps of the same micro-step (fp32, torch {torch.__version__} CPU, "
-                      f"{torch.get_num_threads()} threads), median {med * 1e3:.1f} ms",
-            "ms_per_step": round(med * 1e3, 3)}
+    return {"value": round(pairs / med, 4), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{pairs} pair(s) x {len(times)} rep(s) of the same micro-step (fp32, torch {torch.__version__} CPU, "
+                      f"{torch.get_num_threads()} threads, no warm-up), {med:.1f} s per step",
+            "ms_per_step": round(med * 1e3, 1)}
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    K, W = args.steps, args.warmup
+    K, W = args.steps, min(args.warmup, 1)
     pairs = args.cpu_pairs
-    one, threads = _make_cpu_step(pairs)
+    one, threads = _make_cpu_step(args, pairs)
+    t_begin = time.perf_counter()
     res = None
-    for _ in range(max(W, 1)):  # each "step" is one bounded micro-step of `pairs` pairs
-        one()
-    t0 = time.perf_counter()
-    for _ in range(K):
+    for _ in range(W):
         res = one()
-    dt = time.perf_counter() - t0
-    ms = dt / K * 1e3
+    times = []
+    for _ in range(K):  # each step: one micro-step over `pairs` pair(s); bounded by --ref-budget-seconds
+        t0 = time.perf_counter()
+        res = one()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > args.ref_budget_seconds:
+            break
+    ms = statistics.mean(times) * 1e3
     value = pairs / (ms * 1e-3)
-    sample = (f"{pairs} pairs per step (bounded sample of the {args.pairs}-pair workload), fp32, torch "
-              f"{torch.__version__} CPU, {torch.get_num_threads()} threads")
-    line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": K, "warmup": max(W, 1), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "online-PSO loss hot path, SDXL-DMD2 shapes: oracle port of the reference's "
-                                   "PyTorch path on host cores (2 sampling steps, 4 scoring steps, inline loss, backward)",
-                       "pairs_per_step": pairs, "latent_shape": list(SHAPE), "beta": 50.0, "eps": 0.1},
-            "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    sample = (f"{pairs} pair(s) per step (bounded sample of the {args.pairs}-pair micro-step), fp32, torch {torch.__version__} CPU, "
+              f"{torch.get_num_threads()} threads; {len(times)} of the {K} requested steps fit the {args.ref_budget_seconds:.0f} s budget")
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(times), "steps_requested": K, "warmup": W, "ms_per_step": round(ms, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD + " -- oracle port of the reference's PyTorch path on the host cores",
+                       "pairs_per_step": pairs, "latent_shape": [4, LATENT_HW, LATENT_HW], "lora_rank": RANK, "beta": 50.0,
+                       "eps": 0.1},
+            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "loss": round(res, 6)}
     print(json.dumps(line), flush=True)
 
@@ -394,15 +514,19 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step")
-    ap.add_argument("--cpu-pairs", type=int, default=16, help="pairs in the bounded CPU sample")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--pairs", type=int, default=4, help="pairs per GPU per micro-step (train.batch_size of the shipped recipe)")
+    ap.add_argument("--cpu-pairs", type=int, default=1, help="pairs in the bounded CPU sample")
+    ap.add_argument("--ref-budget-seconds", type=float, default=200.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-figures", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the micro-step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--separate-forwards", action="store_true", help="4 UNet forwards of batch B instead of 2 of batch 2B")
+    ap.add_argument("--tiny", action="store_true", help="debug: the 32/64-channel fixture instead of the SDXL architecture")
     ap.add_argument("--ncu-traffic", type=float, default=None,
-                    help="dram bytes per launch of the dominant kernel from the committed ncu --set full capture")
+                    help="dram bytes per launch of the loss kernel from the committed ncu --set full capture")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -57,6 +57,35 @@ def product_micro_step(pso, lora, unet, batch, sched, *, beta=50.0, eps=0.1, los
     return loss
 
 
+def batched_view(batch):
+    """Both branches stacked along the batch dimension (win rows then lose rows): the two policy forwards become one of
+    batch 2B, likewise the two frozen-reference forwards.  Per-sample results are unchanged (the UNet has no
+    cross-sample operation); the reference runs them separately (turbo :775-787)."""
+    cat2 = lambda a, b: torch.cat([a, b], dim=0).contiguous()
+    out = dict(batch)
+    out["input_latents_01"] = cat2(batch["input_latents_0"], batch["input_latents_1"])
+    for k in ("prompt_embeds", "text_embeds", "time_ids", "timesteps"):
+        out[k + "_01"] = cat2(batch[k], batch[k])
+    return out
+
+
+def product_micro_step_batched(pso, lora, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0):
+    """Same micro-step with ONE policy forward and ONE frozen-reference forward of batch 2B (``batched_view``)."""
+    B = batch["latents_0"].shape[0]
+    cond = {"text_embeds": batch["text_embeds_01"], "time_ids": batch["time_ids_01"].to(batch["input_latents_01"].dtype)}
+    pol = unet(batch["input_latents_01"], batch["timesteps_01"], batch["prompt_embeds_01"], added_cond_kwargs=cond).sample
+    lora.disable_adapters(unet)
+    with torch.no_grad():
+        ref = unet(batch["input_latents_01"], batch["timesteps_01"], batch["prompt_embeds_01"], added_cond_kwargs=cond).sample
+    lora.enable_adapters(unet)
+    ts = batch["timesteps"]
+    loss = pso.pso_pair_loss(pol[:B], pol[B:], ref[:B], ref[B:], batch["latents_0"], batch["latents_1"],
+                             batch["next_latents_0"], batch["next_latents_1"], ts, ts, batch["human_prefer"],
+                             scheduler=sched, kind="turbo", beta=beta, eps=eps, loss_scale=loss_scale)
+    loss.backward()
+    return loss
+
+
 def oracle_micro_step(olora, olosses, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0):
     """The reference's flow restated with the oracle pieces (CPU): same four forwards, four step-with-logprob calls,
     inline loss, autograd backward."""

@@ -271,7 +271,7 @@ class UNet2DConditionModel(nn.Module):
 
     def _run(self, module, *args):
         if self.gradient_checkpointing and self.training and torch.is_grad_enabled():
-            return checkpoint(module, *args, use_reentrant=False)
+            return checkpoint(module, *args, use_reentrant=False, preserve_rng_state=False)
         return module(*args)
 
     def forward(self, sample, timestep, encoder_hidden_states, added_cond_kwargs=None, return_dict=True, **_):

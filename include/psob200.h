@@ -97,6 +97,8 @@ PSOB200_API const char* psob200_strerror(int rc);
 PSOB200_API const char* psob200_last_error_detail(void);
 /* Number of SMs / compute capability the library was queried with; -1 if no device. */
 PSOB200_API int psob200_device_sm_count(void);
+/* Kernels this library has launched successfully in this process (monotonic; for launch accounting). */
+PSOB200_API long long psob200_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
  * Workspace for the pair-loss kernels: >= psob200_pair_loss_workspace_bytes(B) bytes,

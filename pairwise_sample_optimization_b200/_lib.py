@@ -98,6 +98,7 @@ SIGNATURES = {
     "psob200_strerror": (C.c_char_p, [C.c_int]),
     "psob200_last_error_detail": (C.c_char_p, []),
     "psob200_device_sm_count": (C.c_int, []),
+    "psob200_launch_count": (C.c_longlong, []),
     "psob200_struct_size": (C.c_size_t, [C.c_int]),
     "psob200_pair_loss_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "psob200_online_pso_loss_grad": (C.c_int, [C.POINTER(Schedule), C.POINTER(OnlinePsoArgs), _vp]),

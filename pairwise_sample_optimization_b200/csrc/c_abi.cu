@@ -1,6 +1,7 @@
 // Library-level entry points of the C ABI (include/psob200.h).
 #include "common.cuh"
 
+#include <atomic>
 #include <cstdio>
 
 namespace psob200 {
@@ -8,7 +9,11 @@ static thread_local char g_error_detail[256] = "";
 void set_error_detail(const char* where, cudaError_t e) {
   std::snprintf(g_error_detail, sizeof(g_error_detail), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace psob200
+
+extern "C" long long psob200_launch_count(void) { return psob200::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* psob200_last_error_detail(void) { return psob200::g_error_detail; }
 

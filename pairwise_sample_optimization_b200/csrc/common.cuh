@@ -222,10 +222,15 @@ __device__ __forceinline__ StepCoef resolve_coef(const psob200_schedule& sc, con
 // ---------------------------------------------------------------------------------------------
 // Records what CUDA said about the last failed call of this thread (psob200_last_error_detail()).
 void set_error_detail(const char* where, cudaError_t e);
+// Bumps the library's launch counter (psob200_launch_count()).
+void count_launch();
 // Consumes the sticky-free last error; returns PSOB200_ERR_LAUNCH (and records the detail) if there was one.
 inline int consume_launch_error(const char* where, cudaError_t e) {
   if (e == cudaSuccess) e = cudaPeekAtLastError();
-  if (e == cudaSuccess) return PSOB200_OK;
+  if (e == cudaSuccess) {
+    count_launch();
+    return PSOB200_OK;
+  }
   set_error_detail(where, e);
   cudaGetLastError();
   return PSOB200_ERR_LAUNCH;

@@ -43,6 +43,16 @@ class LoraConfig:
     lora_dropout: float = 0.0
 
 
+# When a list is installed here, every projection call appends (start_event, end_event, flops, launches): the
+# instrumented pass bench.py uses to attribute device time to the GEMM kernels.  None in normal operation.
+_TIMING = None
+
+
+def set_timing_sink(sink) -> None:
+    global _TIMING
+    _TIMING = sink
+
+
 def _ceil8(n: int) -> int:
     return (n + 7) // 8 * 8
 
@@ -103,14 +113,22 @@ class LoRALinear(nn.Module):
             return p.detach()
         key = (which, dtype)
         hit = self._op_cache.get(key)
-        if hit is not None and hit[0] == p._version and hit[1] == p.data_ptr():
-            return hit[2]
         cols = p.shape[1]
-        buf = torch.zeros(p.shape[0], _ceil8(cols), dtype=dtype, device=p.device)
-        buf[:, :cols].copy_(p.detach())
-        view = buf[:, :cols]
-        self._op_cache[key] = (p._version, p.data_ptr(), view)
-        return view
+        if hit is None or hit[1] != p.data_ptr() or hit[2].device != p.device:
+            buf = torch.zeros(p.shape[0], _ceil8(cols), dtype=dtype, device=p.device)
+            hit = [-1, p.data_ptr(), buf[:, :cols]]
+            self._op_cache[key] = hit
+        if hit[0] != p._version:  # refreshed IN PLACE: the buffer address is stable (CUDA-graph friendly)
+            hit[2].copy_(p.detach())
+            hit[0] = p._version
+        return hit[2]
+
+    def refresh_operands(self) -> None:
+        """Bring the 16-bit operand copies up to date with the parameters (call after an optimizer step when the
+        forward is replayed from a CUDA graph, where this Python code does not run)."""
+        dtype = self.base_layer.weight.dtype
+        self._operand("a", dtype)
+        self._operand("b", dtype)
 
     def forward(self, x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
         n = self.active_adapter
@@ -165,8 +183,16 @@ class _LoraLinearFn(torch.autograd.Function):
             if want_wgrad:
                 tt = torch.empty(r, _ceil8(M), dtype=dtype, device=dev)
                 a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
+        if _TIMING is not None:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         rc = _lib.lib().psob200_lora_linear_forward(C.byref(a), _lib.current_stream(dev))
         _lib.check(rc, "psob200_lora_linear_forward")
+        if _TIMING is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            fl = 2.0 * M * K * N + (2.0 * M * r * (K + N) if enabled else 0.0)
+            _TIMING.append((ev0, ev1, fl, 2 if enabled else 1))
         ctx.layer, ctx.enabled, ctx.x_shape, ctx.x_dtype, ctx.want_wgrad = layer, enabled, x.shape, x.dtype, want_wgrad
         ctx.save_for_backward(x2, tt)
         return y.view(*x.shape[:-1], N)
@@ -214,8 +240,24 @@ class _LoraLinearFn(torch.autograd.Function):
                 a.d_lora_b, a.ld_db = gb.data_ptr(), gb.stride(0)
                 keep += [ut, ga, gb]
         if dx is not None or (ctx.enabled and a.d_lora_a):
+            if _TIMING is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
             rc = _lib.lib().psob200_lora_linear_backward(C.byref(a), _lib.current_stream(dev))
             _lib.check(rc, "psob200_lora_linear_backward")
+            if _TIMING is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                wg = bool(ctx.enabled and a.d_lora_a)
+                fl = (2.0 * M * K * N if dx is not None else 0.0)
+                n_l = 1 if dx is not None else 0
+                if ctx.enabled and (dx is not None or wg):
+                    fl += 2.0 * M * N * r + (2.0 * M * r * K if dx is not None else 0.0)
+                    n_l += 1
+                if wg:
+                    fl += 2.0 * M * r * K + 2.0 * M * N * r
+                    n_l += 2
+                _TIMING.append((ev0, ev1, fl, n_l))
         del keep
         if dx is not None:
             dx = dx.view(ctx.x_shape)
@@ -271,6 +313,11 @@ def disable_adapters(model: nn.Module) -> None:
 def enable_adapters(model: nn.Module) -> None:
     for m in lora_layers(model):
         m.enable_adapters(True)
+
+
+def refresh_operands(model: nn.Module) -> None:
+    for m in lora_layers(model):
+        m.refresh_operands()
 
 
 def lora_parameters(model: nn.Module):
