@@ -17,7 +17,6 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-import bench  # noqa: E402
 import pairwise_sample_optimization_b200 as pso  # noqa: E402
 from pairwise_sample_optimization_b200 import _lib, runtime, step_ops  # noqa: E402
 
@@ -63,9 +62,10 @@ def main():
     x0, x1, r0, r1, n0, n1 = mk(), mk(), mk(), mk(), mk(), mk()
     p0 = (r0.float() + 0.02 * torch.randn_like(r0, dtype=torch.float32)).to(dt)
     p1 = (r1.float() + 0.02 * torch.randn_like(r1, dtype=torch.float32)).to(dt)
-    ts = torch.tensor(bench.DMD_TS, device=dev)[torch.randint(0, 3, (B,), device=dev)]
+    ts = torch.tensor([999, 749, 499], device=dev)[torch.randint(0, 3, (B,), device=dev)]
     h = torch.tensor([[-1.0, 1.0]], device=dev).repeat(B, 1)
-    sched = types.SimpleNamespace(alphas_cumprod=bench.alphas_cumprod().to(dev))
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2
+    sched = types.SimpleNamespace(alphas_cumprod=torch.cumprod(1.0 - betas, dim=0).to(dev))
 
     def loss(tune=(0, 0)):
         with torch.no_grad():
