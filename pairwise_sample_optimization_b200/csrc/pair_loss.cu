@@ -217,7 +217,8 @@ __device__ __forceinline__ void residual8(const float (&vx)[8], const float (&vn
 
 }  // namespace psob200
 
-#include "pair_loss_tma.cuh"  // fast path: persistent clusters + TMA ring
+#include "pair_loss_tma.cuh"   // second design: persistent clusters + TMA ring, residuals in registers
+#include "pair_loss_tmem.cuh"  // fast path: residuals in tensor memory, per-thread cp.async ring
 
 namespace psob200 {
 
@@ -388,15 +389,62 @@ static int launch_pair_tma_inst(const PairKernelArgs& ka, int cluster, int sm_co
   return consume_launch_error("launch pair_loss_grad_tma_kernel", e);
 }
 
-// tune_threads: 0 = heuristics (the persistent TMA kernel, 512 threads); > 0 = the general (LDG) kernel with that
-//               many threads.  tune_cluster: 0 = heuristics.
+template <typename TP, typename TL, bool HAS_REF>
+static int launch_pair_tmem_inst(const PairKernelArgs& ka, int cluster, int sm_count, cudaStream_t stream) {
+  auto kern = pair_loss_grad_tmem_kernel<TP, TL, HAS_REF>;
+  using Cfg = V3Cfg<TP, TL, HAS_REF>;
+  constexpr size_t smem = Cfg::kSmemBytes;
+  static std::atomic<size_t> configured{48 * 1024};
+  static std::atomic<int> active[4];
+  const int rc = ensure_dynamic_smem(kern, smem, configured, "configure pair_loss_grad_tmem_kernel");
+  if (rc != PSOB200_OK) return rc;
+  long long clusters = max_active_clusters(kern, Cfg::kThreads, smem, cluster, sm_count, 1, active);
+  if (clusters > ka.B) clusters = ka.B;  // persistent: every cluster loops over pairs cluster_id, +clusters, ...
+  const cudaError_t e = launch_cluster(kern, dim3((unsigned)(clusters * cluster)), dim3(Cfg::kThreads), smem, stream,
+                                       (unsigned)cluster, ka);
+  return consume_launch_error("launch pair_loss_grad_tmem_kernel", e);
+}
+
+// Cluster size for the tensor-memory kernel: the smallest that fits a pair's residuals (at most kMaxIters/2 chunk
+// iterations per branch per CTA), widened for small batches so that more SMs share a pair.  0 = does not fit.
+template <typename TP, typename TL, bool HAS_REF>
+static int tmem_cluster_for(long long nchunk, long long B, int sm_count, int tune_cluster) {
+  using Cfg = V3Cfg<TP, TL, HAS_REF>;
+  const long long cap = (long long)(Cfg::kMaxIters / 2) * Cfg::kThreads;  // chunks per branch per CTA
+  if (tune_cluster != 0) return (nchunk + tune_cluster - 1) / tune_cluster <= cap ? tune_cluster : 0;
+  int c = 1;
+  while (c < kMaxCluster && (nchunk + c - 1) / c > cap) c <<= 1;
+  if ((nchunk + c - 1) / c > cap) return 0;
+  while (c < kMaxCluster && B * c * 2 <= sm_count && nchunk / (c * 2) >= Cfg::kThreads) c <<= 1;
+  return c;
+}
+
+// tune_threads: 0 = heuristics (the tensor-memory kernel); 1 = the TMA-ring kernel (second design, kept for A/B
+//               measurements); >= 32 = the general (LDG) kernel with that many threads.  tune_cluster: 0 = heuristics.
 static int launch_pair(PairKernelArgs ka, bool has_ref, int32_t pred_dtype, int32_t latent_dtype, bool vec_ok,
                        int tune_threads, int tune_cluster, int sm_count, cudaStream_t stream) {
   if (tune_cluster != 0 && tune_cluster != 1 && tune_cluster != 2 && tune_cluster != 4 && tune_cluster != 8)
     return PSOB200_ERR_INVALID_ARG;
   if (tune_threads < 0) return PSOB200_ERR_INVALID_ARG;
-  // ---- fast path: persistent TMA ring, <= 2 * kTmaThreads chunks per branch per CTA
+  // ---- fast path: residuals in tensor memory
   if (vec_ok && tune_threads == 0) {
+    const long long nchunk = ka.N / 8;
+    const int rc = dispatch2(pred_dtype, latent_dtype, [&](auto tp, auto tl) -> int {
+      using TP = decltype(tp);
+      using TL = decltype(tl);
+      const int cluster = has_ref ? tmem_cluster_for<TP, TL, true>(nchunk, ka.B, sm_count, tune_cluster)
+                                  : tmem_cluster_for<TP, TL, false>(nchunk, ka.B, sm_count, tune_cluster);
+      if (cluster == 0) return 1;  // does not fit: fall through to the general path
+      PairKernelArgs k2 = ka;
+      k2.chunks_per_cta = (int)((nchunk + cluster - 1) / cluster);
+      return has_ref ? launch_pair_tmem_inst<TP, TL, true>(k2, cluster, sm_count, stream)
+                     : launch_pair_tmem_inst<TP, TL, false>(k2, cluster, sm_count, stream);
+    });
+    if (rc != 1) return rc;
+    if (tune_cluster != 0) return PSOB200_ERR_SHAPE;
+  }
+  // ---- second design: persistent TMA ring, <= 2 * kTmaThreads chunks per branch per CTA
+  if (vec_ok && tune_threads == 1) {
     const long long nchunk = ka.N / 8;
     int cluster = tune_cluster;
     if (cluster == 0) {
@@ -420,7 +468,7 @@ static int launch_pair(PairKernelArgs ka, bool has_ref, int32_t pred_dtype, int3
   // ---- general path
   const int W = vec_ok ? 8 : 1;
   const long long nchunk = (ka.N + W - 1) / W;
-  const int threads = tune_threads > 0 ? tune_threads : 256;
+  const int threads = tune_threads >= 32 ? tune_threads : 256;
   if (threads > kMaxThreads || threads < 32 || (threads & 31)) return PSOB200_ERR_INVALID_ARG;
   // cluster size: keep the fp32 residual slab <= 64 KB per CTA (>= 3 CTAs per SM) when possible,
   // and spread small batches over more SMs for latency.

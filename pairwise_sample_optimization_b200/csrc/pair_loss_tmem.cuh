@@ -1,0 +1,292 @@
+// Fast path of the fused pair-loss kernel, third design: residuals parked in TENSOR MEMORY.
+//
+// The two-pass structure (all 8N inputs of a pair must be reduced before any of its 2N gradient elements can be
+// written) needs 2N fp32 residuals of on-chip storage per pair.  Registers force few warps per SM and shared memory
+// competes with the load pipeline (profiles/r01_pair_loss.md: 16 warps/SM, SM-bound at 45-57 % of HBM).  Blackwell has
+// a third on-chip memory that this kernel otherwise leaves idle: 256 KB of tensor memory per SM.  Every thread parks
+// its residuals there with tcgen05.st (one instruction per 8-element chunk) and reads them back with tcgen05.ld for
+// the gradient pass.  That frees
+//   * the register file: 1024 threads per SM at <= 64 registers (32 warps hide the latencies), and
+//   * all of shared memory for a deep cp.async ring (192 KB in flight per SM) in which every thread fetches and later
+//     reads ONLY ITS OWN 16-byte pieces: no mbarrier, no producer role, no block barrier on the load path
+//     (cp.async.wait_group is per thread),
+// and shrinks the cluster: a pair of 4x128x128 latents fits two CTAs (148 SMs busy instead of 120), 4x64x64 fits one.
+//
+// Per pair: pass 1 (stream, residuals -> TMEM, 6 partial sums), block (+ cluster) reduction, the pair's scalar
+// function on one thread, pass 2 (TMEM -> g*r -> global).  The ring runs ahead across pairs, so HBM stays busy while a
+// pair is being finished.  Deterministic: fixed summation order, no atomics on the data path.
+//
+// Included by pair_loss.cu (needs PairKernelArgs, PairEntry, pair_scalar_function_fast and the shared helpers).
+#pragma once
+
+namespace psob200 {
+
+constexpr int kV3SmemRing = 192 * 1024;
+constexpr int kV3TmemCols = 512;
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns of tensor memory <-> 8 registers per thread.  SASS: STTM / LDTM
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <typename TP, typename TL, bool HAS_REF>
+struct V3Cfg {
+  static constexpr int kNPred = HAS_REF ? 2 : 1;
+  static constexpr int kBytesL = 8 * (int)sizeof(TL);  // one 8-element chunk of one latent tensor
+  static constexpr int kBytesP = 8 * (int)sizeof(TP);
+  static constexpr int kThreadBytes = 2 * kBytesL + kNPred * kBytesP;  // bf16/bf16: 64, fp32 preds + bf16 latents: 96
+  static constexpr int kThreads = kThreadBytes <= 64 ? 1024 : 512;
+  static constexpr int kSlotBytes = kThreads * kThreadBytes;
+  static constexpr int kDepthRaw = kV3SmemRing / kSlotBytes;
+  static constexpr int kDepth = kDepthRaw > 4 ? 4 : kDepthRaw;  // ring slots = chunk-iterations in flight
+  static constexpr int kSmemBytes = kDepth * kSlotBytes;
+  static constexpr int kWarpGroups = kThreads / 128;
+  static constexpr int kMaxIters = kV3TmemCols / (8 * kWarpGroups);  // chunk-iterations per pair that fit in TMEM
+  // tensor offsets inside a ring slot ([tensor][16-byte piece][thread])
+  static constexpr int kOffX = 0;
+  static constexpr int kOffXn = kThreads * kBytesL;
+  static constexpr int kOffP = 2 * kThreads * kBytesL;
+  static constexpr int kOffR = kOffP + kThreads * kBytesP;
+};
+
+// this thread's 8 elements of one tensor out of a ring slot (pieces of 16 bytes, thread-interleaved: conflict-free)
+template <typename T, int kThreads>
+__device__ __forceinline__ void lds_chunk(const unsigned char* sub, int tid, float (&v)[8]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 a = reinterpret_cast<const float4*>(sub)[tid], b = reinterpret_cast<const float4*>(sub)[kThreads + tid];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    typename Vec8<T>::Raw raw{reinterpret_cast<const uint4*>(sub)[tid]};
+    Vec8<T>::decode(raw, v);
+  }
+}
+
+template <typename T, int kThreads>
+__device__ __forceinline__ void cp_chunk(unsigned char* sub, int tid, const T* src, uint32_t src_bytes) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sub) + (uint32_t)tid * 16u;
+  cp_async_16(dst, src, src_bytes);
+  if constexpr (sizeof(T) == 4) cp_async_16(dst + kThreads * 16u, reinterpret_cast<const unsigned char*>(src) + 16, src_bytes);
+}
+
+template <typename TP, typename TL, bool HAS_REF>
+__global__ void __launch_bounds__(V3Cfg<TP, TL, HAS_REF>::kThreads, 1) pair_loss_grad_tmem_kernel(const PairKernelArgs a) {
+  using Cfg = V3Cfg<TP, TL, HAS_REF>;
+  constexpr int T = Cfg::kThreads;
+  constexpr int D = Cfg::kDepth;
+  constexpr int kWarps = T / 32;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned C = cluster.num_blocks();
+  const unsigned rank = cluster.block_rank();
+  const long long cluster_id = blockIdx.x / C, n_clusters = gridDim.x / C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ float s_warp[kWarps][8];
+  __shared__ __align__(16) float s_xch[2][kMaxCluster][8];  // CTA partial sums of the cluster, double-buffered by pair parity
+  __shared__ float s_g[2];
+  __shared__ PairEntry s_tab[2][kTabPairs];
+  __shared__ uint32_t s_tmem_base;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(&s_tmem_base)),
+                 "n"(kV3TmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // this thread's TMEM window: lanes 32*(warp%4).., columns of its warp group
+  const uint32_t tmem_mine = s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+
+  // ---- this CTA's slab of every sample: chunks [cbeg, cend) of each branch; Ib chunk-iterations per branch
+  const int cpc = a.chunks_per_cta;
+  const long long nchunk = a.N / 8;
+  const long long cbeg = (long long)rank * cpc;
+  const long long cend = (cbeg + cpc < nchunk) ? cbeg + cpc : nchunk;
+  const int Ib = (cpc + T - 1) / T;  // host guarantees 2*Ib <= kMaxIters
+  const int I = 2 * Ib;
+  const uint32_t col0 = (uint32_t)((warp >> 2) * I * 8);
+  const long long my_pairs = cluster_id < a.B ? (a.B - cluster_id + n_clusters - 1) / n_clusters : 0;
+  const long long total = my_pairs * I;  // chunk-iterations of this CTA
+
+  // start this thread's copies of chunk-iteration g into ring slot g % D (always commits a group)
+  auto issue = [&](long long g) {
+    if (g < total) {
+      const long long it = g / I;
+      const int i = (int)(g - it * I);
+      const int k = i >= Ib ? 1 : 0;
+      const long long c = cbeg + (long long)(i - k * Ib) * T + tid;
+      const uint32_t nb = c < cend ? 16u : 0u;  // beyond the slab: zero-fill (src-size 0), address clamped
+      const long long off = (c < cend ? c : cbeg) * 8;
+      const long long pair = cluster_id + it * n_clusters;
+      unsigned char* slot = ring + (size_t)(g % D) * Cfg::kSlotBytes;
+      cp_chunk<TL, T>(slot + Cfg::kOffX, tid, reinterpret_cast<const TL*>(a.x[k]) + pair * a.stride[2][k] + off, nb);
+      cp_chunk<TL, T>(slot + Cfg::kOffXn, tid, reinterpret_cast<const TL*>(a.xn[k]) + pair * a.stride[3][k] + off, nb);
+      cp_chunk<TP, T>(slot + Cfg::kOffP, tid, reinterpret_cast<const TP*>(a.pred[k]) + pair * a.stride[0][k] + off, nb);
+      if constexpr (HAS_REF)
+        cp_chunk<TP, T>(slot + Cfg::kOffR, tid, reinterpret_cast<const TP*>(a.ref[k]) + pair * a.stride[1][k] + off, nb);
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int d = 0; d < D; ++d) issue(d);
+
+  double loss_acc = 0.0;  // rank 0, thread 0
+  long long g = 0;
+  for (long long it = 0; it < my_pairs; ++it) {
+    const long long pair = cluster_id + it * n_clusters;
+    const int tb = (int)((it / kTabPairs) & 1), slot_t = (int)(it % kTabPairs);
+    if (slot_t == 0) {  // per-pair scalars of the next kTabPairs pairs, resolved in parallel (fp64, table look-ups)
+      __syncthreads();
+      if (tid < 2 * kTabPairs && it + (tid >> 1) < my_pairs) {
+        const long long p = pair + (long long)(tid >> 1) * n_clusters;
+        const int k = tid & 1;
+        resolve_pair_coefs(a, p, k, &s_tab[tb][tid >> 1].c[k]);
+        s_tab[tb][tid >> 1].h[k] = a.mode == kModeOnline ? a.human_prefer[p * 2 + k] : 0.f;
+      }
+      __syncthreads();
+    }
+    const PairEntry& ent = s_tab[tb][slot_t];
+
+    // ------------------------------------------------------------------ pass 1
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int i = 0; i < I; ++i, ++g) {
+      const int k = i >= Ib ? 1 : 0;
+      cp_async_wait<D - 1>();  // this thread's pieces of chunk-iteration g have landed
+      const unsigned char* slot = ring + (size_t)(g % D) * Cfg::kSlotBytes;
+      float vx[8], vn[8], vp[8], vr[8], r[8];
+      lds_chunk<TL, T>(slot + Cfg::kOffX, tid, vx);
+      lds_chunk<TL, T>(slot + Cfg::kOffXn, tid, vn);
+      lds_chunk<TP, T>(slot + Cfg::kOffP, tid, vp);
+      if constexpr (HAS_REF) lds_chunk<TP, T>(slot + Cfg::kOffR, tid, vr);
+      float s_t = 0.f, s_r = 0.f, s_d = 0.f;
+      residual8<HAS_REF>(vx, vn, vp, vr, ent.c[k].k, ent.c[k].a, r, s_t, s_r, s_d);  // zero-filled chunks contribute 0
+      issue(g + D);  // refill the slot just drained (its values are in registers)
+      tmem_st8(tmem_mine + col0 + (uint32_t)i * 8u, r);
+      if (k == 0) { acc[0] += s_t; acc[1] += s_r; acc[2] += s_d; }
+      else        { acc[3] += s_t; acc[4] += s_r; acc[5] += s_d; }
+    }
+    // ------------------------------------------------------------------ reduce: warp -> CTA -> cluster
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) s_warp[warp][j] = acc[j];
+    }
+    tmem_st_wait();
+    __syncthreads();
+    const int par = (int)(it & 1);
+    if (warp == 0) {
+      float part[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) part[j] = warp_sum(lane < kWarps ? s_warp[lane][j] : 0.f);
+      if (C == 1) {
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 6; ++j) s_xch[par][0][j] = part[j];
+        }
+      } else if (lane < (int)C) {  // lane r pushes this CTA's partials into CTA r
+        float* dst = cluster.map_shared_rank(&s_xch[par][rank][0], lane);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dst[j] = part[j];
+      }
+    }
+    if (C > 1) cluster.sync();  // release/acquire: every CTA's partials are visible everywhere
+    if (tid == 0) {
+      float S[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (unsigned r = 0; r < C; ++r)  // rank order: identical in all CTAs
+#pragma unroll
+        for (int j = 0; j < 6; ++j) S[j] += s_xch[par][r][j];
+      float g0, g1, st[8];
+      const float per = pair_scalar_function_fast(a, S, ent, g0, g1, st);
+      s_g[0] = g0;
+      s_g[1] = g1;
+      if (rank == 0) {
+        loss_acc += (double)per;
+        if (a.stats != nullptr) {
+          float4* dst = reinterpret_cast<float4*>(a.stats + pair * 8);
+          dst[0] = make_float4(st[0], st[1], st[2], st[3]);
+          dst[1] = make_float4(st[4], st[5], st[6], st[7]);
+        }
+      }
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------ pass 2: grad = g_k * r from tensor memory
+    const float g0 = s_g[0], g1 = s_g[1];
+#pragma unroll 1
+    for (int i = 0; i < I; ++i) {
+      const int k = i >= Ib ? 1 : 0;
+      float r[8];
+      tmem_ld8(tmem_mine + col0 + (uint32_t)i * 8u, r);
+      const long long c = cbeg + (long long)(i - k * Ib) * T + tid;
+      if (c < cend) {
+        const float gk = k == 0 ? g0 : g1;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = gk * r[j];
+        Vec8<TP>::store(reinterpret_cast<TP*>(a.grad[k]) + pair * a.N + c * 8, o);
+      }
+    }
+    // s_g / s_warp are rewritten only after the next pair's first __syncthreads: every thread has read them by then
+  }
+  cp_async_wait<0>();
+
+  // ---- mean over pairs: one ticket per cluster; the last cluster sums the per-cluster sums in a fixed order
+  if (rank == 0 && warp == 0 && my_pairs > 0) {
+    unsigned ticket = 0;
+    if (lane == 0) {
+      reinterpret_cast<volatile float*>(a.pair_loss)[cluster_id] = (float)loss_acc;
+      __threadfence();
+      ticket = atomicAdd(a.counter, 1u);
+    }
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    const long long active = a.B < n_clusters ? a.B : n_clusters;
+    if (ticket == (unsigned)(active - 1)) {
+      __threadfence();
+      double s = 0.0;
+      for (long long i = lane; i < active; i += 32) s += (double)__ldcg(a.pair_loss + i);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) {
+        a.loss[0] = (float)((double)a.loss_scale * s / (double)a.B);
+        *a.counter = 0u;
+      }
+    }
+  }
+  if (C > 1) cluster.sync();  // nobody leaves while a neighbour may still write its shared memory
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem_base), "n"(kV3TmemCols) : "memory");
+  }
+}
+
+}  // namespace psob200

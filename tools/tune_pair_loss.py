@@ -89,8 +89,8 @@ def main():
     print(f"pairs={B} latent=4x{args.hw}x{args.hw} dtype={args.dtype} algorithmic bytes={alg / 1e6:.1f} MB")
     print("threads cluster      us    GB/s")
     res = []
-    # threads == 0 selects the persistent TMA-ring kernel, > 0 the general LDG kernel
-    for threads in (0, 256, 512):
+    # threads == 0: tensor-memory kernel, 1: TMA-ring kernel, >= 32: general LDG kernel
+    for threads in (0, 1, 256):
         for cluster in (1, 2, 4, 8):
             try:
                 us = timed(lambda: loss((threads, cluster)), args.reps)
