@@ -52,6 +52,27 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Residual and partial sums in the "u form": with u = eps_pol - eps_ref the reference-branch residual is r + a*u, so
+//   S_ref = S_pol + D,   D = a * (2 * sum(u r) + a * sum(u^2))
+// needs only sum(r^2), sum(u r), sum(u^2): 6 instead of 9 flops per element, and D is still formed from the (small)
+// prediction difference itself, never by cancelling the two large sums.
+template <bool HAS_REF>
+__device__ __forceinline__ void residual8_u(const float (&vx)[8], const float (&vn)[8], const float (&vp)[8],
+                                            const float (&vr)[8], float kx, float ca, float (&r)[8], float& s_t,
+                                            float& s_ur, float& s_uu) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float rt = fmaf(-ca, vp[i], fmaf(-kx, vx[i], vn[i]));
+    r[i] = rt;
+    s_t = fmaf(rt, rt, s_t);
+    if constexpr (HAS_REF) {
+      const float u = vp[i] - vr[i];
+      s_ur = fmaf(u, rt, s_ur);
+      s_uu = fmaf(u, u, s_uu);
+    }
+  }
+}
+
 template <typename TP, typename TL, bool HAS_REF>
 struct V3Cfg {
   static constexpr int kNPred = HAS_REF ? 2 : 1;
@@ -82,13 +103,6 @@ __device__ __forceinline__ void lds_chunk(const unsigned char* sub, int tid, flo
     typename Vec8<T>::Raw raw{reinterpret_cast<const uint4*>(sub)[tid]};
     Vec8<T>::decode(raw, v);
   }
-}
-
-template <typename T, int kThreads>
-__device__ __forceinline__ void cp_chunk(unsigned char* sub, int tid, const T* src, uint32_t src_bytes) {
-  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sub) + (uint32_t)tid * 16u;
-  cp_async_16(dst, src, src_bytes);
-  if constexpr (sizeof(T) == 4) cp_async_16(dst + kThreads * 16u, reinterpret_cast<const unsigned char*>(src) + 16, src_bytes);
 }
 
 template <typename TP, typename TL, bool HAS_REF>
@@ -134,31 +148,59 @@ __global__ void __launch_bounds__(V3Cfg<TP, TL, HAS_REF>::kThreads, 1) pair_loss
   const long long my_pairs = cluster_id < a.B ? (a.B - cluster_id + n_clusters - 1) / n_clusters : 0;
   const long long total = my_pairs * I;  // chunk-iterations of this CTA
 
-  // start this thread's copies of chunk-iteration g into ring slot g % D (always commits a group)
-  auto issue = [&](long long g) {
-    if (g < total) {
-      const long long it = g / I;
-      const int i = (int)(g - it * I);
-      const int k = i >= Ib ? 1 : 0;
-      const long long c = cbeg + (long long)(i - k * Ib) * T + tid;
-      const uint32_t nb = c < cend ? 16u : 0u;  // beyond the slab: zero-fill (src-size 0), address clamped
-      const long long off = (c < cend ? c : cbeg) * 8;
-      const long long pair = cluster_id + it * n_clusters;
-      unsigned char* slot = ring + (size_t)(g % D) * Cfg::kSlotBytes;
-      cp_chunk<TL, T>(slot + Cfg::kOffX, tid, reinterpret_cast<const TL*>(a.x[k]) + pair * a.stride[2][k] + off, nb);
-      cp_chunk<TL, T>(slot + Cfg::kOffXn, tid, reinterpret_cast<const TL*>(a.xn[k]) + pair * a.stride[3][k] + off, nb);
-      cp_chunk<TP, T>(slot + Cfg::kOffP, tid, reinterpret_cast<const TP*>(a.pred[k]) + pair * a.stride[0][k] + off, nb);
-      if constexpr (HAS_REF)
-        cp_chunk<TP, T>(slot + Cfg::kOffR, tid, reinterpret_cast<const TP*>(a.ref[k]) + pair * a.stride[1][k] + off, nb);
+  const int mine = cend > cbeg ? (int)(cend - cbeg) : 0;  // chunks per branch in this CTA's slab
+
+  // ---- load cursor: the next chunk-iteration to fetch, kept incrementally (no divisions, no 64-bit per-thread
+  // arithmetic on the hot path).  Addresses = CTA-uniform base of (pair, branch, tensor, slab) + 32-bit thread offset.
+  long long c_it = 0;                  // pair ordinal of the cursor
+  int c_j = 0, c_k = 0, c_slot = 0;    // chunk-iteration inside the branch, branch, ring slot
+  int c_lc = tid;                      // this thread's chunk inside the slab for the cursor's iteration
+  const unsigned char *ub_x = nullptr, *ub_n = nullptr, *ub_p = nullptr, *ub_r = nullptr;
+  auto set_bases = [&]() {  // CTA-uniform
+    const long long pair = cluster_id + c_it * n_clusters;
+    const int k = c_k;
+    ub_x = reinterpret_cast<const unsigned char*>(reinterpret_cast<const TL*>(a.x[k]) + pair * a.stride[2][k] + cbeg * 8);
+    ub_n = reinterpret_cast<const unsigned char*>(reinterpret_cast<const TL*>(a.xn[k]) + pair * a.stride[3][k] + cbeg * 8);
+    ub_p = reinterpret_cast<const unsigned char*>(reinterpret_cast<const TP*>(a.pred[k]) + pair * a.stride[0][k] + cbeg * 8);
+    if constexpr (HAS_REF)
+      ub_r = reinterpret_cast<const unsigned char*>(reinterpret_cast<const TP*>(a.ref[k]) + pair * a.stride[1][k] + cbeg * 8);
+  };
+  if (my_pairs > 0) set_bases();
+  const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring) + (uint32_t)tid * 16u;
+  auto issue = [&]() {  // start this thread's copies of the cursor's chunk-iteration (always commits a group)
+    if (c_it < my_pairs) {
+      const bool in = c_lc < mine;
+      const uint32_t nb = in ? 16u : 0u;  // beyond the slab: zero-fill (src-size 0), address clamped to the slab start
+      const uint32_t lc = in ? (uint32_t)c_lc : 0u;
+      const uint32_t offL = lc * (uint32_t)Cfg::kBytesL, offP = lc * (uint32_t)Cfg::kBytesP;
+      const uint32_t dst = ring_base + (uint32_t)c_slot * (uint32_t)Cfg::kSlotBytes;
+      cp_async_16(dst + Cfg::kOffX, ub_x + offL, nb);
+      if constexpr (sizeof(TL) == 4) cp_async_16(dst + Cfg::kOffX + T * 16u, ub_x + offL + 16, nb);
+      cp_async_16(dst + Cfg::kOffXn, ub_n + offL, nb);
+      if constexpr (sizeof(TL) == 4) cp_async_16(dst + Cfg::kOffXn + T * 16u, ub_n + offL + 16, nb);
+      cp_async_16(dst + Cfg::kOffP, ub_p + offP, nb);
+      if constexpr (sizeof(TP) == 4) cp_async_16(dst + Cfg::kOffP + T * 16u, ub_p + offP + 16, nb);
+      if constexpr (HAS_REF) {
+        cp_async_16(dst + Cfg::kOffR, ub_r + offP, nb);
+        if constexpr (sizeof(TP) == 4) cp_async_16(dst + Cfg::kOffR + T * 16u, ub_r + offP + 16, nb);
+      }
+      c_lc += T;
+      if (++c_j == Ib) {  // next branch / next pair (uniform branch, taken once per Ib iterations)
+        c_j = 0;
+        c_lc = tid;
+        if (++c_k == 2) { c_k = 0; ++c_it; }
+        if (c_it < my_pairs) set_bases();
+      }
+      if (++c_slot == D) c_slot = 0;
     }
     cp_async_commit();
   };
 
 #pragma unroll
-  for (int d = 0; d < D; ++d) issue(d);
+  for (int d = 0; d < D; ++d) issue();
 
   double loss_acc = 0.0;  // rank 0, thread 0
-  long long g = 0;
+  int slot_i = 0;         // ring slot of the chunk-iteration being consumed
   for (long long it = 0; it < my_pairs; ++it) {
     const long long pair = cluster_id + it * n_clusters;
     const int tb = (int)((it / kTabPairs) & 1), slot_t = (int)(it % kTabPairs);
@@ -176,22 +218,28 @@ __global__ void __launch_bounds__(V3Cfg<TP, TL, HAS_REF>::kThreads, 1) pair_loss
 
     // ------------------------------------------------------------------ pass 1
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t tcol = tmem_mine + col0;
 #pragma unroll 1
-    for (int i = 0; i < I; ++i, ++g) {
-      const int k = i >= Ib ? 1 : 0;
-      cp_async_wait<D - 1>();  // this thread's pieces of chunk-iteration g have landed
-      const unsigned char* slot = ring + (size_t)(g % D) * Cfg::kSlotBytes;
-      float vx[8], vn[8], vp[8], vr[8], r[8];
-      lds_chunk<TL, T>(slot + Cfg::kOffX, tid, vx);
-      lds_chunk<TL, T>(slot + Cfg::kOffXn, tid, vn);
-      lds_chunk<TP, T>(slot + Cfg::kOffP, tid, vp);
-      if constexpr (HAS_REF) lds_chunk<TP, T>(slot + Cfg::kOffR, tid, vr);
+    for (int k = 0; k < 2; ++k) {
+      const float ck = ent.c[k].k, ca = ent.c[k].a;
       float s_t = 0.f, s_r = 0.f, s_d = 0.f;
-      residual8<HAS_REF>(vx, vn, vp, vr, ent.c[k].k, ent.c[k].a, r, s_t, s_r, s_d);  // zero-filled chunks contribute 0
-      issue(g + D);  // refill the slot just drained (its values are in registers)
-      tmem_st8(tmem_mine + col0 + (uint32_t)i * 8u, r);
-      if (k == 0) { acc[0] += s_t; acc[1] += s_r; acc[2] += s_d; }
-      else        { acc[3] += s_t; acc[4] += s_r; acc[5] += s_d; }
+#pragma unroll 1
+      for (int j = 0; j < Ib; ++j) {
+        cp_async_wait<D - 1>();  // this thread's pieces of the oldest chunk-iteration in flight have landed
+        const unsigned char* slot = ring + (size_t)slot_i * Cfg::kSlotBytes;
+        float vx[8], vn[8], vp[8], vr[8], r[8];
+        lds_chunk<TL, T>(slot + Cfg::kOffX, tid, vx);
+        lds_chunk<TL, T>(slot + Cfg::kOffXn, tid, vn);
+        lds_chunk<TP, T>(slot + Cfg::kOffP, tid, vp);
+        if constexpr (HAS_REF) lds_chunk<TP, T>(slot + Cfg::kOffR, tid, vr);
+        residual8_u<HAS_REF>(vx, vn, vp, vr, ck, ca, r, s_t, s_r, s_d);  // (sum r^2, sum u r, sum u^2); zero-filled chunks add 0
+        issue();  // refill the slot just drained (its values are in registers)
+        tmem_st8(tcol, r);
+        tcol += 8u;
+        if (++slot_i == D) slot_i = 0;
+      }
+      if (k == 0) { acc[0] = s_t; acc[1] = s_r; acc[2] = s_d; }  // (no runtime-indexed register array)
+      else        { acc[3] = s_t; acc[4] = s_r; acc[5] = s_d; }
     }
     // ------------------------------------------------------------------ reduce: warp -> CTA -> cluster
 #pragma unroll
@@ -224,6 +272,13 @@ __global__ void __launch_bounds__(V3Cfg<TP, TL, HAS_REF>::kThreads, 1) pair_loss
       for (unsigned r = 0; r < C; ++r)  // rank order: identical in all CTAs
 #pragma unroll
         for (int j = 0; j < 6; ++j) S[j] += s_xch[par][r][j];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {  // u form -> (S_pol, S_ref, D)
+        const float ca = ent.c[k].a;
+        const float d = ca * fmaf(ca, S[3 * k + 2], 2.f * S[3 * k + 1]);
+        S[3 * k + 1] = S[3 * k] + d;
+        S[3 * k + 2] = d;
+      }
       float g0, g1, st[8];
       const float per = pair_scalar_function_fast(a, S, ent, g0, g1, st);
       s_g[0] = g0;
@@ -239,19 +294,22 @@ __global__ void __launch_bounds__(V3Cfg<TP, TL, HAS_REF>::kThreads, 1) pair_loss
     }
     __syncthreads();
     // ------------------------------------------------------------------ pass 2: grad = g_k * r from tensor memory
-    const float g0 = s_g[0], g1 = s_g[1];
+    tcol = tmem_mine + col0;
 #pragma unroll 1
-    for (int i = 0; i < I; ++i) {
-      const int k = i >= Ib ? 1 : 0;
-      float r[8];
-      tmem_ld8(tmem_mine + col0 + (uint32_t)i * 8u, r);
-      const long long c = cbeg + (long long)(i - k * Ib) * T + tid;
-      if (c < cend) {
-        const float gk = k == 0 ? g0 : g1;
-        float o[8];
+    for (int k = 0; k < 2; ++k) {
+      const float gk = s_g[k];
+      TP* gp = reinterpret_cast<TP*>(a.grad[k]) + pair * a.N + (cbeg + tid) * 8;
+      int lc = tid;
+#pragma unroll 1
+      for (int j = 0; j < Ib; ++j, lc += T, gp += T * 8, tcol += 8u) {
+        float r[8];
+        tmem_ld8(tcol, r);
+        if (lc < mine) {
+          float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = gk * r[j];
-        Vec8<TP>::store(reinterpret_cast<TP*>(a.grad[k]) + pair * a.N + c * 8, o);
+          for (int e = 0; e < 8; ++e) o[e] = gk * r[e];
+          Vec8<TP>::store(gp, o);
+        }
       }
     }
     // s_g / s_warp are rewritten only after the next pair's first __syncthreads: every thread has read them by then
