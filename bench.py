@@ -248,8 +248,11 @@ def run_b200(args):
     d = {k: v.to(dev) for k, v in host.items()}
     fwd_bwd = micro_step.product_micro_step if args.separate_forwards else micro_step.product_micro_step_batched
 
+    ref_stream = torch.cuda.Stream() if (args.overlap_reference and not args.separate_forwards) else None
+
     def micro(batch):
-        return fwd_bwd(pso, lora, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM)
+        kw = {"ref_stream": ref_stream} if ref_stream is not None else {}
+        return fwd_bwd(pso, lora, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM, **kw)
 
     def optimizer_boundary(i):
         if (i + 1) % ACCUM == 0:  # turbo trainer :858-861 (sync_gradients)
@@ -398,7 +401,8 @@ def run_b200(args):
                        "parallelism": f"dp{world} (pairs sharded; one all-reduce of the flat LoRA gradient per {ACCUM} steps)",
                        "l2_policy": "working set larger than L2 (5.1 GB of bf16 weights streamed every forward)",
                        "forwards": "4 separate (as the reference)" if args.separate_forwards else
-                                   "win+lose batched: 1 policy + 1 reference forward of batch 2B",
+                                   "win+lose batched: 1 policy + 1 reference forward of batch 2B" +
+                                   (", reference forward on a second stream" if ref_stream is not None else ""),
                        "timing": ("eager launches" if args.no_graph else "micro-step replayed from one CUDA graph; optimizer "
                                   "boundary eager") + ", CUDA events around K steps, max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
@@ -524,6 +528,9 @@ def main():
     ap.add_argument("--no-kernel-figures", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the micro-step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--separate-forwards", action="store_true", help="4 UNet forwards of batch B instead of 2 of batch 2B")
+    ap.add_argument("--overlap-reference", action="store_true", default=True,
+                    help="issue the frozen-reference forward on a second stream (default)")
+    ap.add_argument("--no-overlap-reference", dest="overlap_reference", action="store_false")
     ap.add_argument("--tiny", action="store_true", help="debug: the 32/64-channel fixture instead of the SDXL architecture")
     ap.add_argument("--ncu-traffic", type=float, default=None,
                     help="dram bytes per launch of the loss kernel from the committed ncu --set full capture")

@@ -69,15 +69,29 @@ def batched_view(batch):
     return out
 
 
-def product_micro_step_batched(pso, lora, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0):
-    """Same micro-step with ONE policy forward and ONE frozen-reference forward of batch 2B (``batched_view``)."""
+def product_micro_step_batched(pso, lora, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0, ref_stream=None):
+    """Same micro-step with ONE policy forward and ONE frozen-reference forward of batch 2B (``batched_view``).
+    With ``ref_stream`` the no-grad reference forward is issued on a second CUDA stream: it is independent of the policy
+    forward, and most kernels of a batch-8 forward leave SMs idle, so the two overlap (inside a captured CUDA graph the
+    fork / join become graph edges)."""
     B = batch["latents_0"].shape[0]
     cond = {"text_embeds": batch["text_embeds_01"], "time_ids": batch["time_ids_01"].to(batch["input_latents_01"].dtype)}
+    cur = torch.cuda.current_stream()
+    if ref_stream is not None:
+        ref_stream.wait_stream(cur)
+        lora.disable_adapters(unet)
+        with torch.cuda.stream(ref_stream), torch.no_grad():
+            ref = unet(batch["input_latents_01"], batch["timesteps_01"], batch["prompt_embeds_01"], added_cond_kwargs=cond).sample
+        lora.enable_adapters(unet)
     pol = unet(batch["input_latents_01"], batch["timesteps_01"], batch["prompt_embeds_01"], added_cond_kwargs=cond).sample
-    lora.disable_adapters(unet)
-    with torch.no_grad():
-        ref = unet(batch["input_latents_01"], batch["timesteps_01"], batch["prompt_embeds_01"], added_cond_kwargs=cond).sample
-    lora.enable_adapters(unet)
+    if ref_stream is not None:
+        cur.wait_stream(ref_stream)
+        ref.record_stream(cur)
+    else:
+        lora.disable_adapters(unet)
+        with torch.no_grad():
+            ref = unet(batch["input_latents_01"], batch["timesteps_01"], batch["prompt_embeds_01"], added_cond_kwargs=cond).sample
+        lora.enable_adapters(unet)
     ts = batch["timesteps"]
     loss = pso.pso_pair_loss(pol[:B], pol[B:], ref[:B], ref[B:], batch["latents_0"], batch["latents_1"],
                              batch["next_latents_0"], batch["next_latents_1"], ts, ts, batch["human_prefer"],
