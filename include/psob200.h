@@ -343,6 +343,10 @@ typedef struct psob200_gemm_args {
   int32_t accumulate;
   int32_t split_k;
   int32_t tune_bn;
+  int32_t pdl;  /* programmatic dependent launch: 1 = let the next launch on the stream start early (this grid signals
+                   at its start); 2 = this launch may start before the previous one has finished and waits for it only
+                   before reading the second K segment (a2); 6 = ... waits before its first load; 8 = independent of the
+                   previous launch, may overlap it entirely (waits for it only before exiting).  0 = plain launch */
   int32_t diag; /* timing experiments only (results are then wrong): bit 0 skip the MMAs, bit 1 skip the stores,
                    bit 2 skip the B loads */
 } psob200_gemm_args;

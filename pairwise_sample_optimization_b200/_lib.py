@@ -76,7 +76,7 @@ class GemmArgs(C.Structure):
                 ("K2", C.c_int64), ("alpha", C.c_float), ("ab_dtype", C.c_int32), ("d_dtype", C.c_int32),
                 ("bias_dtype", C.c_int32), ("a_reduction_major", C.c_int32), ("b_reduction_major", C.c_int32),
                 ("accumulate", C.c_int32),
-                ("split_k", C.c_int32), ("tune_bn", C.c_int32), ("diag", C.c_int32)]
+                ("split_k", C.c_int32), ("tune_bn", C.c_int32), ("pdl", C.c_int32), ("diag", C.c_int32)]
 
 
 class LoraLinearArgs(C.Structure):

@@ -47,6 +47,7 @@ struct GemmKernelParams {
   float alpha;
   int d_dtype, bias_dtype, ab_format, a_mn, b_mn, atomic, diag;
   int stages;             // even; stage = 16 KB of A + bn*128 B of B
+  int pdl;                // programmatic dependent launch role bits (psob200_gemm_args.pdl)
 };
 
 template <typename T>
@@ -197,6 +198,9 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     }
     ptx::fence_mbar_init();
   }
+  // primary of a programmatic dependent launch: the dependent grid (the main GEMM that needs this launch's output only
+  // for its last k-blocks) may start filling the SMs this small grid leaves idle
+  if (p.pdl & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 2) ptx::tmem_alloc<kTmemCols>(&tmem_base_slot);
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -221,6 +225,12 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     const uint32_t tx = ((p.diag & 8) ? 0u : (uint32_t)kStageABytes) + ((p.diag & 4) ? 0u : (uint32_t)p.bn * kBK * 2u);
     int stage = 0;
     uint32_t phase = 0;
+    bool dep_pending = (p.pdl & 2) != 0;  // launched ahead of the grid that produces a2 (or, bit 2, any operand)
+    if (dep_pending && (p.pdl & 4)) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");
+      dep_pending = false;
+    }
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int m_blk, n_blk, kb0, kb1;
       tile_coords(t, m_blk, n_blk, kb0, kb1);
@@ -228,6 +238,11 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
       for (int kb = kb0; kb < kb1; ++kb) {
         if ((stage & 1) == 0) ptx::mbar_wait(&empty_bar[stage >> 1], phase ^ 1u);  // the pair (stage, stage+1) is free
         const bool seg2 = kb >= p.nk1;
+        if (seg2 && dep_pending) {  // first read of the previous launch's output: wait for that grid, then fence the
+          asm volatile("griddepcontrol.wait;" ::: "memory");  // generic-proxy writes against the TMA (async proxy) reads
+          asm volatile("fence.proxy.async;" ::: "memory");
+          dep_pending = false;
+        }
         const CUtensorMap* ma = seg2 ? &map_a2 : &map_a1;
         const CUtensorMap* mb = seg2 ? &map_b2 : &map_b1;
         const int kk = (seg2 ? kb - p.nk1 : kb) * kBK;
@@ -325,6 +340,9 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<kTmemCols>(tmem_base);
   }
+  // an independent dependent launch (bit 3): it never reads the previous grid's output, but it must not be seen as
+  // complete before that grid is, so that later launches on the stream stay ordered after both
+  if ((p.pdl & 8) && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------- host
@@ -441,6 +459,7 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
   p.b_mn = g.b_reduction_major ? 1 : 0;
   p.atomic = g.accumulate ? 1 : 0;
   p.diag = g.diag;
+  p.pdl = g.pdl;
   p.stages = (kStages * (kStageABytes + kStageBBytes)) / (kStageABytes + p.bn * kBK * 2);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.stages &= ~1;
@@ -472,8 +491,20 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
   }
   const long long total = (long long)p.m_tiles * p.n_tiles * p.splits;
   const unsigned grid = (unsigned)(total < sms ? total : sms);
-  lora_gemm_kernel<<<grid, kGemmThreads, kGemmSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(ma1, mb1, ma2, mb2, p);
-  return consume_launch_error("launch lora_gemm_kernel", cudaSuccess);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = kGemmSmemBytes;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  if (g.pdl & (2 | 8)) {  // may begin while the previous kernel on the stream is still running (it waits on the device)
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, lora_gemm_kernel, ma1, mb1, ma2, mb2, p);
+  return consume_launch_error("launch lora_gemm_kernel", e);
 }
 
 // ---------------------------------------------------------------------------------------------- LoRA-wrapped Linear
@@ -498,12 +529,13 @@ extern "C" int psob200_lora_linear_forward(const psob200_lora_linear_args* args,
     g.M = a.M; g.N = a.r; g.K1 = a.K;
     g.alpha = a.scaling;
     g.d = a.t; g.ldd = a.ldt; g.dt = a.tt; g.lddt = a.ldtt;
+    g.pdl = 1;  // the main pass below reads t only in its last k-blocks: let it start on the SMs this launch leaves idle
     if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
   }
   psob200_gemm_args g = gemm_defaults(a.dtype);
   g.a1 = a.x; g.lda1 = a.ldx; g.b1 = a.w; g.ldb1 = a.ldw;
   g.M = a.M; g.N = a.N; g.K1 = a.K;
-  if (lora) { g.a2 = a.t; g.lda2 = a.ldt; g.b2 = a.lora_b; g.ldb2 = a.ldb; g.K2 = a.r; }
+  if (lora) { g.a2 = a.t; g.lda2 = a.ldt; g.b2 = a.lora_b; g.ldb2 = a.ldb; g.K2 = a.r; g.pdl = 2; }
   g.bias = a.bias; g.bias_dtype = a.bias_dtype;
   g.d = a.y; g.ldd = a.ldy;
   return psob200_lora_gemm(&g, stream);
@@ -525,13 +557,14 @@ extern "C" int psob200_lora_linear_backward(const psob200_lora_linear_args* args
     g.M = a.M; g.N = a.r; g.K1 = a.N;
     g.alpha = a.scaling;
     g.d = a.u; g.ldd = a.ldu; g.dt = a.d_lora_a ? a.ut : nullptr; g.lddt = a.ldut;
+    g.pdl = a.dx != nullptr ? 1 : 0;
     if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
   }
   if (a.dx != nullptr) {  // dx = dy W + u A   (W [N,K], A [r,K] reduction-major)
     psob200_gemm_args g = gemm_defaults(a.dtype);
     g.a1 = a.dy; g.lda1 = a.lddy; g.b1 = a.w; g.ldb1 = a.ldw; g.b_reduction_major = 1;
     g.M = a.M; g.N = a.K; g.K1 = a.N;
-    if (lora) { g.a2 = a.u; g.lda2 = a.ldu; g.b2 = a.lora_a; g.ldb2 = a.lda; g.K2 = a.r; }
+    if (lora) { g.a2 = a.u; g.lda2 = a.ldu; g.b2 = a.lora_a; g.ldb2 = a.lda; g.K2 = a.r; g.pdl = 2; }
     g.d = a.dx; g.ldd = a.lddx;
     if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
   }
@@ -540,6 +573,7 @@ extern "C" int psob200_lora_linear_backward(const psob200_lora_linear_args* args
     g.a1 = a.x; g.lda1 = a.ldx; g.a_reduction_major = 1; g.b1 = a.ut; g.ldb1 = a.ldut;
     g.M = a.K; g.N = a.r; g.K1 = a.M;
     g.dt = a.d_lora_a; g.lddt = a.ld_da; g.d_dtype = PSOB200_F32; g.accumulate = 1;
+    g.pdl = a.d_lora_b != nullptr ? 1 : 0;  // dB below is independent of this launch: let the two overlap
     if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
   }
   if (lora && a.d_lora_b != nullptr) {  // dB[N,r] += dy^T t
@@ -547,6 +581,7 @@ extern "C" int psob200_lora_linear_backward(const psob200_lora_linear_args* args
     g.a1 = a.dy; g.lda1 = a.lddy; g.a_reduction_major = 1; g.b1 = a.tt; g.ldb1 = a.ldtt;
     g.M = a.N; g.N = a.r; g.K1 = a.M;
     g.d = a.d_lora_b; g.ldd = a.ld_db; g.d_dtype = PSOB200_F32; g.accumulate = 1;
+    g.pdl = a.d_lora_a != nullptr ? 8 : 0;
     if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
   }
   return PSOB200_OK;

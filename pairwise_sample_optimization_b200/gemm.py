@@ -25,7 +25,7 @@ def _mat(t: torch.Tensor, what: str) -> torch.Tensor:
 
 def lora_gemm(a1, b1, a2=None, b2=None, *, bias=None, alpha: float = 1.0, out=None, out_t=None, out_dtype=None,
               want_out: bool = True, want_out_t: bool = False, a_reduction_major: bool = False,
-              accumulate: bool = False, split_k: int = 0, tune_bn: int = 0, diag: int = 0):
+              accumulate: bool = False, split_k: int = 0, tune_bn: int = 0, diag: int = 0, pdl: int = 0):
     """D[M,N] = alpha * (a1 @ b1.T + a2 @ b2.T) + bias on the tcgen05 tensor cores.
 
     ``a1``: [M,K1] (or [K1,M] when ``a_reduction_major``), ``b1``: [N,K1], ``a2``: [M,K2], ``b2``: [N,K2]; bf16 or
@@ -85,7 +85,7 @@ def lora_gemm(a1, b1, a2=None, b2=None, *, bias=None, alpha: float = 1.0, out=No
     g.d_dtype = _lib._DTYPES[out_dtype]
     g.a_reduction_major = int(a_reduction_major)
     g.accumulate = int(accumulate)
-    g.split_k, g.tune_bn, g.diag = int(split_k), int(tune_bn), int(diag)
+    g.split_k, g.tune_bn, g.diag, g.pdl = int(split_k), int(tune_bn), int(diag), int(pdl)
     rc = _lib.lib().psob200_lora_gemm(C.byref(g), _lib.current_stream(dev))
     _lib.check(rc, "psob200_lora_gemm")
     del keep

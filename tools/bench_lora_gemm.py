@@ -91,8 +91,8 @@ def main():
             flops_b = flops_f + 2.0 * M * K * N + 2.0 * M * r * (K + N) + 2.0 * M * r * (K + N)  # fwd + dX (+U) + dA, dB
 
             def fused():
-                T, _ = gemm.lora_gemm(x, A, alpha=1.0)
-                return gemm.lora_gemm(x, w, T, Bm, bias=b, tune_bn=args.bn)
+                T, _ = gemm.lora_gemm(x, A, alpha=1.0, pdl=1)
+                return gemm.lora_gemm(x, w, T, Bm, bias=b, tune_bn=args.bn, pdl=2)
 
             def main_only(T=gemm.lora_gemm(x, A)[0]):
                 return gemm.lora_gemm(x, w, T, Bm, bias=b, tune_bn=args.bn)
