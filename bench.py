@@ -181,7 +181,7 @@ def loss_kernel_roofline(pso, dev, peaks, ncu_traffic):
     ms = graph_timed(call, 20, per_graph=1)
     alg = 10 * n * 2 * B
     ach = alg / (ms * 1e-3) / 1e9
-    return {"kernel": "pair_loss_grad_tma_kernel<bf16,bf16,ref>", "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"],
+    return {"kernel": "pair_loss_grad_tmem_kernel<bf16,bf16,ref>", "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"],
             "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4), "traffic": ncu_traffic,
             "workload": "256 pairs x 4x128x128 bf16 (BASELINE config 5 top of sweep)", "algorithmic_bytes_per_launch": alg,
             "avg_launch_us": round(ms * 1e3, 2), "peak_source": peaks["source"]}

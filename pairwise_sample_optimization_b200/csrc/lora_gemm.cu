@@ -345,6 +345,12 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
   if ((p.pdl & 8) && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+}  // namespace psob200
+
+#include "lora_gemm2.cuh"  // cta_group::2 variant (CTA pairs) for the large tensor-bound shapes
+
+namespace psob200 {
+
 // ---------------------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -428,6 +434,68 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
   if ((g.d && g.ldd < g.N) || (g.dt && g.lddt < g.M)) return PSOB200_ERR_SHAPE;
   if (g.M > 0x7fffffffLL - 256 || g.N > 0x7fffffffLL - 256 || g.K1 > 0x7fffffffLL - 256 || g.K2 > 0x7fffffffLL - 256)
     return PSOB200_ERR_SHAPE;
+
+  // ---- CTA-pair kernel (cta_group::2) for the large K-major problems: at least one full wave of 256-row pair tiles
+  {
+    const bool eligible = !g.a_reduction_major && !g.accumulate && g.dt == nullptr && g.split_k <= 1 && g.tune_bn == 0;
+    const int bn2 = g.N >= 256 ? 256 : (int)(((g.N + (g.b_reduction_major ? 127 : 31)) / (g.b_reduction_major ? 128 : 32)) *
+                                             (g.b_reduction_major ? 128 : 32));
+    const long long pair_tiles = ((g.M + 255) / 256) * ((g.N + bn2 - 1) / bn2);
+    const int sms = gemm_sm_count();
+    const bool want = (g.diag & 0x10000) || (pair_tiles >= sms / 2 && g.N >= 128 && !(g.diag & 0x20000));
+    if (eligible && want && bn2 <= kBNMax) {
+      GemmKernelParams p = {};
+      p.M = g.M; p.N = g.N;
+      p.nk1 = (int)((g.K1 + kBK - 1) / kBK);
+      p.nk2 = (int)((g.K2 + kBK - 1) / kBK);
+      p.bn = bn2;
+      p.m_tiles = (int)((g.M + 255) / 256);
+      p.n_tiles = (int)((g.N + bn2 - 1) / bn2);
+      p.splits = 1; p.kb_per_split = p.nk1 + p.nk2;
+      p.d = g.d; p.ldd = g.ldd; p.bias = g.bias;
+      p.alpha = g.alpha; p.d_dtype = g.d_dtype; p.bias_dtype = g.bias_dtype;
+      p.ab_format = g.ab_dtype == PSOB200_BF16 ? 1 : 0;
+      p.b_mn = g.b_reduction_major ? 1 : 0;
+      p.diag = g.diag; p.pdl = g.pdl; p.stages = kStages2;
+      CUtensorMap ma1, mb1, ma2, mb2;
+      int rc;
+      if ((rc = make_map(&ma1, g.a1, g.M, g.K1, g.lda1, kBM, g.ab_dtype)) != PSOB200_OK) return rc;
+      if (p.b_mn) rc = make_map(&mb1, g.b1, g.K1, g.N, g.ldb1, kBK, g.ab_dtype);
+      else rc = make_map(&mb1, g.b1, g.N, g.K1, g.ldb1, bn2 / 2, g.ab_dtype);
+      if (rc != PSOB200_OK) return rc;
+      if (g.K2 > 0) {
+        if ((rc = make_map(&ma2, g.a2, g.M, g.K2, g.lda2, kBM, g.ab_dtype)) != PSOB200_OK) return rc;
+        if (p.b_mn) rc = make_map(&mb2, g.b2, g.K2, g.N, g.ldb2, kBK, g.ab_dtype);
+        else rc = make_map(&mb2, g.b2, g.N, g.K2, g.ldb2, bn2 / 2, g.ab_dtype);
+        if (rc != PSOB200_OK) return rc;
+      } else {
+        ma2 = ma1;
+        mb2 = mb1;
+      }
+      static std::atomic<bool> configured2{false};
+      if (!configured2.load(std::memory_order_acquire)) {
+        const cudaError_t e = cudaFuncSetAttribute(lora_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm2SmemBytes);
+        if (e != cudaSuccess) return consume_launch_error("configure lora_gemm2_kernel", e);
+        configured2.store(true, std::memory_order_release);
+      }
+      const long long max_pairs = sms / 2;
+      const unsigned grid = 2u * (unsigned)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(kGemmThreads);
+      cfg.dynamicSmemBytes = kGemm2SmemBytes;
+      cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+      cudaLaunchAttribute attr[1];
+      if (g.pdl & (2 | 8)) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+      }
+      const cudaError_t e = cudaLaunchKernelEx(&cfg, lora_gemm2_kernel, ma1, mb1, ma2, mb2, p);
+      return consume_launch_error("launch lora_gemm2_kernel", e);
+    }
+  }
 
   GemmKernelParams p = {};
   p.M = g.M; p.N = g.N;

@@ -1,0 +1,233 @@
+// Two-SM variant of the LoRA projection GEMM: tcgen05.mma.cta_group::2 on a CTA PAIR (cluster of 2).
+//
+// Why: with cta_group::1 a CTA must ingest 48 KB of operands per 64-wide k-block (A 128 x 64, B 256 x 64) for 512
+// cycles of MMA work; measured, the SM takes ~740 cycles to ingest that much, which caps the tensor pipe at ~69 %
+// (profiles/r01_lora_gemm.md).  A CTA pair computes a 256 x bn tile: each CTA holds ITS 128 rows of A and HALF of the B
+// tile (bn/2 rows), the MMA reads both halves of B across the pair, and each CTA's tensor memory receives its 128 rows
+// of the accumulator.  Per-SM ingest drops to 32 KB per k-block for the same 512 cycles of MMA.
+//
+// Same roles as lora_gemm_kernel; differences:
+//   * both CTAs run a TMA producer for their own halves; every copy signals the LEADER's (rank 0) full barrier
+//     (cp.async.bulk.tensor ... .cta_group::2 with the barrier address mapped to the even CTA of the pair);
+//   * only the leader issues MMAs (M = 256) and commits; commits are MULTICAST to both CTAs' barriers (empty slots,
+//     accumulator full);
+//   * the peer's epilogue warps release the accumulator on the leader's barrier (remote mbarrier arrive);
+//   * tensor memory is allocated / freed with .cta_group::2 by the same warp of both CTAs.
+// Supports: two K segments, bias, alpha, K-major or reduction-major B, PDL waits.  Not: reduction-major A, atomics,
+// transposed output, split-K (the 1-SM kernel keeps those).
+#pragma once
+
+namespace psob200 {
+
+constexpr int kStageB2Bytes = (kBNMax / 2) * kBK * 2;                         // 16 KB: half of the widest B tile
+constexpr int kStages2 = 6;                                                   // 6 x (16 + 16) KB
+constexpr int kGemm2SmemBytes = kStages2 * (kStageABytes + kStageB2Bytes) + 1024;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                                // shared::cluster address -> even CTA of the pair
+
+namespace ptx {
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_addr(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_addr(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the even CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_addr(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+}  // namespace ptx
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+lora_gemm2_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
+                  const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
+                  const GemmKernelParams p) {
+  extern __shared__ unsigned char gemm_smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages2], empty_bar[kStages2 / 2], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + kStages2 * kStageABytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int nk = p.nk1 + p.nk2;
+  const int half_bn = p.bn / 2;
+  const int stage_b_bytes = half_bn * kBK * 2;
+  const long long total_tiles = (long long)p.m_tiles * p.n_tiles;  // m_tiles counts 256-row pair tiles here
+  const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a1);
+    ptx::prefetch_tensormap(&map_b1);
+    if (p.nk2 > 0) {
+      ptx::prefetch_tensormap(&map_a2);
+      ptx::prefetch_tensormap(&map_b2);
+    }
+  }
+  if (p.pdl & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp == 1 && lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages2; ++s) ptx::mbar_init(&full_bar[s], 1);  // leader's arrive.expect_tx (both CTAs' bytes)
+#pragma unroll
+    for (int s = 0; s < kStages2 / 2; ++s) ptx::mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);   // multicast tcgen05.commit
+      ptx::mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps of each CTA (waited on by the leader only)
+    }
+    ptx::fence_mbar_init();
+  }
+  ptx::cluster_sync_all();  // both CTAs are resident and their barriers initialised before anything crosses the pair
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_addr(&tmem_base_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  auto tile_coords = [&](long long t, int& m_blk, int& n_blk) {
+    n_blk = (int)(t % p.n_tiles);
+    m_blk = (int)(t / p.n_tiles);
+  };
+
+  if (warp == 0) {
+    // ================================================================= TMA producer (both CTAs: own A rows, own half of B)
+    const uint32_t tx_pair = 2u * ((uint32_t)kStageABytes + (uint32_t)stage_b_bytes);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool dep_pending = (p.pdl & 2) != 0;
+    if (dep_pending && (p.pdl & 4)) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");
+      dep_pending = false;
+    }
+    for (long long t = cluster_id; t < total_tiles; t += n_clusters) {
+      int m_blk, n_blk;
+      tile_coords(t, m_blk, n_blk);
+      const int m0 = m_blk * 256 + (int)rank * kBM, n0 = n_blk * p.bn + (int)rank * half_bn;
+      for (int kb = 0; kb < nk; ++kb) {
+        if ((stage & 1) == 0) ptx::mbar_wait(&empty_bar[stage >> 1], phase ^ 1u);
+        const bool seg2 = kb >= p.nk1;
+        if (seg2 && dep_pending) {
+          asm volatile("griddepcontrol.wait;" ::: "memory");
+          asm volatile("fence.proxy.async;" ::: "memory");
+          dep_pending = false;
+        }
+        const CUtensorMap* ma = seg2 ? &map_a2 : &map_a1;
+        const CUtensorMap* mb = seg2 ? &map_b2 : &map_b1;
+        const int kk = (seg2 ? kb - p.nk1 : kb) * kBK;
+        unsigned char* sa = smem_a + stage * kStageABytes;
+        unsigned char* sb = smem_b + stage * stage_b_bytes;
+        if (ptx::elect_one()) {
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_pair);
+          ptx::tma_load_2d_pair(sa, ma, kk, m0, &full_bar[stage]);
+          if (p.b_mn) {
+            for (int j = 0; j < half_bn / 64; ++j)
+              ptx::tma_load_2d_pair(sb + j * (kBK * 128), mb, n0 + 64 * j, kk, &full_bar[stage]);
+          } else {
+            ptx::tma_load_2d_pair(sb, mb, kk, n0, &full_bar[stage]);
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ================================================================= MMA issuer (leader CTA, M = 256 across the pair)
+    const uint32_t idesc = (1u << 4) | ((uint32_t)p.ab_format << 7) | ((uint32_t)p.ab_format << 10) |
+                           ((uint32_t)p.b_mn << 16) | (((uint32_t)p.bn >> 3) << 17) | ((256u >> 4) << 24);
+    const uint64_t a_hi = ptx::smem_desc_sw128(0, 0, 1024);
+    const uint64_t b_hi = ptx::smem_desc_sw128(0, p.b_mn ? kBK * 128 : 0, 1024);
+    const uint32_t b_step = p.b_mn ? 2048u >> 4 : 32u >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    long long iter = 0;
+    for (long long t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
+      const int acc = (int)(iter & 1);
+      const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
+      ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);  // both CTAs' epilogues have drained this accumulator
+      ptx::tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * kBNMax;
+      for (int kb = 0; kb < nk; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after_sync();
+        const uint64_t a_desc = a_hi | (uint64_t)((ptx::smem_addr(smem_a + stage * kStageABytes) >> 4) & 0x3FFFu);
+        const uint64_t b_desc = b_hi | (uint64_t)((ptx::smem_addr(smem_b + stage * stage_b_bytes) >> 4) & 0x3FFFu);
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            ptx::umma_f16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * b_step), idesc,
+                               (kb > 0 || k > 0) ? 1u : 0u);
+          if (stage & 1) ptx::umma_commit_pair(&empty_bar[stage >> 1]);
+          if (kb == nk - 1) ptx::umma_commit_pair(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================= epilogue (each CTA: its 128 rows)
+    const int ew = warp - 4;
+    long long iter = 0;
+    for (long long t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
+      int m_blk, n_blk;
+      tile_coords(t, m_blk, n_blk);
+      const int acc = (int)(iter & 1);
+      const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
+      const long long row = (long long)m_blk * 256 + (long long)rank * kBM + ew * 32 + lane;
+      const long long n_tile0 = (long long)n_blk * p.bn;
+      const bool add_bias = p.bias != nullptr;
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kBNMax;
+      if (p.d_dtype == PSOB200_F32) epilogue_tile<float, false>(p, taddr, row, n_tile0, add_bias);
+      else if (p.d_dtype == PSOB200_BF16) epilogue_tile<__nv_bfloat16, false>(p, taddr, row, n_tile0, add_bias);
+      else epilogue_tile<__half, false>(p, taddr, row, n_tile0, add_bias);
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_leader(&tmem_empty_bar[acc]);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync_all();  // both CTAs are done with the pair's tensor memory and with each other's shared memory
+  if (warp == 2) {
+    ptx::tc_fence_after_sync();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace psob200

@@ -62,10 +62,11 @@ def lora_gemm(a1, b1, a2=None, b2=None, *, bias=None, alpha: float = 1.0, out=No
             raise _lib.Psob200Error("accumulate=True needs the fp32 tensor(s) to accumulate into")
     elif out_dtype is None:
         out_dtype = a1.dtype
+    pad8 = lambda n: (n + 7) // 8 * 8  # row pitch a multiple of 16 bytes: the result can feed the next launch's TMA as is
     if out is None and want_out and not (accumulate and out_t is not None):
-        out = torch.empty(M, N, dtype=out_dtype, device=dev)
+        out = torch.empty(M, pad8(N), dtype=out_dtype, device=dev)[:, :N]
     if out_t is None and want_out_t and not accumulate:
-        out_t = torch.empty(N, M, dtype=out_dtype, device=dev)
+        out_t = torch.empty(N, pad8(M), dtype=out_dtype, device=dev)[:, :M]
     for t, shape, name in ((out, (M, N), "out"), (out_t, (N, M), "out_t")):
         if t is not None and (tuple(t.shape) != shape or t.dtype != out_dtype or t.stride(1) != 1):
             raise _lib.Psob200Error(f"{name} must be a row-major {shape} {out_dtype} tensor")

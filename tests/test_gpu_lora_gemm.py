@@ -101,3 +101,40 @@ def test_argument_errors(gemm):
         gemm.lora_gemm(a, b[:, :32])
     with pytest.raises(_lib.Psob200Error):
         gemm.lora_gemm(a, b, accumulate=True)
+
+
+@pytest.mark.parametrize("M,K,N,r", [(256, 64, 256, 0), (512, 320, 256, 0), (1000, 200, 328, 8), (2048, 1280, 1280, 64),
+                                     (300, 640, 640, 16), (4096, 640, 160, 0), (37 * 256, 128, 512, 8)])
+@pytest.mark.parametrize("b_mn", [False, True])
+def test_cta_pair_kernel(gemm, M, K, N, r, b_mn):
+    """The cta_group::2 variant (forced with diag bit 16): 256-row pair tiles, halves of B per CTA, multicast commits."""
+    dt = torch.bfloat16
+    a1, b1 = _rand(M, K, dt, 21), _rand(N, K, dt, 22, K ** -0.5)
+    a2, b2 = (_rand(M, r, dt, 23), _rand(N, r, dt, 24, 0.1)) if r else (None, None)
+    bias = _rand(1, N, dt, 25)[0]
+    want = _ref(a1, b1, a2, b2, bias=bias, alpha=0.5)
+    if b_mn:  # B given reduction-major ([K, N] row-major), as the backward consumes W / lora_A / lora_B
+        if N % 8:
+            pytest.skip("reduction-major operands need a 16-byte row pitch")
+        from pairwise_sample_optimization_b200 import _lib
+        import ctypes as C
+        b1t = b1.t().contiguous()
+        b2t = b2.t().contiguous() if r else None
+        out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+        g = _lib.GemmArgs()
+        g.a1, g.lda1, g.b1, g.ldb1 = a1.data_ptr(), a1.stride(0), b1t.data_ptr(), b1t.stride(0)
+        if r:
+            a2p = torch.zeros(M, (r + 7) // 8 * 8, device="cuda", dtype=dt)
+            a2p[:, :r] = a2
+            g.a2, g.lda2, g.b2, g.ldb2, g.K2 = a2p.data_ptr(), a2p.stride(0), b2t.data_ptr(), b2t.stride(0), r
+        g.bias, g.bias_dtype = bias.data_ptr(), _lib.BF16
+        g.d, g.ldd, g.M, g.N, g.K1 = out.data_ptr(), N, M, N, K
+        g.alpha, g.ab_dtype, g.d_dtype, g.b_reduction_major, g.diag = 0.5, _lib.BF16, _lib.F32, 1, 0x10000
+        _lib.check(_lib.lib().psob200_lora_gemm(C.byref(g), _lib.current_stream(a1.device)), "psob200_lora_gemm")
+        got = out
+    else:
+        got, _ = gemm.lora_gemm(a1, b1, a2, b2, bias=bias, alpha=0.5, out_dtype=torch.float32, diag=0x10000)
+    _check(got, want, torch.float32)
+    if not b_mn:
+        got16, _ = gemm.lora_gemm(a1, b1, a2, b2, bias=bias, alpha=0.5, diag=0x10000)
+        _check(got16, want, dt)
