@@ -424,4 +424,5 @@ class PSOAttnProcessor2_0:
             hidden_states = hidden_states.transpose(-1, -2).reshape(bsz, ch, h, w)
         if getattr(attn, "residual_connection", False):
             hidden_states = hidden_states + residual
-        return hidden_states / getattr(attn, "rescale_output_factor", 1.0)
+        rescale = getattr(attn, "rescale_output_factor", 1.0)
+        return hidden_states if rescale == 1.0 else hidden_states / rescale  # x / 1.0 would still launch a kernel

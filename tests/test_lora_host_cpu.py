@@ -96,3 +96,33 @@ def test_oracle_micro_step_on_tiny_unet_cpu():
     g = torch.cat([m.lora_A["default"].weight.grad.flatten() for m in wrapped])
     assert torch.isfinite(g).all() and g.abs().max() > 0
     assert all(m.base_layer.weight.grad is None for m in wrapped)
+
+
+def test_lora_checkpoint_wire_format_round_trip(built_lib, tmp_path):
+    """pytorch_lora_weights.safetensors with the diffusers key naming the reference's save hook produces
+    (train_online_pso_sdxl_turbo.py:361-379), and back."""
+    from safetensors import safe_open
+    from pairwise_sample_optimization_b200 import checkpoint, lora
+    torch.manual_seed(0)
+    a = sdxl_unet.UNet2DConditionModel(sdxl_unet.tiny_config())
+    wa = lora.add_adapter(a, lora.LoraConfig(r=4, lora_alpha=4))
+    for m in wa:
+        torch.nn.init.normal_(m.lora_B["default"].weight, std=0.02)
+    path = checkpoint.save_lora_weights(str(tmp_path), a)
+    assert os.path.basename(path) == "pytorch_lora_weights.safetensors"
+    with safe_open(path, framework="pt") as f:
+        keys = sorted(f.keys())
+        assert f.metadata() == {"format": "pt"}
+    assert len(keys) == 192 and all(k.startswith("unet.") for k in keys)
+    assert "unet.down_blocks.1.attentions.0.transformer_blocks.0.attn1.to_q.lora.down.weight" in keys
+    assert "unet.mid_block.attentions.0.transformer_blocks.1.attn2.to_out.0.lora.up.weight" in keys
+    b = sdxl_unet.UNet2DConditionModel(sdxl_unet.tiny_config())
+    wb = lora.add_adapter(b, lora.LoraConfig(r=4, lora_alpha=4))
+    assert len(checkpoint.load_lora_weights(str(tmp_path), b)) == 192
+    for ma, mb in zip(wa, wb):
+        assert torch.equal(ma.lora_A["default"].weight, mb.lora_A["default"].weight)
+        assert torch.equal(ma.lora_B["default"].weight, mb.lora_B["default"].weight)
+    c = sdxl_unet.UNet2DConditionModel(sdxl_unet.tiny_config())
+    lora.add_adapter(c, lora.LoraConfig(r=8, lora_alpha=8))
+    with pytest.raises(ValueError):
+        checkpoint.load_lora_weights(path, c)
