@@ -11,7 +11,8 @@ reference writes it (train_online_pso_sdxl_turbo.py:771-861):
     2 UNet forwards with grad (policy) + 2 adapter-disabled forwards without (frozen reference), gradient checkpointing on
     fused PSO loss+grad kernel  (replaces 4 x turbo_step_with_logprob + the inline loss + its backward)
     backward through the UNet   (LoRA dX / dA / dB on the tcgen05 GEMM path, accumulated into ONE flat fp32 buffer)
-    every `accum` = GA x T = 6 steps: all-reduce of the flat LoRA gradient (NCCL, N > 1), clip-norm, AdamW
+    every `accum` = GA x T = 6 steps: all-reduce of the flat LoRA gradient (NCCL, N > 1), then clip-norm + AdamW +
+    zero_grad + operand refresh fused over the flat buffers (2 launches)
 
 The 560 projections (forward + backward) and the loss run on this repo's sm_100a kernels; convolutions, norms and the
 attention core are stock torch kernels (outside the PSO hot path).  One rank per GPU, pairs sharded
@@ -236,9 +237,10 @@ def run_b200(args):
     unet.set_attn_processor(lora.PSOAttnProcessor2_0())
     unet.train()
     unet.enable_gradient_checkpointing()  # turbo trainer :358
-    params = lora.lora_parameters(unet)
-    bucket = lora.LoRAGradBucket(params)
-    opt = torch.optim.AdamW(params, lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-4, eps=1e-8, fused=True)
+    # parameters, gradients and Adam moments of all 1120 adapter matrices live in four flat fp32 buffers: the optimizer
+    # boundary is one all-reduce + two launches (clip + AdamW + zero_grad + 16-bit operand refresh)
+    opt = lora.FusedLoRAOptimizer(unet, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_grad_norm=1.0)
+    bucket = opt.bucket
     sched = turbo_scheduler()
     pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
     host = micro_step.synth_batch(B, LATENT_HW, cfg.cross_attention_dim, pooled, 100 + rank, sched.sigmas, dtype=torch.bfloat16)
@@ -255,12 +257,9 @@ def run_b200(args):
         return fwd_bwd(pso, lora, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM, **kw)
 
     def optimizer_boundary(i):
-        if (i + 1) % ACCUM == 0:  # turbo trainer :858-861 (sync_gradients)
-            bucket.all_reduce()
-            bucket.clip_grad_norm_(1.0)
+        if (i + 1) % ACCUM == 0:  # turbo trainer :858-861 (sync_gradients): all-reduce, clip, AdamW, zero_grad
+            opt.all_reduce()
             opt.step()
-            lora.refresh_operands(unet)
-            bucket.zero_()
 
     graph = None
     static_loss = None

@@ -396,10 +396,36 @@ typedef struct psob200_lora_linear_args {
 PSOB200_API int psob200_lora_linear_forward(const psob200_lora_linear_args* args, void* stream);
 PSOB200_API int psob200_lora_linear_backward(const psob200_lora_linear_args* args, void* stream);
 
+/*
+ * Optimizer boundary over the FLAT LoRA buffers (one fp32 buffer each for parameters, gradients and the two Adam
+ * moments; every adapter matrix is a slice): global-norm clipping (accelerate clip_grad_norm_, T:859), AdamW
+ * (T:428-448: lr, betas, weight_decay, eps) with torch.optim.AdamW's update rule, zero_grad, and the refresh of the
+ * 16-bit operand copies the GEMM kernels read -- two launches instead of thousands.
+ *   norm  = grad_scale * ||grad||_2 ;  coef = max_grad_norm > 0 ? min(1, max_grad_norm / (norm + 1e-6)) : 1
+ *   g     = grad * grad_scale * coef   (grad_scale folds the 1/world of a summed all-reduce, or 1)
+ * operand (may be NULL): 16-bit copy of the updated parameters, same flat layout.  norm_out (may be NULL): float[1].
+ * workspace: 16 bytes, 16-byte aligned, zero-initialised once; left zeroed.  step: 1-based optimizer step count.
+ */
+typedef struct psob200_flat_adamw_args {
+  float* param;
+  float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  void* operand;
+  float* norm_out;
+  void* workspace;
+  int64_t n;
+  int64_t step;
+  float lr, beta1, beta2, eps, weight_decay, max_grad_norm, grad_scale;
+  int32_t operand_dtype;
+} psob200_flat_adamw_args;
+
+PSOB200_API int psob200_flat_adamw_step(const psob200_flat_adamw_args* args, void* stream);
+
 /* sizeof() of the argument structs as compiled into the library, for FFI bindings to
  * verify their mirror of this header: which = 0 schedule, 1 online_pso_args,
  * 2 dreambooth_args, 3 step_args, 4 step_bwd_args, 5 gemm_args,
- * 6 lora_linear_args.  Returns 0 for unknown ids. */
+ * 6 lora_linear_args, 7 flat_adamw_args.  Returns 0 for unknown ids. */
 PSOB200_API size_t psob200_struct_size(int which);
 
 #ifdef __cplusplus

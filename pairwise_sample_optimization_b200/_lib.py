@@ -89,8 +89,15 @@ class LoraLinearArgs(C.Structure):
                 ("dtype", C.c_int32), ("bias_dtype", C.c_int32), ("adapters_enabled", C.c_int32)]
 
 
+class FlatAdamwArgs(C.Structure):
+    _fields_ = [("param", _fp), ("grad", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("operand", _vp), ("norm_out", _fp),
+                ("workspace", _vp), ("n", C.c_int64), ("step", C.c_int64), ("lr", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float), ("max_grad_norm", C.c_float),
+                ("grad_scale", C.c_float), ("operand_dtype", C.c_int32)]
+
+
 _STRUCTS = {0: Schedule, 1: OnlinePsoArgs, 2: DreamboothArgs, 3: StepArgs, 4: StepBwdArgs, 5: GemmArgs,
-            6: LoraLinearArgs}
+            6: LoraLinearArgs, 7: FlatAdamwArgs}
 
 # name -> (restype, argtypes): every symbol include/psob200.h declares
 SIGNATURES = {
@@ -110,6 +117,7 @@ SIGNATURES = {
     "psob200_lora_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "psob200_lora_linear_forward": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
     "psob200_lora_linear_backward": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
+    "psob200_flat_adamw_step": (C.c_int, [C.POINTER(FlatAdamwArgs), _vp]),
     "psob200_scale": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, C.c_int32, C.c_int32, _vp]),
     "psob200_scale_inplace_by_device_scalar": (C.c_int, [_vp, C.c_int64, C.c_int32, _fp, _vp]),
 }

@@ -1,0 +1,122 @@
+// Optimizer boundary of the PSO training step over the FLAT LoRA buffers: global-norm clipping + AdamW + refresh of the
+// 16-bit GEMM operand copies + zeroing of the gradient, in two launches for all 1120 adapter matrices.
+//
+// Replaces, at every accumulation boundary (train_online_pso_sdxl_turbo.py:858-861): accelerate's clip_grad_norm_ (one
+// norm kernel per parameter + stack + norm + one scale per parameter), optimizer.step() (AdamW, :428-448) and
+// optimizer.zero_grad(), plus this repo's own per-layer fp32 -> bf16 operand refresh.  Pure streaming work: 5 fp32 reads
+// + 3 fp32 writes + one 16-bit write per parameter.
+#include <atomic>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace psob200 {
+
+constexpr int kOptThreads = 256;
+
+// sum of squares of the gradient into ws[0] (double), block partials combined with one atomic per block
+__global__ void __launch_bounds__(kOptThreads) flat_sumsq_kernel(const float* __restrict__ g, long long n, double* ws) {
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      const float4 v = *reinterpret_cast<const float4*>(g + i);
+      acc = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, acc))));
+    } else {
+      for (long long j = i; j < n; ++j) acc = fmaf(g[j], g[j], acc);
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float s[kOptThreads / 32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kOptThreads / 32 ? s[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(ws, (double)v);
+  }
+}
+
+struct AdamParams {
+  float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, max_norm, grad_scale;
+};
+
+template <typename TO>
+__global__ void __launch_bounds__(kOptThreads)
+flat_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, TO* __restrict__ op,
+                  long long n, AdamParams a, double* ws, float* norm_out) {
+  // global-norm clip coefficient (accelerate / torch clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)))
+  const float norm = (float)sqrt(ws[0]) * a.grad_scale;
+  const float coef = a.max_norm > 0.f ? fminf(1.f, a.max_norm / (norm + 1e-6f)) * a.grad_scale : a.grad_scale;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * coef;
+    float pi = p[i] * (1.f - a.lr * a.weight_decay);          // decoupled weight decay
+    const float mi = fmaf(1.f - a.beta1, gi - m[i], m[i]);    // exp_avg.lerp_(g, 1 - beta1)
+    const float vi = fmaf(a.beta2, v[i], (1.f - a.beta2) * gi * gi);
+    const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
+    pi -= (a.lr / a.bc1) * (mi / denom);
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+    g[i] = 0.f;                                               // optimizer.zero_grad()
+    if (op != nullptr) Vec8<TO>::store1(op + i, pi);          // the GEMM kernels' 16-bit operand copy
+  }
+  // the last block to finish publishes the norm and leaves the workspace zeroed for the next boundary
+  __shared__ unsigned ticket;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    ticket = atomicAdd(reinterpret_cast<unsigned*>(ws + 1), 1u);
+  }
+  __syncthreads();
+  if (ticket == gridDim.x - 1 && threadIdx.x == 0) {
+    if (norm_out != nullptr) *norm_out = norm;
+    ws[0] = 0.0;
+    *reinterpret_cast<unsigned*>(ws + 1) = 0u;
+  }
+}
+
+}  // namespace psob200
+
+using namespace psob200;
+
+extern "C" int psob200_flat_adamw_step(const psob200_flat_adamw_args* args, void* stream) {
+  if (args == nullptr) return PSOB200_ERR_INVALID_ARG;
+  const psob200_flat_adamw_args& o = *args;
+  if (!o.param || !o.grad || !o.exp_avg || !o.exp_avg_sq || !o.workspace || o.n <= 0 || o.step <= 0)
+    return PSOB200_ERR_INVALID_ARG;
+  if (o.operand && o.operand_dtype != PSOB200_BF16 && o.operand_dtype != PSOB200_F16) return PSOB200_ERR_DTYPE;
+  if (!aligned16(o.grad) || !aligned16(o.workspace)) return PSOB200_ERR_ALIGNMENT;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static std::atomic<int> sms{0};
+  int n_sm = sms.load(std::memory_order_relaxed);
+  if (n_sm <= 0) {
+    n_sm = psob200_device_sm_count();
+    if (n_sm <= 0) n_sm = 148;
+    sms.store(n_sm, std::memory_order_relaxed);
+  }
+  long long blocks = (o.n + kOptThreads * 4 - 1) / (kOptThreads * 4);
+  if (blocks > n_sm * 8) blocks = n_sm * 8;
+  double* ws = reinterpret_cast<double*>(o.workspace);
+  if (o.max_grad_norm > 0.f || o.norm_out != nullptr) {
+    flat_sumsq_kernel<<<(unsigned)blocks, kOptThreads, 0, st>>>(o.grad, o.n, ws);
+    const int rc = consume_launch_error("launch flat_sumsq_kernel", cudaSuccess);
+    if (rc != PSOB200_OK) return rc;
+  }
+  AdamParams a;
+  a.lr = o.lr; a.beta1 = o.beta1; a.beta2 = o.beta2; a.eps = o.eps; a.weight_decay = o.weight_decay;
+  a.bc1 = (float)(1.0 - std::pow((double)o.beta1, (double)o.step));
+  a.bc2_sqrt = (float)std::sqrt(1.0 - std::pow((double)o.beta2, (double)o.step));
+  a.max_norm = o.max_grad_norm;
+  a.grad_scale = o.grad_scale;
+  blocks = (o.n + kOptThreads - 1) / kOptThreads;
+  if (blocks > n_sm * 8) blocks = n_sm * 8;
+  if (o.operand == nullptr || o.operand_dtype == PSOB200_BF16)
+    flat_adamw_kernel<__nv_bfloat16><<<(unsigned)blocks, kOptThreads, 0, st>>>(
+        o.param, o.grad, o.exp_avg, o.exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(o.operand), o.n, a, ws, o.norm_out);
+  else
+    flat_adamw_kernel<__half><<<(unsigned)blocks, kOptThreads, 0, st>>>(
+        o.param, o.grad, o.exp_avg, o.exp_avg_sq, reinterpret_cast<__half*>(o.operand), o.n, a, ws, o.norm_out);
+  return consume_launch_error("launch flat_adamw_kernel", cudaSuccess);
+}

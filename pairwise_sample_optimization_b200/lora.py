@@ -336,17 +336,18 @@ class LoRAGradBucket:
     collective over the flat buffer, averaged over ranks (what DDP does for the reference, bucket by bucket).
     ``clip_grad_norm_`` is accelerate's ``clip_grad_norm_`` (turbo :859) on the flat buffer: one norm, one scale."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], align: int = 8):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable LoRA parameters")
         dev = self.params[0].device
-        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]  # keep every view 16-byte aligned
+        sizes = [(p.numel() + align - 1) // align * align for p in self.params]  # every view (also a 16-bit twin) 16-byte aligned
         self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-        self.views = []
+        self.views, self.offsets = [], []
         off = 0
         for p, n in zip(self.params, sizes):
             v = self.flat[off:off + p.numel()].view(p.shape)
+            self.offsets.append(off)
             off += n
             self.views.append(v)
             if p.dtype == torch.float32:
@@ -381,6 +382,74 @@ class LoRAGradBucket:
         for p, v in zip(self.params, self.views):
             if p.dtype != torch.float32:
                 p.grad = v.to(p.dtype)
+
+
+class FusedLoRAOptimizer:
+    """The optimizer boundary of the training step on the flat LoRA buffers: ``clip_grad_norm_`` + AdamW +
+    ``zero_grad`` + refresh of the 16-bit GEMM operands in two kernel launches (psob200_flat_adamw_step) instead of the
+    reference's per-parameter kernels (train_online_pso_sdxl_turbo.py:428-448 optimizer, :859 clipping, :860-861
+    step / zero_grad).  Parameters, gradients and both Adam moments of every adapter matrix are slices of four flat
+    fp32 buffers with one layout; ``self.bucket`` is the gradient buffer (``all_reduce()`` = the data-parallel exchange).
+    Update rule = ``torch.optim.AdamW`` (decoupled weight decay, bias correction)."""
+
+    def __init__(self, model: nn.Module, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-4, max_grad_norm: float = 1.0):
+        self.layers = lora_layers(model)
+        params = lora_parameters(model)
+        if any(p.dtype != torch.float32 for p in params):
+            raise _lib.Psob200Error("FusedLoRAOptimizer trains fp32 adapter parameters (the shipped mixed-precision recipes)")
+        _lib.require_cuda(*params)
+        self.bucket = LoRAGradBucket(params, align=8)
+        flat = self.bucket.flat
+        self.flat_param = torch.zeros_like(flat)
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        op_dtype = self.layers[0].base_layer.weight.dtype
+        self.flat_operand = torch.zeros(flat.numel(), dtype=op_dtype, device=flat.device)
+        self.workspace = torch.zeros(2, dtype=torch.float64, device=flat.device)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=flat.device)
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.step_count = 0
+        self._unbacked = []  # adapter matrices whose operand copy needs a padded pitch (rank not a multiple of 8)
+        by_param = {}
+        for lay in self.layers:
+            n = lay.active_adapter
+            by_param[id(lay.lora_A[n].weight)] = (lay, "a")
+            by_param[id(lay.lora_B[n].weight)] = (lay, "b")
+        for p, off in zip(self.bucket.params, self.bucket.offsets):
+            view = self.flat_param[off:off + p.numel()].view(p.shape)
+            view.copy_(p.detach())
+            p.data = view  # the parameter now lives in the flat buffer
+            lay, which = by_param[id(p)]
+            if p.shape[1] % 8 == 0:
+                op = self.flat_operand[off:off + p.numel()].view(p.shape)
+                op.copy_(view)
+                lay._op_cache[(which, op_dtype)] = [p._version, p.data_ptr(), op]  # kept current by the fused kernel
+            else:
+                self._unbacked.append((lay, which, op_dtype))
+
+    def all_reduce(self, group=None):
+        return self.bucket.all_reduce(group)
+
+    def step(self) -> torch.Tensor:
+        """Clip, update, zero the gradient, refresh the operands.  Returns the (pre-clip) gradient norm, on the device."""
+        self.step_count += 1
+        a = _lib.FlatAdamwArgs()
+        a.param, a.grad = self.flat_param.data_ptr(), self.bucket.flat.data_ptr()
+        a.exp_avg, a.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        a.operand, a.operand_dtype = self.flat_operand.data_ptr(), _lib.dtype_code(self.flat_operand)
+        a.norm_out, a.workspace = self.grad_norm.data_ptr(), self.workspace.data_ptr()
+        a.n, a.step = self.flat_param.numel(), self.step_count
+        a.lr, a.beta1, a.beta2, a.eps = self.lr, self.betas[0], self.betas[1], self.eps
+        a.weight_decay, a.max_grad_norm, a.grad_scale = self.weight_decay, self.max_grad_norm, 1.0
+        rc = _lib.lib().psob200_flat_adamw_step(C.byref(a), _lib.current_stream(self.flat_param.device))
+        _lib.check(rc, "psob200_flat_adamw_step")
+        for lay, which, dt in self._unbacked:  # padded-pitch copies: re-made in place by the layer itself
+            hit = lay._op_cache.get((which, dt))
+            if hit is not None:
+                hit[0] = -1
+            lay._operand(which, dt)
+        return self.grad_norm
 
 
 # ----------------------------------------------------------------------------------------------- attention processor

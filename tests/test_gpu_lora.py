@@ -197,3 +197,41 @@ def test_cpu_tensor_is_refused(L):
     lay = _layer(L, 64, 64, 4, False, torch.bfloat16, 61)
     with pytest.raises(_lib.Psob200Error):
         lay(torch.zeros(2, 64, dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("r", [8, 4])
+def test_fused_flat_optimizer_matches_torch_adamw_with_clipping(L, r):
+    """psob200_flat_adamw_step (clip + AdamW + zero_grad + operand refresh, two launches) against
+    torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW on the same gradients, three steps."""
+    torch.manual_seed(3)
+    attn = _Attention(640, 2048, 10, 64).to(device="cuda", dtype=torch.bfloat16)
+    wrapped = L.add_adapter(attn, L.LoraConfig(r=r, lora_alpha=r))
+    for m in wrapped:
+        torch.nn.init.normal_(m.lora_B["default"].weight, std=0.05)
+    ref_params = [p.detach().clone().requires_grad_(True) for p in L.lora_parameters(attn)]
+    ref_opt = torch.optim.AdamW(ref_params, lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    opt = L.FusedLoRAOptimizer(attn, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0)
+    params = L.lora_parameters(attn)
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(opt.bucket.params, opt.bucket.views))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for step in range(3):
+        for p, q in zip(params, ref_params):
+            grad = torch.randn(p.shape, device="cuda", generator=g) * (3.0 if step == 0 else 0.01)  # step 0 clips, later ones do not
+            p.grad.copy_(grad)
+            q.grad = grad.clone()
+        want_norm = torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+        ref_opt.step()
+        norm = opt.step()
+        assert abs(norm.item() - want_norm.item()) <= 1e-5 * want_norm.item()
+        assert float(opt.bucket.flat.abs().max()) == 0.0  # zero_grad fused
+        for p, q in zip(params, ref_params):
+            assert (p.detach() - q.detach()).abs().max().item() <= 2e-6 * max(q.detach().abs().max().item(), 1e-3)
+    # the GEMM operands follow the parameters without any per-layer refresh
+    for m in wrapped:
+        for which, lin in (("a", m.lora_A["default"]), ("b", m.lora_B["default"])):
+            op = m._operand(which, torch.bfloat16)
+            assert torch.equal(op, lin.weight.detach().to(torch.bfloat16)) and op.stride(0) % 8 == 0
+    # and the projection still works (forward + backward into the flat gradient)
+    x = _mk((2, 64, 640), 9).cuda().requires_grad_(True)
+    attn.to_q(x).float().square().mean().backward()
+    assert float(opt.bucket.flat.abs().max()) > 0.0
