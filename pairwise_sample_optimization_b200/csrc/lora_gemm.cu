@@ -83,9 +83,10 @@ __device__ __forceinline__ void load_bias32(const void* bias, long long n0, long
 
 // One 32-column chunk of one accumulator row: v[j] belongs to (row, n0 + j).
 template <typename TD, bool kAtomic>
-__device__ __forceinline__ void store_chunk(const GemmKernelParams& p, const float (&v)[32], long long row, long long n0) {
+__device__ __forceinline__ void store_chunk(const GemmKernelParams& p, const float (&v)[32], long long row, long long n0,
+                                            long long n_end) {
   if (row >= p.M) return;
-  const long long nleft = p.N - n0;  // columns of this chunk that exist
+  const long long nleft = n_end - n0;  // columns of this chunk that belong to this tile and exist
   if (p.d != nullptr) {
     TD* dst = reinterpret_cast<TD*>(p.d) + row * p.ldd + n0;
     if constexpr (kAtomic) {
@@ -128,6 +129,7 @@ template <typename TD, bool kAtomic>
 __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_t taddr, long long row, long long n_tile0,
                                               bool add_bias) {
   const int chunks = (p.bn + 31) / 32;
+  const long long n_end = n_tile0 + p.bn < p.N ? n_tile0 + p.bn : p.N;  // a chunk must not spill into the next tile
   uint32_t raw[2][32];
   ptx::tmem_ld_32x32(taddr, raw[0]);
 #pragma unroll 1
@@ -151,7 +153,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(raw[h][j]);
         }
-        if (!(p.diag & 2)) store_chunk<TD, kAtomic>(p, v, row, n0);
+        if (!(p.diag & 2)) store_chunk<TD, kAtomic>(p, v, row, n0, n_end);
       }
     }
   }

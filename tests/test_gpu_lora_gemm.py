@@ -138,3 +138,12 @@ def test_cta_pair_kernel(gemm, M, K, N, r, b_mn):
     if not b_mn:
         got16, _ = gemm.lora_gemm(a1, b1, a2, b2, bias=bias, alpha=0.5, diag=0x10000)
         _check(got16, want, dt)
+
+
+@pytest.mark.parametrize("bn", [16, 48, 80, 144, 208])
+def test_tile_widths_that_are_not_multiples_of_the_epilogue_chunk(gemm, bn):
+    """Several column tiles whose width is not a multiple of the 32-column epilogue chunk: a chunk must not spill into
+    the neighbouring tile."""
+    a, b = _rand(300, 200, torch.bfloat16, 31), _rand(500, 200, torch.bfloat16, 32, 200 ** -0.5)
+    got, _ = gemm.lora_gemm(a, b, out_dtype=torch.float32, tune_bn=bn)
+    _check(got, _ref(a, b), torch.float32)
