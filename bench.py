@@ -364,9 +364,13 @@ def run_b200(args):
         micro(d)  # eager (the event pairs are host-side objects), same kernels as the captured step
     lora.set_timing_sink(None)
     torch.cuda.synchronize()
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in sink)
-    gemm_flops = sum(f for _, _, f, _ in sink)
-    gemm_launches = sum(n for _, _, _, n in sink)
+    gemm_ms = sum(e[0].elapsed_time(e[1]) for e in sink)
+    gemm_flops = sum(e[2] for e in sink)
+    gemm_launches = sum(e[3] for e in sink)
+    by_shape = {}
+    for e in sink:
+        t = by_shape.setdefault(e[4], [0.0, 0, 0.0])
+        t[0] += e[0].elapsed_time(e[1]); t[1] += 1; t[2] += e[2]
     ach = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"kernel": "lora_gemm_kernel (560 LoRA-wrapped projections, forward + backward)", "bound": "tensor",
                 "achieved": round(ach, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
@@ -375,6 +379,9 @@ def run_b200(args):
                 "launches_per_step": gemm_launches // n_inst, "avg_launch_us": round(gemm_ms * 1e3 / max(gemm_launches, 1), 2),
                 "share_of_step": round(gemm_ms / n_inst / ms_per_step, 4),
                 "flops_per_step": gemm_flops / n_inst,
+                "by_call": [{"call": k[0], "M": k[1], "K": k[2], "N": k[3], "calls_per_step": v[1] // n_inst,
+                             "ms_per_step": round(v[0] / n_inst, 2), "tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1)}
+                            for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])],
                 "how": "CUDA-event pair around every psob200_lora_linear_forward/backward call in 2 extra instrumented "
                        "steps (each pair brackets 1-4 back-to-back launches of this kernel and nothing else)"}
     bucket.zero_()
@@ -531,8 +538,9 @@ def main():
                     help="issue the frozen-reference forward on a second stream (default)")
     ap.add_argument("--no-overlap-reference", dest="overlap_reference", action="store_false")
     ap.add_argument("--tiny", action="store_true", help="debug: the 32/64-channel fixture instead of the SDXL architecture")
-    ap.add_argument("--ncu-traffic", type=float, default=None,
-                    help="dram bytes per launch of the loss kernel from the committed ncu --set full capture")
+    ap.add_argument("--ncu-traffic", type=float, default=311483648.0,
+                    help="dram__bytes_read.sum + dram__bytes_write.sum per launch of the loss kernel, from the committed "
+                         "ncu --set full capture profiles/r01_pair_loss_tmem_ncu_raw.txt (268.56 MB + 42.92 MB)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

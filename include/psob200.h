@@ -125,7 +125,9 @@ PSOB200_API size_t psob200_pair_loss_workspace_bytes(int64_t B);
  * human_prefer: float[B*2] rows (h0,h1) as produced by T:401-416 / D:420-434.
  * Outputs: grad_k [B,N] pred_dtype; loss float[1]; stats float[B*8] (may be NULL) =
  *   (logp_pol0, logp_ref0, logp_pol1, logp_ref1, delta0, delta1, z, pair_loss) per pair.
- * tune_threads / tune_cluster: 0 = library heuristics.
+ * tune_threads: 0 = library heuristics (the tensor-memory kernel when N is a multiple of 8 and everything is 16-byte
+ *   aligned, else the general kernel); 1 = the TMA-ring kernel (kept for A/B timing); >= 32 = the general kernel with
+ *   that many threads.  tune_cluster: CTAs per pair (1, 2, 4, 8), 0 = heuristics.
  */
 typedef struct psob200_online_pso_args {
   const void* pred[2];

@@ -192,7 +192,7 @@ class _LoraLinearFn(torch.autograd.Function):
             ev1 = torch.cuda.Event(enable_timing=True)
             ev1.record()
             fl = 2.0 * M * K * N + (2.0 * M * r * (K + N) if enabled else 0.0)
-            _TIMING.append((ev0, ev1, fl, 2 if enabled else 1))
+            _TIMING.append((ev0, ev1, fl, 2 if enabled else 1, ("fwd" if enabled else "fwd-ref", M, K, N)))
         ctx.layer, ctx.enabled, ctx.x_shape, ctx.x_dtype, ctx.want_wgrad = layer, enabled, x.shape, x.dtype, want_wgrad
         ctx.save_for_backward(x2, tt)
         return y.view(*x.shape[:-1], N)
@@ -257,7 +257,7 @@ class _LoraLinearFn(torch.autograd.Function):
                 if wg:
                     fl += 2.0 * M * r * K + 2.0 * M * N * r
                     n_l += 2
-                _TIMING.append((ev0, ev1, fl, n_l))
+                _TIMING.append((ev0, ev1, fl, n_l, ("bwd" + ("" if dx is not None else "-nodx"), M, K, N)))
         del keep
         if dx is not None:
             dx = dx.view(ctx.x_shape)
