@@ -3,10 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--pairs B]
 
-Workload (config.workload) = BASELINE configs[1]: SDXL-Turbo online PSO, LoRA rank 8, 512x512 (64x64 latents), bf16,
-on a random-init SDXL-ARCHITECTURE UNet (fixtures/sdxl_unet.py: 2.57 B parameters, 70 transformer blocks, 560 LoRA-wrapped
-attention projections; diffusers is not installed here).  A "step" is one training micro-step over B pairs, written as the
-reference writes it (train_online_pso_sdxl_turbo.py:771-861):
+Workload (config.workload): the configuration BASELINE.json's metric is quoted on ("SDXL 128x128 latents") = configs[2]'s
+per-GPU slice: SDXL-DMD2 online PSO, LoRA rank 64, 1024x1024 (128x128 latents), bf16 (`--config dmd128`, default); configs[1]
+(SDXL-Turbo, rank 8, 64x64 latents) is `--config turbo64`.  Both run on a random-init SDXL-ARCHITECTURE UNet
+(fixtures/sdxl_unet.py: 2.57 B parameters, 70 transformer blocks, 560 LoRA-wrapped attention projections; diffusers is not
+installed here).  A "step" is one training micro-step over B pairs, written as the reference writes it
+(train_online_pso_sdxl_dmd2.py:773-864 / train_online_pso_sdxl_turbo.py:771-861):
 
     2 UNet forwards with grad (policy) + 2 adapter-disabled forwards without (frozen reference), gradient checkpointing on
     fused PSO loss+grad kernel  (replaces 4 x turbo_step_with_logprob + the inline loss + its backward)
@@ -49,12 +51,18 @@ if ROOT not in sys.path:
 
 METRIC = "pso_train_pairs_per_sec"
 UNIT = "pairs/s"
-LATENT_HW = 64
-RANK = 8
-ACCUM = 6  # gradient_accumulation_steps (2) x trained timesteps (3): turbo trainer :232
-WORKLOAD = ("BASELINE configs[1]: SDXL-Turbo online PSO micro-step (2 policy + 2 frozen-reference UNet forwards, fused PSO "
-            "loss+grad, backward), random-init SDXL-architecture UNet (2.57 B params, 560 LoRA projections), LoRA rank 8, "
-            "64x64 latents, bf16, gradient checkpointing, optimizer step every 6 micro-steps")
+ACCUM = 6  # gradient_accumulation_steps (2) x trained timesteps (3): turbo trainer :232, dmd2 trainer :236
+_COMMON = ("online PSO micro-step (2 policy + 2 frozen-reference UNet forwards, fused PSO loss+grad, backward), random-init "
+           "SDXL-architecture UNet (2.57 B params, 560 LoRA projections), bf16, gradient checkpointing, optimizer step every 6 "
+           "micro-steps")
+# BASELINE.json's metric is quoted on SDXL 128x128 latents = configs[2] (SDXL-DMD2, rank 64, 1024 px): the default.
+# configs[1] (SDXL-Turbo, rank 8, 64x64 latents, the reference's 512-px recipe) is `--config turbo64`.
+CONFIGS = {
+    "dmd128": {"kind": "dmd", "latent_hw": 128, "rank": 64,
+               "workload": "BASELINE configs[2] per-GPU slice: SDXL-DMD2 " + _COMMON + ", LoRA rank 64, 128x128 latents (1024 px)"},
+    "turbo64": {"kind": "turbo", "latent_hw": 64, "rank": 8,
+                "workload": "BASELINE configs[1]: SDXL-Turbo " + _COMMON + ", LoRA rank 8, 64x64 latents (512 px)"},
+}
 
 
 # ----------------------------------------------------------------------------------------------- utilities
@@ -125,6 +133,13 @@ def measured_peaks():
                 "tf_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
                 "source": "measured (MEASURED_PEAKS.json)"}
     return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def dmd_scheduler():
+    """SDXL alphas_cumprod (scaled_linear betas; restated, see oracle/schedules.py): all the DMD2 / LCM step reads."""
+    import types
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2
+    return types.SimpleNamespace(alphas_cumprod=torch.cumprod(1.0 - betas, dim=0))
 
 
 def turbo_scheduler():
@@ -224,6 +239,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.pairs, args.steps, max(args.warmup, 3)
     peaks = measured_peaks()
+    conf = CONFIGS[args.config]
+    KIND, LATENT_HW, RANK = conf["kind"], conf["latent_hw"], conf["rank"]
 
     # ---- model: random-init SDXL-architecture UNet in bf16, LoRA rank 8 on to_q/to_k/to_v/to_out.0
     torch.manual_seed(1234)  # same base weights on every rank (as a checkpoint would give)
@@ -241,9 +258,10 @@ def run_b200(args):
     # boundary is one all-reduce + two launches (clip + AdamW + zero_grad + 16-bit operand refresh)
     opt = lora.FusedLoRAOptimizer(unet, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_grad_norm=1.0)
     bucket = opt.bucket
-    sched = turbo_scheduler()
+    sched = turbo_scheduler() if KIND == "turbo" else dmd_scheduler()
     pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
-    host = micro_step.synth_batch(B, LATENT_HW, cfg.cross_attention_dim, pooled, 100 + rank, sched.sigmas, dtype=torch.bfloat16)
+    host = micro_step.synth_batch(B, LATENT_HW, cfg.cross_attention_dim, pooled, 100 + rank, getattr(sched, "sigmas", None),
+                                  dtype=torch.bfloat16, kind=KIND)
     if not args.separate_forwards:
         host = micro_step.batched_view(host)
     host = {k: v.pin_memory() for k, v in host.items()}
@@ -254,7 +272,7 @@ def run_b200(args):
 
     def micro(batch):
         kw = {"ref_stream": ref_stream} if ref_stream is not None else {}
-        return fwd_bwd(pso, lora, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM, **kw)
+        return fwd_bwd(pso, lora, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM, kind=KIND, **kw)
 
     def optimizer_boundary(i):
         if (i + 1) % ACCUM == 0:  # turbo trainer :858-861 (sync_gradients): all-reduce, clip, AdamW, zero_grad
@@ -401,7 +419,8 @@ def run_b200(args):
             "ms_per_step": round(ms_per_step, 3), "ms_per_step_each": [round(v, 1) for v in per_step],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD if not args.tiny else "TINY fixture (debug run, not the benchmark)",
+            "config": {"workload": conf["workload"] if not args.tiny else "TINY fixture (debug run, not the benchmark)",
+                       "name": args.config,
                        "pairs_per_gpu_per_step": B, "latent_shape": [4, LATENT_HW, LATENT_HW], "lora_rank": RANK,
                        "beta": 50.0, "eps": 0.1, "accum": ACCUM,
                        "parallelism": f"dp{world} (pairs sharded; one all-reduce of the flat LoRA gradient per {ACCUM} steps)",
@@ -452,17 +471,21 @@ def _make_cpu_step(args, pairs):
                 mod.weight.fill_(1.0)
                 mod.bias.zero_()
     unet.requires_grad_(False)
+    conf = CONFIGS[args.config]
+    KIND, LATENT_HW, RANK = conf["kind"], conf["latent_hw"], conf["rank"]
     wrapped = olora.oracle_add_adapter(unet, RANK, RANK)
     for m in wrapped:
         torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
     unet.train()
     unet.enable_gradient_checkpointing()
-    sched = schedules.turbo_scheduler(4)
+    sched = schedules.turbo_scheduler(4) if KIND == "turbo" else schedules.dmd_scheduler()
     pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
-    batch = micro_step.synth_batch(pairs, LATENT_HW, cfg.cross_attention_dim, pooled, 100, sched.sigmas)
+    batch = micro_step.synth_batch(pairs, LATENT_HW, cfg.cross_attention_dim, pooled, 100, getattr(sched, "sigmas", None),
+                                   kind=KIND)
 
     def one():
-        loss = micro_step.oracle_micro_step(olora, olosses, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM)
+        loss = micro_step.oracle_micro_step(olora, olosses, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM,
+                                            kind=KIND)
         for m in wrapped:
             m.lora_A["default"].weight.grad = None
             m.lora_B["default"].weight.grad = None
@@ -512,9 +535,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
             "steps": len(times), "steps_requested": K, "warmup": W, "ms_per_step": round(ms, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD + " -- oracle port of the reference's PyTorch path on the host cores",
-                       "pairs_per_step": pairs, "latent_shape": [4, LATENT_HW, LATENT_HW], "lora_rank": RANK, "beta": 50.0,
-                       "eps": 0.1},
+            "config": {"workload": CONFIGS[args.config]["workload"] + " -- oracle port of the reference's PyTorch path on the "
+                                   "host cores", "name": args.config,
+                       "pairs_per_step": pairs,
+                       "latent_shape": [4, CONFIGS[args.config]["latent_hw"], CONFIGS[args.config]["latent_hw"]],
+                       "lora_rank": CONFIGS[args.config]["rank"], "beta": 50.0, "eps": 0.1},
             "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "loss": round(res, 6)}
@@ -527,6 +552,8 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="dmd128", choices=sorted(CONFIGS),
+                    help="dmd128 = the configuration BASELINE.json's metric is quoted on (SDXL 128x128 latents); turbo64 = configs[1]")
     ap.add_argument("--pairs", type=int, default=4, help="pairs per GPU per micro-step (train.batch_size of the shipped recipe)")
     ap.add_argument("--cpu-pairs", type=int, default=1, help="pairs in the bounded CPU sample")
     ap.add_argument("--ref-budget-seconds", type=float, default=200.0)

@@ -10,24 +10,33 @@ import torch
 TURBO_TS = [999, 749, 499]  # trained timesteps: first 3 of the 4-step trailing schedule (turbo :617)
 
 
-def synth_batch(B, latent_hw, cross_dim, pooled_dim, seed, sigmas, dtype=torch.float32, device="cpu"):
-    """Synthetic stored trajectories of one micro-step: per pair and branch the current latent
-    (sigma-scaled noise), the UNet input (latent / sqrt(sigma^2+1), turbo :121), the stored next latent, one trained
-    timestep per pair, prompt embeddings and the reward sign."""
+DMD_STEP_RATIO = 250        # 1000 // num_steps (dmd2 trainer :542); prev_timestep = t - step_ratio (:816)
+
+
+def synth_batch(B, latent_hw, cross_dim, pooled_dim, seed, sigmas=None, dtype=torch.float32, device="cpu", kind="turbo"):
+    """Synthetic stored trajectories of one micro-step: per pair and branch the current latent, the
+    UNet input, the stored next latent, one trained timestep per pair, prompt embeddings and the reward sign.
+    kind="turbo": latents are sigma-scaled noise and the UNet sees latent / sqrt(sigma^2+1) (turbo :121, :776);
+    kind="dmd":   unit-variance latents, fed to the UNet unscaled (dmd2 :778), 1024x1024 time ids (:347-355)."""
     g = torch.Generator().manual_seed(seed)
     idx = torch.randint(0, len(TURBO_TS), (B,), generator=g)
-    ts = torch.tensor(TURBO_TS)[idx]
-    sig = sigmas[idx].float()
-    sig_next = sigmas[idx + 1].float()
+    ts = torch.tensor(TURBO_TS)[idx]  # both samplers train the first 3 of [999, 749, 499, 249]
     out = {"timesteps": ts, "step_index": idx}
+    if kind == "turbo":
+        sig = sigmas[idx].float()[:, None, None, None]
+        sig_next = sigmas[idx + 1].float()[:, None, None, None]
+        in_scale = 1.0 / (sig ** 2 + 1) ** 0.5
+    else:
+        sig = sig_next = in_scale = torch.ones(B, 1, 1, 1)
     for k in (0, 1):
-        lat = torch.randn(B, 4, latent_hw, latent_hw, generator=g) * sig[:, None, None, None]
+        lat = torch.randn(B, 4, latent_hw, latent_hw, generator=g) * sig
         out[f"latents_{k}"] = lat
-        out[f"input_latents_{k}"] = lat / (sig[:, None, None, None] ** 2 + 1) ** 0.5
-        out[f"next_latents_{k}"] = torch.randn(B, 4, latent_hw, latent_hw, generator=g) * sig_next[:, None, None, None]
+        out[f"input_latents_{k}"] = lat * in_scale
+        out[f"next_latents_{k}"] = torch.randn(B, 4, latent_hw, latent_hw, generator=g) * sig_next
     out["prompt_embeds"] = torch.randn(B, 77, cross_dim, generator=g)
     out["text_embeds"] = torch.randn(B, pooled_dim, generator=g)
-    out["time_ids"] = torch.tensor([[512.0, 512.0, 0.0, 0.0, 512.0, 512.0]]).repeat(B, 1)
+    px = 8.0 * latent_hw
+    out["time_ids"] = torch.tensor([[px, px, 0.0, 0.0, px, px]]).repeat(B, 1)
     sign = torch.randint(0, 2, (B,), generator=g).float() * 2 - 1
     out["human_prefer"] = torch.stack([-sign, sign], 1)
     cast = lambda t: t.to(device=device, dtype=dtype) if t.is_floating_point() else t.to(device)
@@ -39,7 +48,11 @@ def _unet_call(unet, x, ts, batch):
                                                                   "time_ids": batch["time_ids"].to(x.dtype)}).sample
 
 
-def product_micro_step(pso, lora, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0):
+def _loss_kind(kind):
+    return {"kind": kind, "step_ratio": DMD_STEP_RATIO if kind == "dmd" else None}
+
+
+def product_micro_step(pso, lora, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0, kind="turbo"):
     """Product path: 2 policy forwards with grad, 2 adapter-disabled forwards without (turbo :775-805), the fused
     loss+grad kernel in place of the four step calls + inline loss (:810-850), backward (:857)."""
     ts = batch["timesteps"]
@@ -52,7 +65,7 @@ def product_micro_step(pso, lora, unet, batch, sched, *, beta=50.0, eps=0.1, los
     lora.enable_adapters(unet)
     loss = pso.pso_pair_loss(p0, p1, r0, r1, batch["latents_0"], batch["latents_1"],
                              batch["next_latents_0"], batch["next_latents_1"], ts, ts, batch["human_prefer"],
-                             scheduler=sched, kind="turbo", beta=beta, eps=eps, loss_scale=loss_scale)
+                             scheduler=sched, beta=beta, eps=eps, loss_scale=loss_scale, **_loss_kind(kind))
     loss.backward()
     return loss
 
@@ -69,7 +82,8 @@ def batched_view(batch):
     return out
 
 
-def product_micro_step_batched(pso, lora, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0, ref_stream=None):
+def product_micro_step_batched(pso, lora, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0, ref_stream=None,
+                               kind="turbo"):
     """Same micro-step with ONE policy forward and ONE frozen-reference forward of batch 2B (``batched_view``).
     With ``ref_stream`` the no-grad reference forward is issued on a second CUDA stream: it is independent of the policy
     forward, and most kernels of a batch-8 forward leave SMs idle, so the two overlap (inside a captured CUDA graph the
@@ -95,12 +109,12 @@ def product_micro_step_batched(pso, lora, unet, batch, sched, *, beta=50.0, eps=
     ts = batch["timesteps"]
     loss = pso.pso_pair_loss(pol[:B], pol[B:], ref[:B], ref[B:], batch["latents_0"], batch["latents_1"],
                              batch["next_latents_0"], batch["next_latents_1"], ts, ts, batch["human_prefer"],
-                             scheduler=sched, kind="turbo", beta=beta, eps=eps, loss_scale=loss_scale)
+                             scheduler=sched, beta=beta, eps=eps, loss_scale=loss_scale, **_loss_kind(kind))
     loss.backward()
     return loss
 
 
-def oracle_micro_step(olora, olosses, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0):
+def oracle_micro_step(olora, olosses, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0, kind="turbo"):
     """The reference's flow restated with the oracle pieces (CPU): same four forwards, four step-with-logprob calls,
     inline loss, autograd backward."""
     ts = batch["timesteps"]
@@ -111,9 +125,10 @@ def oracle_micro_step(olora, olosses, unet, batch, sched, *, beta=50.0, eps=0.1,
         r0 = _unet_call(unet, batch["input_latents_0"], ts, batch)
         r1 = _unet_call(unet, batch["input_latents_1"], ts, batch)
     olora.oracle_set_adapters(unet, True)
-    loss, _ = olosses.online_micro_step("turbo", sched, [p0.float(), p1.float()], [r0.float(), r1.float()],
+    loss, _ = olosses.online_micro_step(kind, sched, [p0.float(), p1.float()], [r0.float(), r1.float()],
                                         [batch["latents_0"].float(), batch["latents_1"].float()],
                                         [batch["next_latents_0"].float(), batch["next_latents_1"].float()], [ts, ts],
-                                        batch["human_prefer"], beta, eps)
+                                        batch["human_prefer"], beta, eps,
+                                        step_ratio=DMD_STEP_RATIO if kind == "dmd" else None)
     (loss * loss_scale).backward()
     return loss * loss_scale
