@@ -556,7 +556,7 @@ def main():
                     help="dmd128 = the configuration BASELINE.json's metric is quoted on (SDXL 128x128 latents); turbo64 = configs[1]")
     ap.add_argument("--pairs", type=int, default=4, help="pairs per GPU per micro-step (train.batch_size of the shipped recipe)")
     ap.add_argument("--cpu-pairs", type=int, default=1, help="pairs in the bounded CPU sample")
-    ap.add_argument("--ref-budget-seconds", type=float, default=200.0)
+    ap.add_argument("--ref-budget-seconds", type=float, default=150.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-figures", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the micro-step eagerly instead of replaying a CUDA graph")
