@@ -46,20 +46,20 @@ def _build(lora, r, seed, gradient_checkpointing):
     return cfg, cpu, gpu, wrapped_o, wrapped_g
 
 
-@pytest.mark.parametrize("gradient_checkpointing", [False, True])
-def test_config1_tiny_unet_micro_step(mods, gradient_checkpointing):
+@pytest.mark.parametrize("kind,gradient_checkpointing", [("turbo", False), ("turbo", True), ("dmd", True)])
+def test_config1_tiny_unet_micro_step(mods, kind, gradient_checkpointing):
     pso, lora = mods
     r, B = 4, 2
     cfg, cpu, gpu, wo, wg = _build(lora, r, 0, gradient_checkpointing)
-    sched = schedules.turbo_scheduler(4)
-    batch = micro_step.synth_batch(B, 64, cfg.cross_attention_dim, 32, 5, sched.sigmas)
+    sched = schedules.turbo_scheduler(4) if kind == "turbo" else schedules.dmd_scheduler()
+    batch = micro_step.synth_batch(B, 64, cfg.cross_attention_dim, 32, 5, getattr(sched, "sigmas", None), kind=kind)
     to_gpu = {k: (v.cuda().bfloat16() if v.is_floating_point() and k not in ("human_prefer", "time_ids") else v.cuda())
               for k, v in batch.items()}
     # the oracle sees the same bf16-rounded inputs
     batch = {k: (v.bfloat16().float() if v.is_floating_point() and k not in ("human_prefer", "time_ids") else v)
              for k, v in batch.items()}
     bucket = lora.LoRAGradBucket(lora.lora_parameters(gpu))
-    kw = dict(beta=5.0, eps=0.9)
+    kw = dict(beta=5.0, eps=0.9, kind=kind)
     loss_g = micro_step.product_micro_step(pso, lora, gpu, to_gpu, sched, **kw)
     loss_o = micro_step.oracle_micro_step(olora, olosses, cpu, batch, sched, **kw)
     pso.check_status()
