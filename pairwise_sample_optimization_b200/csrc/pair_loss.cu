@@ -1,24 +1,24 @@
 // Fused pairwise PSO loss + gradient (sm_100a).
 //
-// One thread-block CLUSTER per (win, lose) pair.  Every CTA owns a contiguous slab of the pair's
-// eight tensors (policy / frozen-reference predictions, current and next latents, both branches):
+// Per (win, lose) pair the eight tensors (policy / frozen-reference predictions, current and next latents, both
+// branches) are processed in two passes with the residuals kept ON CHIP in between:
 //
-//   pass 1  stream the slab from HBM, form the policy residual r = x' - (k x + a eps) and the three
-//           per-branch sums  S_pol = sum r^2,  S_ref = sum r_ref^2,  D = sum (r_ref^2 - r^2);
-//   reduce  warp shuffles -> shared memory -> distributed shared memory all-gather over the cluster;
-//           every CTA evaluates the pair's scalar loss function redundantly in fp64 (deterministic,
-//           no atomics on the data path);
-//   pass 2  write grad = g_k * r from the residuals kept ON CHIP.
+//   pass 1  stream the pair from HBM, form the policy residual r = x' - (k x + a eps) and, per branch, the sums needed
+//           for  S_pol = sum r^2,  S_ref = sum r_ref^2,  D = S_ref - S_pol;
+//   reduce  warp shuffles -> shared memory -> distributed shared memory over the cluster that shares the pair; the
+//           pair's scalar loss function (clamp gate, log-sigmoid / hinge, prior) gives one multiplier per branch;
+//           deterministic: fixed summation order, no atomics on the data path;
+//   pass 2  write grad = g_k * r from the on-chip residuals.
 //
 // HBM traffic is the algorithmic 8N reads + 2N writes per pair.
 //
-// Two kernels share that structure:
-//   pair_loss_grad_tma_kernel  (fast path) the slab is fetched by 1-D TMA bulk copies
-//           (cp.async.bulk ... mbarrier::complete_tx) issued up front by one thread into a shared-memory
-//           ring: the whole slab is in flight at once with no register staging, overlapping the fp64
-//           coefficient prologue; residuals live in registers (32 per thread).
-//   pair_loss_grad_kernel      (general path) vectorised or scalar LDG, residuals in shared memory;
-//           any N, any alignment, up to 25600 elements per branch per CTA.
+// Three kernels share that structure (profiles/r01_pair_loss.md):
+//   pair_loss_grad_tmem_kernel  (fast path, pair_loss_tmem.cuh) residuals parked in TENSOR MEMORY (tcgen05.st / ld),
+//           1024 threads per SM, a per-thread cp.async ring of 192 KB, cluster of 1 (64^2 latents) or 2 (128^2);
+//   pair_loss_grad_tma_kernel   (second design, pair_loss_tma.cuh, kept for A/B timing: tune_threads = 1) 1-D TMA ring,
+//           residuals in registers, st.async partial-sum exchange;
+//   pair_loss_grad_kernel       (general path, this file) vectorised or scalar LDG, residuals in shared memory;
+//           any N, any alignment, up to 25600 elements per branch per CTA, one cluster per pair.
 //
 // Replaces: train_online_pso_sdxl_turbo.py:810-850,857 / train_online_pso_sdxl_dmd2.py:812-854,859
 // (online) and train_pso_sdxl_turbo_dreambooth.py:1847-1865,1881-1935,1953 (DreamBooth).

@@ -1,5 +1,6 @@
-// Fast path of the fused pair-loss kernel: PERSISTENT clusters, a continuous TMA ring, and a
-// barrier-free cross-CTA reduction.
+// SECOND design of the fused pair-loss kernel (superseded as the fast path by pair_loss_tmem.cuh; selectable with
+// tune_threads = 1 for A/B timing): PERSISTENT clusters, a continuous TMA ring, and a barrier-free cross-CTA reduction.
+// It also defines PairEntry / pair_scalar_function_fast / kTabPairs, which the tensor-memory kernel reuses.
 //
 // What the profiles said (profiles/r01_pair_loss.md): with one cluster per pair the kernel was bound by
 // synchronisation, not memory -- cluster launch/hand-shake, barrier.cluster (which carries a GPU-scope
