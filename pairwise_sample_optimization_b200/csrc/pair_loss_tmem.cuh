@@ -73,6 +73,50 @@ __device__ __forceinline__ void residual8_u(const float (&vx)[8], const float (&
   }
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): two lanes per instruction, each lane rounds like the scalar op
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// residual8_u on packed pairs: 24 instead of 48 floating-point instructions per 8-element chunk.  The three sums are
+// kept as (even-element, odd-element) lane pairs and folded by the caller.
+template <bool HAS_REF>
+__device__ __forceinline__ void residual8_u2(const float (&vx)[8], const float (&vn)[8], const float (&vp)[8],
+                                             const float (&vr)[8], f32x2 nkx, f32x2 nca, float (&r)[8], f32x2& s_t,
+                                             f32x2& s_ur, f32x2& s_uu) {
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    const f32x2 p2 = pack2(vp[i], vp[i + 1]);
+    const f32x2 rt = fma2(nca, p2, fma2(nkx, pack2(vx[i], vx[i + 1]), pack2(vn[i], vn[i + 1])));
+    unpack2(rt, r[i], r[i + 1]);
+    s_t = fma2(rt, rt, s_t);
+    if constexpr (HAS_REF) {
+      const f32x2 u = sub2(p2, pack2(vr[i], vr[i + 1]));
+      s_ur = fma2(u, rt, s_ur);
+      s_uu = fma2(u, u, s_uu);
+    }
+  }
+}
+
 template <typename TP, typename TL, bool HAS_REF>
 struct V3Cfg {
   static constexpr int kNPred = HAS_REF ? 2 : 1;
@@ -221,8 +265,8 @@ __global__ void __launch_bounds__(V3Cfg<TP, TL, HAS_REF>::kThreads, 1) pair_loss
     uint32_t tcol = tmem_mine + col0;
 #pragma unroll 1
     for (int k = 0; k < 2; ++k) {
-      const float ck = ent.c[k].k, ca = ent.c[k].a;
-      float s_t = 0.f, s_r = 0.f, s_d = 0.f;
+      const f32x2 nkx = pack2(-ent.c[k].k, -ent.c[k].k), nca = pack2(-ent.c[k].a, -ent.c[k].a);
+      f32x2 s_t2 = 0ull, s_r2 = 0ull, s_d2 = 0ull;  // (+0.0f, +0.0f)
 #pragma unroll 1
       for (int j = 0; j < Ib; ++j) {
         cp_async_wait<D - 1>();  // this thread's pieces of the oldest chunk-iteration in flight have landed
@@ -232,12 +276,16 @@ __global__ void __launch_bounds__(V3Cfg<TP, TL, HAS_REF>::kThreads, 1) pair_loss
         lds_chunk<TL, T>(slot + Cfg::kOffXn, tid, vn);
         lds_chunk<TP, T>(slot + Cfg::kOffP, tid, vp);
         if constexpr (HAS_REF) lds_chunk<TP, T>(slot + Cfg::kOffR, tid, vr);
-        residual8_u<HAS_REF>(vx, vn, vp, vr, ck, ca, r, s_t, s_r, s_d);  // (sum r^2, sum u r, sum u^2); zero-filled chunks add 0
+        residual8_u2<HAS_REF>(vx, vn, vp, vr, nkx, nca, r, s_t2, s_r2, s_d2);  // (sum r^2, sum u r, sum u^2); zero-filled chunks add 0
         issue();  // refill the slot just drained (its values are in registers)
         tmem_st8(tcol, r);
         tcol += 8u;
         if (++slot_i == D) slot_i = 0;
       }
+      float lo, hi, s_t, s_r, s_d;
+      unpack2(s_t2, lo, hi); s_t = lo + hi;
+      unpack2(s_r2, lo, hi); s_r = lo + hi;
+      unpack2(s_d2, lo, hi); s_d = lo + hi;
       if (k == 0) { acc[0] = s_t; acc[1] = s_r; acc[2] = s_d; }  // (no runtime-indexed register array)
       else        { acc[3] = s_t; acc[4] = s_r; acc[5] = s_d; }
     }
@@ -298,6 +346,7 @@ __global__ void __launch_bounds__(V3Cfg<TP, TL, HAS_REF>::kThreads, 1) pair_loss
 #pragma unroll 1
     for (int k = 0; k < 2; ++k) {
       const float gk = s_g[k];
+      const f32x2 gk2 = pack2(gk, gk);
       TP* gp = reinterpret_cast<TP*>(a.grad[k]) + pair * a.N + (cbeg + tid) * 8;
       int lc = tid;
 #pragma unroll 1
@@ -307,7 +356,7 @@ __global__ void __launch_bounds__(V3Cfg<TP, TL, HAS_REF>::kThreads, 1) pair_loss
         if (lc < mine) {
           float o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = gk * r[e];
+          for (int e = 0; e < 8; e += 2) unpack2(mul2(gk2, pack2(r[e], r[e + 1])), o[e], o[e + 1]);
           Vec8<TP>::store(gp, o);
         }
       }
