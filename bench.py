@@ -252,8 +252,12 @@ def run_b200(args):
     for m in wrapped:  # the reference starts from B = 0; use a small non-zero B so every adapter GEMM does real work
         torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
     unet.set_attn_processor(lora.PSOAttnProcessor2_0())
+    if args.fused_geglu:  # the feed-forward's gated GELU on one fused kernel each way (outside SURVEY section 8's rows)
+        from pairwise_sample_optimization_b200 import feed_forward
+        feed_forward.install_fused_geglu(unet)
     unet.train()
-    unet.enable_gradient_checkpointing()  # turbo trainer :358
+    if args.grad_checkpointing:
+        unet.enable_gradient_checkpointing()  # turbo trainer :358
     # parameters, gradients and Adam moments of all 1120 adapter matrices live in four flat fp32 buffers: the optimizer
     # boundary is one all-reduce + two launches (clip + AdamW + zero_grad + 16-bit operand refresh)
     opt = lora.FusedLoRAOptimizer(unet, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_grad_norm=1.0)
@@ -431,7 +435,7 @@ def run_b200(args):
                        "timing": ("eager launches" if args.no_graph else "micro-step replayed from one CUDA graph; optimizer "
                                   "boundary eager") + ", CUDA events around K steps, max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
-            "loss": round(loss_value, 6),
+            "loss": round(loss_value, 6), "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
         }
         line.update(extra)
         if cpu is not None:
@@ -564,6 +568,12 @@ def main():
     ap.add_argument("--overlap-reference", action="store_true", default=True,
                     help="issue the frozen-reference forward on a second stream (default)")
     ap.add_argument("--no-overlap-reference", dest="overlap_reference", action="store_false")
+    ap.add_argument("--grad-checkpointing", dest="grad_checkpointing", action="store_true", default=True,
+                    help="recompute the transformer blocks in the backward (the reference's setting, turbo trainer :358)")
+    ap.add_argument("--no-grad-checkpointing", dest="grad_checkpointing", action="store_false",
+                    help="keep the activations of the micro-step resident in HBM instead of recomputing them")
+    ap.add_argument("--no-fused-geglu", dest="fused_geglu", action="store_false", default=True,
+                    help="leave the feed-forward's GEGLU on the stock torch kernels")
     ap.add_argument("--tiny", action="store_true", help="debug: the 32/64-channel fixture instead of the SDXL architecture")
     ap.add_argument("--ncu-traffic", type=float, default=311483648.0,
                     help="dram__bytes_read.sum + dram__bytes_write.sum per launch of the loss kernel, from the committed "

@@ -424,10 +424,33 @@ typedef struct psob200_flat_adamw_args {
 
 PSOB200_API int psob200_flat_adamw_step(const psob200_flat_adamw_args* args, void* stream);
 
+/*
+ * Gated GELU of the transformer feed-forward that sits between the LoRA-wrapped attention blocks (diffusers==0.27.0
+ * GEGLU.forward: `hidden, gate = self.proj(x).chunk(2, dim=-1); return hidden * F.gelu(gate)`), forward and backward
+ * in one launch each.  Not a row of the PSO hot path: it is here because the stock lowering of that
+ * line was the largest single item of the measured micro-step.
+ *   proj  [M, 2 I] (row pitch ld_proj): first I columns = hidden, last I = gate.
+ *   forward:  out[M, I]   = hidden * gelu(gate)                 (exact erf GELU, fp32 arithmetic)
+ *   backward: dproj[M, 2 I] = [ dout * gelu(gate) | dout * hidden * gelu'(gate) ]
+ * I and the row pitches must be multiples of 16 bytes worth of elements; pointers 16-byte aligned.
+ */
+typedef struct psob200_geglu_args {
+  const void* proj;
+  void* out;
+  const void* dout;
+  void* dproj;
+  int64_t M, I;
+  int64_t ld_proj, ld_out, ld_dout, ld_dproj;
+  int32_t dtype;
+} psob200_geglu_args;
+
+PSOB200_API int psob200_geglu_forward(const psob200_geglu_args* args, void* stream);
+PSOB200_API int psob200_geglu_backward(const psob200_geglu_args* args, void* stream);
+
 /* sizeof() of the argument structs as compiled into the library, for FFI bindings to
  * verify their mirror of this header: which = 0 schedule, 1 online_pso_args,
  * 2 dreambooth_args, 3 step_args, 4 step_bwd_args, 5 gemm_args,
- * 6 lora_linear_args, 7 flat_adamw_args.  Returns 0 for unknown ids. */
+ * 6 lora_linear_args, 7 flat_adamw_args, 8 geglu_args.  Returns 0 for unknown ids. */
 PSOB200_API size_t psob200_struct_size(int which);
 
 #ifdef __cplusplus

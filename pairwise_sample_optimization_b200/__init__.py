@@ -6,12 +6,13 @@ Only what the path needs:
 * ``pso_pytorch.diffusers_patch`` drop-ins for the reference's step / sampler functions (same names)
 * ``losses``                      fused online-PSO and DreamBooth-PSO loss + gradient
 * ``lora`` / ``gemm``              LoRA-wrapped attention projections (peft / diffusers surface) on the tcgen05 GEMM kernels
+* ``feed_forward``                fused gated GELU (GEGLU) of the transformer feed-forward, forward + backward
 * ``checkpoint``                  LoRA adapters in the reference's safetensors wire format
 * ``runtime``                     device-resident schedule tables, workspace, status word
 
 There is no CPU or PyTorch fallback: every op raises if the CUDA library is missing.
 """
-from . import _lib, checkpoint, gemm, lora, runtime
+from . import _lib, checkpoint, feed_forward, gemm, lora, runtime
 from .losses import compare, pso_db_loss, pso_pair_loss, sample_compare
 from .pso_pytorch.diffusers_patch import (
     _get_x0_from_noise,

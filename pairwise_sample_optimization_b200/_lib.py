@@ -96,8 +96,14 @@ class FlatAdamwArgs(C.Structure):
                 ("grad_scale", C.c_float), ("operand_dtype", C.c_int32)]
 
 
+class GegluArgs(C.Structure):
+    _fields_ = [("proj", _vp), ("out", _vp), ("dout", _vp), ("dproj", _vp), ("M", C.c_int64), ("I", C.c_int64),
+                ("ld_proj", C.c_int64), ("ld_out", C.c_int64), ("ld_dout", C.c_int64), ("ld_dproj", C.c_int64),
+                ("dtype", C.c_int32)]
+
+
 _STRUCTS = {0: Schedule, 1: OnlinePsoArgs, 2: DreamboothArgs, 3: StepArgs, 4: StepBwdArgs, 5: GemmArgs,
-            6: LoraLinearArgs, 7: FlatAdamwArgs}
+            6: LoraLinearArgs, 7: FlatAdamwArgs, 8: GegluArgs}
 
 # name -> (restype, argtypes): every symbol include/psob200.h declares
 SIGNATURES = {
@@ -118,6 +124,8 @@ SIGNATURES = {
     "psob200_lora_linear_forward": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
     "psob200_lora_linear_backward": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
     "psob200_flat_adamw_step": (C.c_int, [C.POINTER(FlatAdamwArgs), _vp]),
+    "psob200_geglu_forward": (C.c_int, [C.POINTER(GegluArgs), _vp]),
+    "psob200_geglu_backward": (C.c_int, [C.POINTER(GegluArgs), _vp]),
     "psob200_scale": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, C.c_int32, C.c_int32, _vp]),
     "psob200_scale_inplace_by_device_scalar": (C.c_int, [_vp, C.c_int64, C.c_int32, _fp, _vp]),
 }

@@ -10,21 +10,29 @@ from fixtures import micro_step, sdxl_unet
 from pairwise_sample_optimization_b200 import lora
 from torch.profiler import profile, ProfilerActivity
 
+import argparse
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="dmd128", choices=sorted(bench.CONFIGS))
+ap.add_argument("--pairs", type=int, default=4)
+ap.add_argument("--top", type=int, default=40)
+args = ap.parse_args()
+conf = bench.CONFIGS[args.config]
 dev = torch.device("cuda", 0)
 torch.manual_seed(1234)
 cfg = sdxl_unet.sdxl_config()
 with torch.device(dev):
     unet = sdxl_unet.UNet2DConditionModel(cfg)
 unet = unet.to(torch.bfloat16).requires_grad_(False)
-wrapped = lora.add_adapter(unet, lora.LoraConfig(r=8, lora_alpha=8))
+wrapped = lora.add_adapter(unet, lora.LoraConfig(r=conf["rank"], lora_alpha=conf["rank"]))
 for m in wrapped:
     torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
 unet.set_attn_processor(lora.PSOAttnProcessor2_0()); unet.train(); unet.enable_gradient_checkpointing()
 bucket = lora.LoRAGradBucket(lora.lora_parameters(unet))
-sched = bench.turbo_scheduler()
-host = micro_step.batched_view(micro_step.synth_batch(4, 64, 2048, 1280, 100, sched.sigmas, dtype=torch.bfloat16))
+sched = bench.turbo_scheduler() if conf["kind"] == "turbo" else bench.dmd_scheduler()
+host = micro_step.batched_view(micro_step.synth_batch(args.pairs, conf["latent_hw"], 2048, 1280, 100, getattr(sched, "sigmas", None),
+                                                      dtype=torch.bfloat16, kind=conf["kind"]))
 d = {k: v.to(dev) for k, v in host.items()}
-step = lambda: micro_step.product_micro_step_batched(pso, lora, unet, d, sched, loss_scale=1 / 6)
+step = lambda: micro_step.product_micro_step_batched(pso, lora, unet, d, sched, loss_scale=1 / 6, kind=conf["kind"])
 for _ in range(3):
     step()
 torch.cuda.synchronize()
@@ -39,5 +47,12 @@ for e in prof.events():
         cnt[name] += 1
 total = sum(tot.values())
 print(f"total kernel time {total / 1e3:.1f} ms over {sum(cnt.values())} launches")
-for name, t in tot.most_common(25):
+for name, t in tot.most_common(args.top):
     print(f"{t / 1e3:8.2f} ms {100 * t / total:5.1f}%  x{cnt[name]:5d}  avg {t / cnt[name]:7.1f} us  {name}")
+
+# ---- which ATen operators the time belongs to (CPU-side op -> device time of the kernels it launched)
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof2:
+    step()
+    torch.cuda.synchronize()
+print(prof2.key_averages(group_by_input_shape=True).table(sort_by="self_device_time_total", row_limit=args.top,
+                                                          max_name_column_width=40, max_shapes_column_width=70))
