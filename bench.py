@@ -10,14 +10,15 @@ per-GPU slice: SDXL-DMD2 online PSO, LoRA rank 64, 1024x1024 (128x128 latents), 
 installed here).  A "step" is one training micro-step over B pairs, written as the reference writes it
 (train_online_pso_sdxl_dmd2.py:773-864 / train_online_pso_sdxl_turbo.py:771-861):
 
-    2 UNet forwards with grad (policy) + 2 adapter-disabled forwards without (frozen reference), gradient checkpointing on
+    2 UNet forwards with grad (policy) + 2 adapter-disabled forwards without (frozen reference); activations stay resident
+        (gradient checkpointing, the reference's memory workaround at :358, is `--grad-checkpointing`: same gradients, +28 % time)
     fused PSO loss+grad kernel  (replaces 4 x turbo_step_with_logprob + the inline loss + its backward)
     backward through the UNet   (LoRA dX / dA / dB on the tcgen05 GEMM path, accumulated into ONE flat fp32 buffer)
     every `accum` = GA x T = 6 steps: all-reduce of the flat LoRA gradient (NCCL, N > 1), then clip-norm + AdamW +
     zero_grad + operand refresh fused over the flat buffers (2 launches)
 
-The 560 projections (forward + backward) and the loss run on this repo's sm_100a kernels; convolutions, norms and the
-attention core are stock torch kernels (outside the PSO hot path).  One rank per GPU, pairs sharded
+The 560 projections (forward + backward), the loss and the feed-forward's gated GELU run on this repo's sm_100a kernels;
+convolutions, norms, the feed-forward GEMMs and the attention core are stock torch kernels (outside the PSO hot path).  One rank per GPU, pairs sharded
 over ranks (weak scaling); the only collective is the LoRA-gradient all-reduce.
 
 Numbers on the JSON line:
@@ -53,8 +54,7 @@ METRIC = "pso_train_pairs_per_sec"
 UNIT = "pairs/s"
 ACCUM = 6  # gradient_accumulation_steps (2) x trained timesteps (3): turbo trainer :232, dmd2 trainer :236
 _COMMON = ("online PSO micro-step (2 policy + 2 frozen-reference UNet forwards, fused PSO loss+grad, backward), random-init "
-           "SDXL-architecture UNet (2.57 B params, 560 LoRA projections), bf16, gradient checkpointing, optimizer step every 6 "
-           "micro-steps")
+           "SDXL-architecture UNet (2.57 B params, 560 LoRA projections), bf16, optimizer step every 6 micro-steps")
 # BASELINE.json's metric is quoted on SDXL 128x128 latents = configs[2] (SDXL-DMD2, rank 64, 1024 px): the default.
 # configs[1] (SDXL-Turbo, rank 8, 64x64 latents, the reference's 512-px recipe) is `--config turbo64`.
 CONFIGS = {
@@ -428,6 +428,9 @@ def run_b200(args):
                        "pairs_per_gpu_per_step": B, "latent_shape": [4, LATENT_HW, LATENT_HW], "lora_rank": RANK,
                        "beta": 50.0, "eps": 0.1, "accum": ACCUM,
                        "parallelism": f"dp{world} (pairs sharded; one all-reduce of the flat LoRA gradient per {ACCUM} steps)",
+                       "activations": ("recomputed in the backward (gradient checkpointing, as the reference)" if args.grad_checkpointing
+                                       else "resident in HBM (no gradient checkpointing: same gradients, no recompute forward)"),
+                       "feed_forward": "fused GEGLU kernels" if args.fused_geglu else "stock torch GEGLU",
                        "l2_policy": "working set larger than L2 (5.1 GB of bf16 weights streamed every forward)",
                        "forwards": "4 separate (as the reference)" if args.separate_forwards else
                                    "win+lose batched: 1 policy + 1 reference forward of batch 2B" +
@@ -568,10 +571,10 @@ def main():
     ap.add_argument("--overlap-reference", action="store_true", default=True,
                     help="issue the frozen-reference forward on a second stream (default)")
     ap.add_argument("--no-overlap-reference", dest="overlap_reference", action="store_false")
-    ap.add_argument("--grad-checkpointing", dest="grad_checkpointing", action="store_true", default=True,
-                    help="recompute the transformer blocks in the backward (the reference's setting, turbo trainer :358)")
-    ap.add_argument("--no-grad-checkpointing", dest="grad_checkpointing", action="store_false",
-                    help="keep the activations of the micro-step resident in HBM instead of recomputing them")
+    ap.add_argument("--grad-checkpointing", dest="grad_checkpointing", action="store_true", default=False,
+                    help="recompute the blocks in the backward (the reference's memory workaround, turbo trainer :358); default: "
+                         "the activations of the 4-pair micro-step (43 GB at 128x128 latents) stay resident in the 180 GB of HBM")
+    ap.add_argument("--no-grad-checkpointing", dest="grad_checkpointing", action="store_false")
     ap.add_argument("--no-fused-geglu", dest="fused_geglu", action="store_false", default=True,
                     help="leave the feed-forward's GEGLU on the stock torch kernels")
     ap.add_argument("--tiny", action="store_true", help="debug: the 32/64-channel fixture instead of the SDXL architecture")

@@ -15,6 +15,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="dmd128", choices=sorted(bench.CONFIGS))
 ap.add_argument("--pairs", type=int, default=4)
 ap.add_argument("--top", type=int, default=40)
+ap.add_argument("--grad-checkpointing", action="store_true")
+ap.add_argument("--no-fused-geglu", action="store_true")
 args = ap.parse_args()
 conf = bench.CONFIGS[args.config]
 dev = torch.device("cuda", 0)
@@ -26,7 +28,12 @@ unet = unet.to(torch.bfloat16).requires_grad_(False)
 wrapped = lora.add_adapter(unet, lora.LoraConfig(r=conf["rank"], lora_alpha=conf["rank"]))
 for m in wrapped:
     torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
-unet.set_attn_processor(lora.PSOAttnProcessor2_0()); unet.train(); unet.enable_gradient_checkpointing()
+unet.set_attn_processor(lora.PSOAttnProcessor2_0()); unet.train()
+if args.grad_checkpointing:
+    unet.enable_gradient_checkpointing()
+if not args.no_fused_geglu:
+    from pairwise_sample_optimization_b200 import feed_forward
+    feed_forward.install_fused_geglu(unet)
 bucket = lora.LoRAGradBucket(lora.lora_parameters(unet))
 sched = bench.turbo_scheduler() if conf["kind"] == "turbo" else bench.dmd_scheduler()
 host = micro_step.batched_view(micro_step.synth_batch(args.pairs, conf["latent_hw"], 2048, 1280, 100, getattr(sched, "sigmas", None),
@@ -56,3 +63,19 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_sh
     torch.cuda.synchronize()
 print(prof2.key_averages(group_by_input_shape=True).table(sort_by="self_device_time_total", row_limit=args.top,
                                                           max_name_column_width=40, max_shapes_column_width=70))
+
+# ---- who launches the non-vectorised `elementwise_kernel`s (strided copies, broadcasts): op, shapes, enclosing ops
+agg = collections.defaultdict(lambda: [0.0, 0])
+for e in prof2.events():
+    for k in getattr(e, "kernels", []) or []:
+        if "elementwise_kernel" in k.name and "vectorized" not in k.name:
+            chain, p = [], e.cpu_parent
+            while p is not None and len(chain) < 3:
+                chain.append(p.name)
+                p = p.cpu_parent
+            key = (e.name, str(e.input_shapes)[:90], " < ".join(chain))
+            agg[key][0] += k.duration
+            agg[key][1] += 1
+print("\nnon-vectorised elementwise kernels by launching operator:")
+for key, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:30]:
+    print(f"{t / 1e3:8.2f} ms x{n:4d}  {key[0]}  {key[1]}  <- {key[2]}")
