@@ -14,7 +14,8 @@ installed here).  A "step" is one training micro-step over B pairs, written as t
         (gradient checkpointing, the reference's memory workaround at :358, is `--grad-checkpointing`: same gradients, +28 % time)
     fused PSO loss+grad kernel  (replaces 4 x turbo_step_with_logprob + the inline loss + its backward)
     backward through the UNet   (LoRA dX / dA / dB on the tcgen05 GEMM path, accumulated into ONE flat fp32 buffer)
-    every `accum` = GA x T = 6 steps: all-reduce of the flat LoRA gradient (NCCL, N > 1), then clip-norm + AdamW +
+    every `accum` = GA x T = 6 steps: exchange of the flat LoRA gradient (N > 1: one multimem kernel of ours over the NVLink
+    multicast mapping, fused with the gradient-norm pass; `--exchange nccl` = ncclAllReduce), then clip + AdamW +
     zero_grad + operand refresh fused over the flat buffers (2 launches)
 
 The 560 projections (forward + backward), the loss and the feed-forward's gated GELU run on this repo's sm_100a kernels;
@@ -260,7 +261,20 @@ def run_b200(args):
         unet.enable_gradient_checkpointing()  # turbo trainer :358
     # parameters, gradients and Adam moments of all 1120 adapter matrices live in four flat fp32 buffers: the optimizer
     # boundary is one all-reduce + two launches (clip + AdamW + zero_grad + 16-bit operand refresh)
-    opt = lora.FusedLoRAOptimizer(unet, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_grad_norm=1.0)
+    # data-parallel exchange: one kernel of ours per rank over the NVLink multicast mapping (in-switch reduction fused with the
+    # norm pass of clip_grad_norm_); `--exchange nccl` (or a group without multicast support) = one NCCL all-reduce
+    opt_kw = dict(lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_grad_norm=1.0)
+    opt, exchange_kind = None, "none (1 GPU)"
+    if world > 1 and args.exchange == "multimem":
+        try:
+            opt = lora.FusedLoRAOptimizer(unet, exchange=lora.SymmetricGradExchange(), **opt_kw)
+            exchange_kind = "multimem.ld_reduce/st kernel fused with the gradient-norm pass (NVLink SHARP), no NCCL call"
+        except Exception as e:  # no NVSwitch multicast on this box: same on every rank
+            print(f"[bench] symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+    if opt is None:
+        opt = lora.FusedLoRAOptimizer(unet, **opt_kw)
+        if world > 1:
+            exchange_kind = "one NCCL all-reduce of the flat gradient"
     bucket = opt.bucket
     sched = turbo_scheduler() if KIND == "turbo" else dmd_scheduler()
     pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
@@ -427,7 +441,8 @@ def run_b200(args):
                        "name": args.config,
                        "pairs_per_gpu_per_step": B, "latent_shape": [4, LATENT_HW, LATENT_HW], "lora_rank": RANK,
                        "beta": 50.0, "eps": 0.1, "accum": ACCUM,
-                       "parallelism": f"dp{world} (pairs sharded; one all-reduce of the flat LoRA gradient per {ACCUM} steps)",
+                       "parallelism": f"dp{world} (pairs sharded; one exchange of the flat LoRA gradient per {ACCUM} steps)",
+                       "gradient_exchange": exchange_kind,
                        "activations": ("recomputed in the backward (gradient checkpointing, as the reference)" if args.grad_checkpointing
                                        else "resident in HBM (no gradient checkpointing: same gradients, no recompute forward)"),
                        "feed_forward": "fused GEGLU kernels" if args.fused_geglu else "stock torch GEGLU",
@@ -575,6 +590,8 @@ def main():
                     help="recompute the blocks in the backward (the reference's memory workaround, turbo trainer :358); default: "
                          "the activations of the 4-pair micro-step (43 GB at 128x128 latents) stay resident in the 180 GB of HBM")
     ap.add_argument("--no-grad-checkpointing", dest="grad_checkpointing", action="store_false")
+    ap.add_argument("--exchange", default="multimem", choices=["multimem", "nccl"],
+                    help="N > 1: the LoRA-gradient exchange (multimem = this repo's NVLink-multicast kernel; nccl = ncclAllReduce)")
     ap.add_argument("--no-fused-geglu", dest="fused_geglu", action="store_false", default=True,
                     help="leave the feed-forward's GEGLU on the stock torch kernels")
     ap.add_argument("--tiny", action="store_true", help="debug: the 32/64-channel fixture instead of the SDXL architecture")

@@ -420,9 +420,36 @@ typedef struct psob200_flat_adamw_args {
   int64_t step;
   float lr, beta1, beta2, eps, weight_decay, max_grad_norm, grad_scale;
   int32_t operand_dtype;
+  /* n_sumsq_parts > 0: the gradient's sum of squares was already produced in n_sumsq_parts pieces (double[], LOCAL
+   * address) by psob200_flat_allreduce_sumsq -- the norm launch is skipped; the pieces are left zeroed. */
+  int32_t n_sumsq_parts;
+  double* sumsq_parts;
 } psob200_flat_adamw_args;
 
 PSOB200_API int psob200_flat_adamw_step(const psob200_flat_adamw_args* args, void* stream);
+
+/*
+ * The data-parallel exchange of the training step (DDP's gradient all-reduce behind accelerator.prepare, T:491, sync
+ * gate T:858) fused with the norm pass of clip_grad_norm_ (T:859), over NVLink SHARP: ONE launch per rank, no NCCL call.
+ * The flat fp32 gradient buffer is symmetric memory (same size on every rank of the group) and grad_multicast is its
+ * MULTICAST address (cuMulticast* / torch.distributed._symmetric_memory): rank r load-reduces its 1/world slice through
+ * the NVSwitch (multimem.ld_reduce.add.v4.f32), multiplies by `scale` (1/world for the mean), stores the result into every
+ * rank's copy (multimem.st) and adds the slice's sum of squares into sumsq_multicast[rank] on every rank
+ * (multimem.red.add.f64; sumsq_multicast = multicast address of a zero-initialised double[world]).
+ * Contract: the caller places a cross-rank barrier on the stream BEFORE this launch (every rank's backward has finished
+ * accumulating) and AFTER it (every slice has landed) -- then all ranks hold bitwise-identical gradients, and
+ * psob200_flat_adamw_step(n_sumsq_parts = world, sumsq_parts = the LOCAL address of that array) finishes the boundary.
+ * n must be a multiple of 4; grad_multicast 16-byte aligned.
+ */
+typedef struct psob200_flat_allreduce_args {
+  float* grad_multicast;
+  double* sumsq_multicast;
+  int64_t n;
+  int32_t rank, world;
+  float scale;
+} psob200_flat_allreduce_args;
+
+PSOB200_API int psob200_flat_allreduce_sumsq(const psob200_flat_allreduce_args* args, void* stream);
 
 /*
  * Gated GELU of the transformer feed-forward that sits between the LoRA-wrapped attention blocks (diffusers==0.27.0
@@ -450,7 +477,8 @@ PSOB200_API int psob200_geglu_backward(const psob200_geglu_args* args, void* str
 /* sizeof() of the argument structs as compiled into the library, for FFI bindings to
  * verify their mirror of this header: which = 0 schedule, 1 online_pso_args,
  * 2 dreambooth_args, 3 step_args, 4 step_bwd_args, 5 gemm_args,
- * 6 lora_linear_args, 7 flat_adamw_args, 8 geglu_args.  Returns 0 for unknown ids. */
+ * 6 lora_linear_args, 7 flat_adamw_args, 8 geglu_args,
+ * 9 flat_allreduce_args.  Returns 0 for unknown ids. */
 PSOB200_API size_t psob200_struct_size(int which);
 
 #ifdef __cplusplus

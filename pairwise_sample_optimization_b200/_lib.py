@@ -93,7 +93,12 @@ class FlatAdamwArgs(C.Structure):
     _fields_ = [("param", _fp), ("grad", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("operand", _vp), ("norm_out", _fp),
                 ("workspace", _vp), ("n", C.c_int64), ("step", C.c_int64), ("lr", C.c_float), ("beta1", C.c_float),
                 ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float), ("max_grad_norm", C.c_float),
-                ("grad_scale", C.c_float), ("operand_dtype", C.c_int32)]
+                ("grad_scale", C.c_float), ("operand_dtype", C.c_int32), ("n_sumsq_parts", C.c_int32), ("sumsq_parts", _vp)]
+
+
+class FlatAllreduceArgs(C.Structure):
+    _fields_ = [("grad_multicast", _vp), ("sumsq_multicast", _vp), ("n", C.c_int64), ("rank", C.c_int32),
+                ("world", C.c_int32), ("scale", C.c_float)]
 
 
 class GegluArgs(C.Structure):
@@ -103,7 +108,7 @@ class GegluArgs(C.Structure):
 
 
 _STRUCTS = {0: Schedule, 1: OnlinePsoArgs, 2: DreamboothArgs, 3: StepArgs, 4: StepBwdArgs, 5: GemmArgs,
-            6: LoraLinearArgs, 7: FlatAdamwArgs, 8: GegluArgs}
+            6: LoraLinearArgs, 7: FlatAdamwArgs, 8: GegluArgs, 9: FlatAllreduceArgs}
 
 # name -> (restype, argtypes): every symbol include/psob200.h declares
 SIGNATURES = {
@@ -124,6 +129,7 @@ SIGNATURES = {
     "psob200_lora_linear_forward": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
     "psob200_lora_linear_backward": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
     "psob200_flat_adamw_step": (C.c_int, [C.POINTER(FlatAdamwArgs), _vp]),
+    "psob200_flat_allreduce_sumsq": (C.c_int, [C.POINTER(FlatAllreduceArgs), _vp]),
     "psob200_geglu_forward": (C.c_int, [C.POINTER(GegluArgs), _vp]),
     "psob200_geglu_backward": (C.c_int, [C.POINTER(GegluArgs), _vp]),
     "psob200_scale": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, C.c_int32, C.c_int32, _vp]),

@@ -53,6 +53,7 @@ extern "C" size_t psob200_struct_size(int which) {
     case 6: return sizeof(psob200_lora_linear_args);
     case 7: return sizeof(psob200_flat_adamw_args);
     case 8: return sizeof(psob200_geglu_args);
+    case 9: return sizeof(psob200_flat_allreduce_args);
     default: return 0;
   }
 }

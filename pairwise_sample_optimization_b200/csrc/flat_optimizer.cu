@@ -37,6 +37,49 @@ __global__ void __launch_bounds__(kOptThreads) flat_sumsq_kernel(const float* __
   }
 }
 
+// ---- data-parallel exchange fused into the optimizer boundary (NVLink SHARP through the multicast mapping) -------------
+// The flat gradient buffer is symmetric memory, mapped at `mc` as a MULTICAST address: a load-reduce from it returns the
+// sum of the N ranks' copies, computed inside the NVSwitch; a store to it lands in every rank's copy.  Rank r owns the
+// slice [lo, hi): it pulls the reduced values (reduce-scatter), scales them to the mean, pushes them back to all ranks
+// (all-gather) and, on the way, accumulates the sum of squares of its slice -- the global-norm pass of clip_grad_norm_
+// costs no extra read.  Each rank's partial norm is added into slot `rank` of a small symmetric array on every rank.
+// The caller brackets this launch with two cross-rank barriers (all backward passes done before; all slices written
+// after); every rank ends up with bitwise-identical gradients and norm.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+flat_allreduce_sumsq_kernel(float* mc, double* mc_sumsq_slot, long long lo, long long hi, float scale) {
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hi; i += stride) {
+    float4 v = multimem_ld_reduce_add(mc + i);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    multimem_st(mc + i, v);
+    acc = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, acc))));
+  }
+  acc = warp_sum(acc);
+  __shared__ float s[kOptThreads / 32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kOptThreads / 32 ? s[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+      const double d = (double)v;
+      asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(mc_sumsq_slot), "d"(d) : "memory");
+    }
+  }
+}
+
 struct AdamParams {
   float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, max_norm, grad_scale;
 };
@@ -44,9 +87,11 @@ struct AdamParams {
 template <typename TO>
 __global__ void __launch_bounds__(kOptThreads)
 flat_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, TO* __restrict__ op,
-                  long long n, AdamParams a, double* ws, float* norm_out) {
+                  long long n, AdamParams a, double* ws, float* norm_out, double* parts, int n_parts) {
   // global-norm clip coefficient (accelerate / torch clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)))
-  const float norm = (float)sqrt(ws[0]) * a.grad_scale;
+  double sumsq = ws[0];
+  for (int r = 0; r < n_parts; ++r) sumsq += parts[r];  // per-rank slices of the fused exchange (same order on every rank)
+  const float norm = (float)sqrt(sumsq) * a.grad_scale;
   const float coef = a.max_norm > 0.f ? fminf(1.f, a.max_norm / (norm + 1e-6f)) * a.grad_scale : a.grad_scale;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -74,6 +119,7 @@ flat_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restric
     if (norm_out != nullptr) *norm_out = norm;
     ws[0] = 0.0;
     *reinterpret_cast<unsigned*>(ws + 1) = 0u;
+    for (int r = 0; r < n_parts; ++r) parts[r] = 0.0;  // local copy only: peers zero theirs; next use is behind a barrier
   }
 }
 
@@ -99,7 +145,8 @@ extern "C" int psob200_flat_adamw_step(const psob200_flat_adamw_args* args, void
   long long blocks = (o.n + kOptThreads * 4 - 1) / (kOptThreads * 4);
   if (blocks > n_sm * 8) blocks = n_sm * 8;
   double* ws = reinterpret_cast<double*>(o.workspace);
-  if (o.max_grad_norm > 0.f || o.norm_out != nullptr) {
+  if (o.n_sumsq_parts < 0 || (o.n_sumsq_parts > 0 && !o.sumsq_parts)) return PSOB200_ERR_INVALID_ARG;
+  if (o.n_sumsq_parts == 0 && (o.max_grad_norm > 0.f || o.norm_out != nullptr)) {
     flat_sumsq_kernel<<<(unsigned)blocks, kOptThreads, 0, st>>>(o.grad, o.n, ws);
     const int rc = consume_launch_error("launch flat_sumsq_kernel", cudaSuccess);
     if (rc != PSOB200_OK) return rc;
@@ -114,9 +161,32 @@ extern "C" int psob200_flat_adamw_step(const psob200_flat_adamw_args* args, void
   if (blocks > n_sm * 8) blocks = n_sm * 8;
   if (o.operand == nullptr || o.operand_dtype == PSOB200_BF16)
     flat_adamw_kernel<__nv_bfloat16><<<(unsigned)blocks, kOptThreads, 0, st>>>(
-        o.param, o.grad, o.exp_avg, o.exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(o.operand), o.n, a, ws, o.norm_out);
+        o.param, o.grad, o.exp_avg, o.exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(o.operand), o.n, a, ws, o.norm_out, o.sumsq_parts,
+        o.n_sumsq_parts);
   else
     flat_adamw_kernel<__half><<<(unsigned)blocks, kOptThreads, 0, st>>>(
-        o.param, o.grad, o.exp_avg, o.exp_avg_sq, reinterpret_cast<__half*>(o.operand), o.n, a, ws, o.norm_out);
+        o.param, o.grad, o.exp_avg, o.exp_avg_sq, reinterpret_cast<__half*>(o.operand), o.n, a, ws, o.norm_out, o.sumsq_parts, o.n_sumsq_parts);
   return consume_launch_error("launch flat_adamw_kernel", cudaSuccess);
+}
+
+extern "C" int psob200_flat_allreduce_sumsq(const psob200_flat_allreduce_args* args, void* stream) {
+  if (args == nullptr) return PSOB200_ERR_INVALID_ARG;
+  const psob200_flat_allreduce_args& o = *args;
+  if (!o.grad_multicast || !o.sumsq_multicast || o.n <= 0 || o.world <= 0 || o.rank < 0 || o.rank >= o.world)
+    return PSOB200_ERR_INVALID_ARG;
+  if (!aligned16(o.grad_multicast) || (reinterpret_cast<uintptr_t>(o.sumsq_multicast) & 7u)) return PSOB200_ERR_ALIGNMENT;
+  if (o.n % 4) return PSOB200_ERR_SHAPE;  // 128-bit multimem accesses
+  // slices of whole 16-byte vectors; the last ranks may own less (or nothing)
+  const long long vecs = o.n / 4, per = (vecs + o.world - 1) / o.world;
+  long long lo = per * o.rank * 4, hi = per * (o.rank + 1) * 4;
+  if (lo > o.n) lo = o.n;
+  if (hi > o.n) hi = o.n;
+  int n_sm = psob200_device_sm_count();
+  if (n_sm <= 0) n_sm = 148;
+  long long blocks = (hi - lo + kOptThreads * 4 - 1) / (kOptThreads * 4);
+  if (blocks > n_sm * 4) blocks = n_sm * 4;
+  if (blocks < 1) blocks = 1;  // an empty slice still launches: uniform launch sequence on every rank
+  flat_allreduce_sumsq_kernel<<<(unsigned)blocks, kOptThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      o.grad_multicast, o.sumsq_multicast + o.rank, lo, hi, o.scale);
+  return consume_launch_error("launch flat_allreduce_sumsq_kernel", cudaSuccess);
 }

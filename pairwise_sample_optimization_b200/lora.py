@@ -336,13 +336,15 @@ class LoRAGradBucket:
     collective over the flat buffer, averaged over ranks (what DDP does for the reference, bucket by bucket).
     ``clip_grad_norm_`` is accelerate's ``clip_grad_norm_`` (turbo :859) on the flat buffer: one norm, one scale."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], align: int = 8):
+    def __init__(self, params: Iterable[torch.nn.Parameter], align: int = 8, allocator=None):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable LoRA parameters")
         dev = self.params[0].device
         sizes = [(p.numel() + align - 1) // align * align for p in self.params]  # every view (also a 16-bit twin) 16-byte aligned
-        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        # allocator(n, device) -> zeroed fp32 tensor of n elements: lets the buffer live in symmetric memory (SymmetricGradExchange)
+        self.flat = (torch.zeros(sum(sizes), dtype=torch.float32, device=dev) if allocator is None
+                     else allocator(sum(sizes), dev))
         self.views, self.offsets = [], []
         off = 0
         for p, n in zip(self.params, sizes):
@@ -384,6 +386,58 @@ class LoRAGradBucket:
                 p.grad = v.to(p.dtype)
 
 
+class SymmetricGradExchange:
+    """The flat LoRA gradient in NVLink symmetric memory, exchanged by ONE kernel of ours per rank instead of an NCCL call.
+
+    ``torch.distributed._symmetric_memory`` is used only as plumbing (allocation, the multicast mapping, the cross-rank
+    barrier on the stream).  ``exchange()`` = barrier, ``psob200_flat_allreduce_sumsq`` (in-switch reduction of this rank's
+    slice with ``multimem.ld_reduce``, mean, broadcast to every rank with ``multimem.st``, the slice's sum of squares for
+    ``clip_grad_norm_`` on the way), barrier.  Replaces DDP's bucketed all-reduce (accelerator.prepare, turbo :491, sync gate
+    :858) and the norm pass of ``clip_grad_norm_`` (:859).  Raises if the group has no multicast support (no NVSwitch)."""
+
+    PARTS_PAD = 64  # floats reserved behind the gradient for the per-rank double[world] sums of squares
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        if not (dist.is_available() and dist.is_initialized()):
+            raise _lib.Psob200Error("SymmetricGradExchange needs an initialised process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if 2 * self.world > self.PARTS_PAD:
+            raise _lib.Psob200Error(f"at most {self.PARTS_PAD // 2} ranks")
+        self._symm = symm
+        self.handle = self.buffer = None
+        self.n = 0
+
+    def allocate(self, n: int, device) -> torch.Tensor:
+        """``LoRAGradBucket`` allocator: n fp32 gradient elements (+ the norm slots) in symmetric memory; collective."""
+        self.n = (n + 3) // 4 * 4
+        self.buffer = self._symm.empty(self.n + self.PARTS_PAD, dtype=torch.float32, device=device)
+        self.buffer.zero_()
+        self.handle = self._symm.rendezvous(self.buffer, self.group)
+        if not getattr(self.handle, "multicast_ptr", 0):
+            raise _lib.Psob200Error("this process group has no NVLink multicast mapping (multimem needs NVSwitch / NVLS)")
+        torch.cuda.synchronize(device)
+        self.handle.barrier(channel=0)
+        return self.buffer[:n]
+
+    @property
+    def sumsq_parts_ptr(self) -> int:
+        return self.buffer.data_ptr() + 4 * self.n
+
+    def exchange(self) -> None:
+        dev = self.buffer.device
+        a = _lib.FlatAllreduceArgs()
+        a.grad_multicast = self.handle.multicast_ptr
+        a.sumsq_multicast = self.handle.multicast_ptr + 4 * self.n
+        a.n, a.rank, a.world, a.scale = self.n, self.rank, self.world, 1.0 / self.world
+        self.handle.barrier(channel=0)  # every rank's backward has finished accumulating into its copy
+        rc = _lib.lib().psob200_flat_allreduce_sumsq(C.byref(a), _lib.current_stream(dev))
+        _lib.check(rc, "psob200_flat_allreduce_sumsq")
+        self.handle.barrier(channel=1)  # every slice (and every norm slot) has landed everywhere
+
+
 class FusedLoRAOptimizer:
     """The optimizer boundary of the training step on the flat LoRA buffers: ``clip_grad_norm_`` + AdamW +
     ``zero_grad`` + refresh of the 16-bit GEMM operands in two kernel launches (psob200_flat_adamw_step) instead of the
@@ -393,13 +447,15 @@ class FusedLoRAOptimizer:
     Update rule = ``torch.optim.AdamW`` (decoupled weight decay, bias correction)."""
 
     def __init__(self, model: nn.Module, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-4, max_grad_norm: float = 1.0):
+                 weight_decay: float = 1e-4, max_grad_norm: float = 1.0, exchange: Optional[SymmetricGradExchange] = None):
+        self.exchange = exchange  # None: all_reduce() is one NCCL call; else the fused NVLink-multicast kernel
         self.layers = lora_layers(model)
         params = lora_parameters(model)
         if any(p.dtype != torch.float32 for p in params):
             raise _lib.Psob200Error("FusedLoRAOptimizer trains fp32 adapter parameters (the shipped mixed-precision recipes)")
         _lib.require_cuda(*params)
-        self.bucket = LoRAGradBucket(params, align=8)
+        self.bucket = LoRAGradBucket(params, align=8, allocator=exchange.allocate if exchange is not None else None)
+        self._parts_ready = False
         flat = self.bucket.flat
         self.flat_param = torch.zeros_like(flat)
         self.exp_avg = torch.zeros_like(flat)
@@ -429,6 +485,12 @@ class FusedLoRAOptimizer:
                 self._unbacked.append((lay, which, op_dtype))
 
     def all_reduce(self, group=None):
+        """The data-parallel exchange: mean of the flat gradient over the ranks.  With a ``SymmetricGradExchange`` it is
+        one launch of ours (which also leaves the norm of the averaged gradient for ``step()``), else one NCCL call."""
+        if self.exchange is not None:
+            self.exchange.exchange()
+            self._parts_ready = True
+            return None
         return self.bucket.all_reduce(group)
 
     def step(self) -> torch.Tensor:
@@ -442,6 +504,9 @@ class FusedLoRAOptimizer:
         a.n, a.step = self.flat_param.numel(), self.step_count
         a.lr, a.beta1, a.beta2, a.eps = self.lr, self.betas[0], self.betas[1], self.eps
         a.weight_decay, a.max_grad_norm, a.grad_scale = self.weight_decay, self.max_grad_norm, 1.0
+        if self._parts_ready:  # the fused exchange already produced the sum of squares, one piece per rank
+            a.n_sumsq_parts, a.sumsq_parts = self.exchange.world, self.exchange.sumsq_parts_ptr
+            self._parts_ready = False
         rc = _lib.lib().psob200_flat_adamw_step(C.byref(a), _lib.current_stream(self.flat_param.device))
         _lib.check(rc, "psob200_flat_adamw_step")
         for lay, which, dt in self._unbacked:  # padded-pitch copies: re-made in place by the layer itself
