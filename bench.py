@@ -256,6 +256,7 @@ def run_b200(args):
     if args.fused_geglu:  # the feed-forward's gated GELU on one fused kernel each way (outside SURVEY section 8's rows)
         from pairwise_sample_optimization_b200 import feed_forward
         feed_forward.install_fused_geglu(unet)
+    lora.set_wgrad_stream(args.wgrad_stream)
     unet.train()
     if args.grad_checkpointing:
         unet.enable_gradient_checkpointing()  # turbo trainer :358
@@ -445,6 +446,7 @@ def run_b200(args):
                        "gradient_exchange": exchange_kind,
                        "activations": ("recomputed in the backward (gradient checkpointing, as the reference)" if args.grad_checkpointing
                                        else "resident in HBM (no gradient checkpointing: same gradients, no recompute forward)"),
+                       "weight_gradients": "dA / dB launches on a side stream" if args.wgrad_stream else "in stream order",
                        "feed_forward": "fused GEGLU kernels" if args.fused_geglu else "stock torch GEGLU",
                        "l2_policy": "working set larger than L2 (5.1 GB of bf16 weights streamed every forward)",
                        "forwards": "4 separate (as the reference)" if args.separate_forwards else
@@ -590,6 +592,9 @@ def main():
                     help="recompute the blocks in the backward (the reference's memory workaround, turbo trainer :358); default: "
                          "the activations of the 4-pair micro-step (43 GB at 128x128 latents) stay resident in the 180 GB of HBM")
     ap.add_argument("--no-grad-checkpointing", dest="grad_checkpointing", action="store_false")
+    ap.add_argument("--wgrad-stream", dest="wgrad_stream", action="store_true", default=True,
+                    help="issue the dA / dB launches of every projection on a side stream (joined at the end of the backward)")
+    ap.add_argument("--no-wgrad-stream", dest="wgrad_stream", action="store_false")
     ap.add_argument("--exchange", default="multimem", choices=["multimem", "nccl"],
                     help="N > 1: the LoRA-gradient exchange (multimem = this repo's NVLink-multicast kernel; nccl = ncclAllReduce)")
     ap.add_argument("--no-fused-geglu", dest="fused_geglu", action="store_false", default=True,

@@ -371,7 +371,12 @@ PSOB200_API int psob200_lora_gemm(const psob200_gemm_args* args, void* stream);
  * them (nn.Linear weight [out,in]); no transposed copies are needed.  Leading dimensions are in elements,
  * multiples of 8 (so lora_b, t, u are stored with ld >= r rounded up to 8).  t/tt (forward) and u/ut (backward)
  * are caller-provided scratch; tt must be kept for the backward.  r <= 256.
+ * backward_phases (backward only): 0 = everything; PSOB200_BWD_INPUT_GRAD = u (+ ut when ut != NULL) and dx only;
+ * PSOB200_BWD_WEIGHT_GRAD = dA and dB only, from the ut / tt a previous INPUT_GRAD call left -- the two halves can then
+ * run on different streams (nothing downstream of the layer waits for dA / dB).
  */
+#define PSOB200_BWD_INPUT_GRAD 1
+#define PSOB200_BWD_WEIGHT_GRAD 2
 typedef struct psob200_lora_linear_args {
   const void* x;
   const void* w;
@@ -393,6 +398,7 @@ typedef struct psob200_lora_linear_args {
   int32_t dtype;
   int32_t bias_dtype;
   int32_t adapters_enabled;
+  int32_t backward_phases;
 } psob200_lora_linear_args;
 
 PSOB200_API int psob200_lora_linear_forward(const psob200_lora_linear_args* args, void* stream);

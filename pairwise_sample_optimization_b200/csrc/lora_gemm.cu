@@ -513,8 +513,10 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
   if (splits == 0) {  // heuristics: split the reduction only for accumulating launches that cannot fill the GPU
     splits = 1;
     if (g.accumulate) {
+      // one wave: the largest split count whose tiles all fit on the SMs at once (rounding UP gave e.g. 150 tiles on 148
+      // SMs: two CTAs ran two tiles each and the launch took twice as long; measured 12.2 -> 10.1 us for dA at M = 8192)
       const long long tiles = (long long)p.m_tiles * p.n_tiles;
-      splits = (int)((sms + tiles - 1) / tiles);
+      splits = (int)(sms / tiles);
       if (splits > nk) splits = nk;
       if (splits < 1) splits = 1;
     }
@@ -620,17 +622,19 @@ extern "C" int psob200_lora_linear_backward(const psob200_lora_linear_args* args
   if (lora && a.d_lora_a && (!a.ut || !a.x)) return PSOB200_ERR_INVALID_ARG;
   if (lora && a.d_lora_b && !a.tt) return PSOB200_ERR_INVALID_ARG;
   int rc;
-  const bool need_u = lora && (a.dx != nullptr || a.d_lora_a != nullptr);
+  const bool do_input = a.backward_phases == 0 || (a.backward_phases & PSOB200_BWD_INPUT_GRAD);
+  const bool do_weight = a.backward_phases == 0 || (a.backward_phases & PSOB200_BWD_WEIGHT_GRAD);
+  const bool need_u = lora && do_input && (a.dx != nullptr || a.ut != nullptr || a.d_lora_a != nullptr);
   if (need_u) {  // u = scaling * dy B   (B [N,r] consumed reduction-major: no transposed copy)
     psob200_gemm_args g = gemm_defaults(a.dtype);
     g.a1 = a.dy; g.lda1 = a.lddy; g.b1 = a.lora_b; g.ldb1 = a.ldb; g.b_reduction_major = 1;
     g.M = a.M; g.N = a.r; g.K1 = a.N;
     g.alpha = a.scaling;
-    g.d = a.u; g.ldd = a.ldu; g.dt = a.d_lora_a ? a.ut : nullptr; g.lddt = a.ldut;
+    g.d = a.u; g.ldd = a.ldu; g.dt = a.ut; g.lddt = a.ldut;
     g.pdl = a.dx != nullptr ? 1 : 0;
     if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
   }
-  if (a.dx != nullptr) {  // dx = dy W + u A   (W [N,K], A [r,K] reduction-major)
+  if (a.dx != nullptr && do_input) {  // dx = dy W + u A   (W [N,K], A [r,K] reduction-major)
     psob200_gemm_args g = gemm_defaults(a.dtype);
     g.a1 = a.dy; g.lda1 = a.lddy; g.b1 = a.w; g.ldb1 = a.ldw; g.b_reduction_major = 1;
     g.M = a.M; g.N = a.K; g.K1 = a.N;
@@ -638,7 +642,7 @@ extern "C" int psob200_lora_linear_backward(const psob200_lora_linear_args* args
     g.d = a.dx; g.ldd = a.lddx;
     if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
   }
-  if (lora && a.d_lora_a != nullptr) {  // dA[r,K] += u^T x : D[K,r] = sum_m x[m,:]^T ut[:,m], written transposed
+  if (lora && do_weight && a.d_lora_a != nullptr) {  // dA[r,K] += u^T x : D[K,r] = sum_m x[m,:]^T ut[:,m], written transposed
     psob200_gemm_args g = gemm_defaults(a.dtype);
     g.a1 = a.x; g.lda1 = a.ldx; g.a_reduction_major = 1; g.b1 = a.ut; g.ldb1 = a.ldut;
     g.M = a.K; g.N = a.r; g.K1 = a.M;
@@ -646,7 +650,7 @@ extern "C" int psob200_lora_linear_backward(const psob200_lora_linear_args* args
     g.pdl = a.d_lora_b != nullptr ? 1 : 0;  // dB below is independent of this launch: let the two overlap
     if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
   }
-  if (lora && a.d_lora_b != nullptr) {  // dB[N,r] += dy^T t
+  if (lora && do_weight && a.d_lora_b != nullptr) {  // dB[N,r] += dy^T t
     psob200_gemm_args g = gemm_defaults(a.dtype);
     g.a1 = a.dy; g.lda1 = a.lddy; g.a_reduction_major = 1; g.b1 = a.tt; g.ldb1 = a.ldtt;
     g.M = a.N; g.N = a.r; g.K1 = a.M;

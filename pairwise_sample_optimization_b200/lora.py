@@ -53,6 +53,39 @@ def set_timing_sink(sink) -> None:
     _TIMING = sink
 
 
+# Weight-gradient side stream.  Nothing downstream of a layer's backward waits for dA / dB (they are read at the optimizer
+# boundary), so their two launches can leave the critical path: with ``set_wgrad_stream(True)`` they are issued on a second
+# CUDA stream (ordered after the layer's u / dx launches) and joined back once, at the end of the backward pass, by an
+# autograd-engine callback.  Works eagerly and under CUDA-graph capture (the fork / join become graph edges).
+_WGRAD_SIDE = {"enabled": False, "streams": {}, "pending": {}, "armed": set()}
+
+
+def set_wgrad_stream(enabled: bool) -> None:
+    _WGRAD_SIDE["enabled"] = bool(enabled)
+
+
+def _wgrad_side_stream(dev: torch.device) -> torch.cuda.Stream:
+    st = _WGRAD_SIDE["streams"].get(dev)
+    if st is None:
+        st = _WGRAD_SIDE["streams"][dev] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def _arm_wgrad_join(dev: torch.device) -> None:
+    """Queue (once per backward pass) the callback that makes the caller's stream wait for the side stream and releases
+    the operands the side launches were still reading."""
+    if dev in _WGRAD_SIDE["armed"]:
+        return
+    _WGRAD_SIDE["armed"].add(dev)
+
+    def join():
+        _WGRAD_SIDE["armed"].discard(dev)
+        torch.cuda.current_stream(dev).wait_stream(_wgrad_side_stream(dev))
+        _WGRAD_SIDE["pending"].pop(dev, None)
+
+    torch.autograd.Variable._execution_engine.queue_callback(join)
+
+
 def _ceil8(n: int) -> int:
     return (n + 7) // 8 * 8
 
@@ -243,8 +276,20 @@ class _LoraLinearFn(torch.autograd.Function):
             if _TIMING is not None:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev0.record()
+            side = _WGRAD_SIDE["enabled"] and bool(ctx.enabled and a.d_lora_a) and _TIMING is None
+            if side:
+                a.backward_phases = 1  # PSOB200_BWD_INPUT_GRAD: u (+ ut), dx
             rc = _lib.lib().psob200_lora_linear_backward(C.byref(a), _lib.current_stream(dev))
             _lib.check(rc, "psob200_lora_linear_backward")
+            if side:
+                st = _wgrad_side_stream(dev)
+                st.wait_stream(torch.cuda.current_stream(dev))
+                a.backward_phases = 2  # PSOB200_BWD_WEIGHT_GRAD: dA, dB
+                rc = _lib.lib().psob200_lora_linear_backward(C.byref(a), st.cuda_stream)
+                _lib.check(rc, "psob200_lora_linear_backward")
+                _WGRAD_SIDE["pending"].setdefault(dev, []).append((x2, tt, dy2, keep))  # alive until the join
+                keep = []
+                _arm_wgrad_join(dev)
             if _TIMING is not None:
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev1.record()

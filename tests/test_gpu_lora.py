@@ -235,3 +235,54 @@ def test_fused_flat_optimizer_matches_torch_adamw_with_clipping(L, r):
     x = _mk((2, 64, 640), 9).cuda().requires_grad_(True)
     attn.to_q(x).float().square().mean().backward()
     assert float(opt.bucket.flat.abs().max()) > 0.0
+
+
+def test_weight_gradients_on_the_side_stream_are_identical(L):
+    """set_wgrad_stream(True): dA / dB leave the critical path (second stream, joined by an autograd-engine callback at the
+    end of the backward); results are those of the single-stream order, eagerly and replayed from a CUDA graph."""
+    dt = torch.bfloat16
+    stack = [_layer(L, 320, 320, 8, True, dt, 40 + i) for i in range(3)]
+    x = _mk((4, 200, 320), 7, 1.0, dt).cuda()
+    dy = _mk((4, 200, 320), 8, 1.0, dt).cuda()
+
+    def run():
+        for lay in stack:
+            for p in (lay.lora_A["default"].weight, lay.lora_B["default"].weight):
+                if p.grad is not None:
+                    p.grad.zero_()
+        xg = x.clone().requires_grad_(True)
+        h = xg
+        for lay in stack:
+            h = lay(h) * 0.5
+        h.backward(dy)
+        torch.cuda.synchronize()
+        return [xg.grad.clone()] + [p.grad.clone() for lay in stack for p in (lay.lora_A["default"].weight, lay.lora_B["default"].weight)]
+
+    want = run()
+    L.set_wgrad_stream(True)
+    try:
+        got = run()
+        for g, w in zip(got, want):
+            assert _rel(g, w.double().cpu()) <= 2e-6  # only the order of the fp32 atomics differs
+        # captured: fork / join become graph edges
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            run()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        xs = x.clone().requires_grad_(True)
+        with torch.cuda.graph(graph, stream=side):
+            h = xs
+            for lay in stack:
+                h = lay(h) * 0.5
+            h.backward(dy)
+        for lay in stack:
+            lay.lora_A["default"].weight.grad.zero_()
+            lay.lora_B["default"].weight.grad.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        got = [p.grad for lay in stack for p in (lay.lora_A["default"].weight, lay.lora_B["default"].weight)]
+        for g, w in zip(got, want[1:]):
+            assert _rel(g, w.double().cpu()) <= 2e-6
+    finally:
+        L.set_wgrad_stream(False)
