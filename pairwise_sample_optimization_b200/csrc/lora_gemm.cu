@@ -403,6 +403,10 @@ static int gemm_sm_count() {
   return n;
 }
 
+// per-tile fixed cost of the pair kernel in units of one accumulator column: measured per-wave times at K = 1344 are
+// 6.7 us (bn 128) and 9.7 us (bn 256) = 3.7 us + 23.4 ns per column (tools/diag_lora_parts.py --bn ...)
+constexpr int kTileFixedCols = 160;
+
 static int choose_bn(long long N, bool b_mn) {
   if (b_mn && N < 256) return (int)(((N + 63) / 64) * 64);  // reduction-major B: whole 64-column boxes
   if (N >= 256) {
@@ -411,6 +415,26 @@ static int choose_bn(long long N, bool b_mn) {
     return w128 < w256 ? 128 : 256;
   }
   return (int)(((N + 15) / 16) * 16);
+}
+
+// Tile width of the CTA-pair kernel.  The kernel is persistent over `pairs` CTA pairs with a static tile order, so its time
+// is (number of waves) x (time of one tile) and a tile costs ~ its width plus a fixed part (pipeline fill, drain of the last
+// accumulator): pick the width that minimises waves x (bn + fixed) instead of always 256.  E.g. M = 8192, N = 1280 on 74
+// pairs: 256 -> 160 tiles = 3 waves, 224 -> 192 tiles = 3 narrower waves (measured 29.0 -> 26.4 us).  Widths that are not
+// multiples of 32 are excluded (bn = 144 measured 30 % slower than the model predicts).
+static int choose_bn2(long long M, long long N, bool b_mn, int pairs) {
+  const int unit = b_mn ? 128 : 32;
+  if (N < 256) return (int)(((N + (b_mn ? 127 : 31)) / (b_mn ? 128 : 32)) * (b_mn ? 128 : 32));
+  const long long m_tiles = (M + 255) / 256;
+  int best = 256;
+  long long best_cost = -1;
+  for (int bn = 256; bn >= 128; bn -= unit) {
+    const long long tiles = m_tiles * ((N + bn - 1) / bn);
+    const long long waves = (tiles + pairs - 1) / pairs;
+    const long long cost = waves * (bn + kTileFixedCols);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
 }
 
 }  // namespace psob200
@@ -439,11 +463,12 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
 
   // ---- CTA-pair kernel (cta_group::2) for the large K-major problems: at least one full wave of 256-row pair tiles
   {
-    const bool eligible = !g.a_reduction_major && !g.accumulate && g.dt == nullptr && g.split_k <= 1 && g.tune_bn == 0;
-    const int bn2 = g.N >= 256 ? 256 : (int)(((g.N + (g.b_reduction_major ? 127 : 31)) / (g.b_reduction_major ? 128 : 32)) *
-                                             (g.b_reduction_major ? 128 : 32));
-    const long long pair_tiles = ((g.M + 255) / 256) * ((g.N + bn2 - 1) / bn2);
     const int sms = gemm_sm_count();
+    const int bn_unit = g.b_reduction_major ? 128 : 16;  // each CTA loads half the tile: whole 64-column boxes / 8-row atoms
+    const bool eligible = !g.a_reduction_major && !g.accumulate && g.dt == nullptr && g.split_k <= 1 &&
+                          (g.tune_bn == 0 || (g.tune_bn % bn_unit == 0 && g.tune_bn >= 32));
+    const int bn2 = g.tune_bn > 0 ? g.tune_bn : choose_bn2(g.M, g.N, g.b_reduction_major != 0, sms / 2);
+    const long long pair_tiles = ((g.M + 255) / 256) * ((g.N + bn2 - 1) / bn2);
     const bool want = (g.diag & 0x10000) || (pair_tiles >= sms / 2 && g.N >= 128 && !(g.diag & 0x20000));
     if (eligible && want && bn2 <= kBNMax) {
       GemmKernelParams p = {};

@@ -60,6 +60,14 @@ def main():
             "dx = dy W + u A": gemm(dev, a1=dy, lda1=N, b1=w, ldb1=K, a2=u, lda2=r, b2=A, ldb2=K, b_reduction_major=1, M=M, N=K,
                                     K1=N, K2=r, d=dx, ldd=K),
         }
+        for bn in (int(v) for v in args.bn.split(",")):
+            if bn == 0:
+                continue
+            parts[f"y  = x W^T + t B^T  bn={bn}"] = gemm(dev, a1=x, lda1=K, b1=w, ldb1=K, a2=t, lda2=r, b2=Bm, ldb2=r, M=M, N=N, K1=K,
+                                                        K2=r, d=y, ldd=N, tune_bn=bn)
+            if bn % 128 == 0:
+                parts[f"dx = dy W + u A  bn={bn}"] = gemm(dev, a1=dy, lda1=N, b1=w, ldb1=K, a2=u, lda2=r, b2=A, ldb2=K,
+                                                         b_reduction_major=1, M=M, N=K, K1=N, K2=r, d=dx, ldd=K, tune_bn=bn)
         for sp in (int(v) for v in args.split.split(",")):
             parts[f"dA += u^T x  split={sp}"] = gemm(dev, a1=x, lda1=K, a_reduction_major=1, b1=ut, ldb1=M8, M=K, N=r, K1=M, dt=dA,
                                                      lddt=K, d_dtype=f32, accumulate=1, split_k=sp)
