@@ -26,8 +26,11 @@ Numbers on the JSON line:
   value / ms_per_step : exactly K steps, inputs resident in HBM, CUDA events, max over ranks.
   e2e                 : the same K steps with the step's inputs copied from pinned host memory and the loss read back,
                         every step, inside the timed region.
-  roofline            : the dominant kernel of OURS in this step (lora_gemm_kernel, tensor-bound), timed with one CUDA-event
-                        pair around every projection call in a separate instrumented pass; peak = sustained bf16 TF/s.
+  roofline            : the dominant kernel of OURS in this step -- the tensor-bound main passes of the LoRA-wrapped
+                        projections (lora_gemm2_kernel, CTA pairs) -- one CUDA-event pair around EVERY launch in a separate
+                        instrumented pass; achieved = 2 M N (K + r) flops per launch / launch time; peak = sustained bf16 TF/s.
+  lora_skinny_launches: the rank-r side launches (t, u, dA, dB: HBM / latency bound) of the same pass, as GB/s of their
+                        algorithmic bytes against the measured HBM copy bandwidth.
   loss_kernel_roofline / lora_gemm_large : the two kernel-level figures of BASELINE config 5 (fused loss+grad kernel at 256
                         pairs x 128x128 latents against the HBM roofline; the fused base+LoRA GEMM at M = 18944).
   cpu_baseline        : the oracle port of the reference's PyTorch path (fp32, same UNet architecture) on this box's host
@@ -289,8 +292,8 @@ def run_b200(args):
 
     ref_stream = torch.cuda.Stream() if (args.overlap_reference and not args.separate_forwards) else None
 
-    def micro(batch):
-        kw = {"ref_stream": ref_stream} if ref_stream is not None else {}
+    def micro(batch, overlap=True):
+        kw = {"ref_stream": ref_stream} if (ref_stream is not None and overlap) else {}
         return fwd_bwd(pso, lora, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM, kind=KIND, **kw)
 
     def optimizer_boundary(i):
@@ -392,35 +395,65 @@ def run_b200(args):
     e2e = {"value": round(world * B * K / (e2e_ms * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
            "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms / K, 3)}
 
-    # ---- roofline of the dominant kernel of ours (lora_gemm_kernel): instrumented pass, one event pair per projection call
+    # ---- roofline of the dominant kernel of ours: instrumented pass, ONE launch between each pair of events
+    peak_hbm_gb = round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2)  # before the second (instrumented) graph
     bucket.zero_()
     sink = []
+    n_inst = 1
     lora.set_timing_sink(sink)
-    n_inst = 2
-    for i in range(n_inst):
-        micro(d)  # eager (the event pairs are host-side objects), same kernels as the captured step
+    if args.no_graph:
+        micro(d, overlap=False)
+    else:
+        # captured like the timed step, with the event records as graph nodes: an eager pass is host-bound (the GPU idles
+        # between a record and the launch behind it) and would charge host latency to the kernels
+        side.wait_stream(torch.cuda.current_stream())
+        inst_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(inst_graph, stream=side):  # the stream the step was warmed up and captured on
+            micro(d, overlap=False)  # one stream: a launch's interval must not include waiting for the other stream's CTAs
+        for _ in range(2):
+            inst_graph.replay()  # the events keep the timestamps of the last replay
     lora.set_timing_sink(None)
     torch.cuda.synchronize()
-    gemm_ms = sum(e[0].elapsed_time(e[1]) for e in sink)
-    gemm_flops = sum(e[2] for e in sink)
-    gemm_launches = sum(e[3] for e in sink)
+    is_main = lambda role: role.startswith("y =") or role.startswith("dx =")
+    agg = {True: [0.0, 0.0, 0.0, 0], False: [0.0, 0.0, 0.0, 0]}  # ms, flops, bytes, launches
     by_shape = {}
-    for e in sink:
-        t = by_shape.setdefault(e[4], [0.0, 0, 0.0])
-        t[0] += e[0].elapsed_time(e[1]); t[1] += 1; t[2] += e[2]
-    ach = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"kernel": "lora_gemm_kernel (560 LoRA-wrapped projections, forward + backward)", "bound": "tensor",
-                "achieved": round(ach, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+    for ev0, ev1, fl, by, role, shape in sink:
+        ms = ev0.elapsed_time(ev1)
+        a_ = agg[is_main(role)]
+        a_[0] += ms; a_[1] += fl; a_[2] += by; a_[3] += 1
+        t = by_shape.setdefault((role,) + tuple(shape), [0.0, 0, 0.0, 0.0])
+        t[0] += ms; t[1] += 1; t[2] += fl; t[3] += by
+    m_ms, m_fl, m_by, m_n = agg[True]
+    s_ms, s_fl, s_by, s_n = agg[False]
+    ach = m_fl / (m_ms * 1e-3) / 1e12 if m_ms > 0 else 0.0
+    rows = [{"launch": k[0], "M": k[1], "K": k[2], "N": k[3], "r": k[4], "launches_per_step": v[1] // n_inst,
+             "avg_us": round(v[0] * 1e3 / v[1], 2), "ms_per_step": round(v[0] / n_inst, 2),
+             **({"tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1)} if is_main(k[0]) else
+                {"gbs": round(v[3] / (v[0] * 1e-3) / 1e9, 1)})}
+            for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])]
+    roofline = {"kernel": "lora_gemm2_kernel / lora_gemm_kernel main passes: y = x W^T + b + t B^T, dx = dy W + u A (tcgen05, "
+                          "frozen weight + adapter in one pass) over the 560 LoRA-wrapped projections",
+                "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(ach / peaks["tf_sustained"], 4), "traffic": None,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "launches_per_step": gemm_launches // n_inst, "avg_launch_us": round(gemm_ms * 1e3 / max(gemm_launches, 1), 2),
-                "share_of_step": round(gemm_ms / n_inst / ms_per_step, 4),
-                "flops_per_step": gemm_flops / n_inst,
-                "by_call": [{"call": k[0], "M": k[1], "K": k[2], "N": k[3], "calls_per_step": v[1] // n_inst,
-                             "ms_per_step": round(v[0] / n_inst, 2), "tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1)}
-                            for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])],
-                "how": "CUDA-event pair around every psob200_lora_linear_forward/backward call in 2 extra instrumented "
-                       "steps (each pair brackets 1-4 back-to-back launches of this kernel and nothing else)"}
+                "launches_per_step": m_n // n_inst, "avg_launch_us": round(m_ms * 1e3 / max(m_n, 1), 2),
+                "share_of_step": round(m_ms / n_inst / ms_per_step, 4), "flops_per_step": m_fl / n_inst,
+                "algorithmic_flops": "2 M N (K + r) per launch (r = 0 for the frozen-reference pass)",
+                "by_launch": [r_ for r_ in rows if is_main(r_["launch"])],
+                "how": "one CUDA-event pair around EVERY launch (psob200 forward_phases / backward_phases issue the launches of "
+                       "a projection one at a time; event records captured as graph nodes) in one extra replayed step on ONE "
+                       "stream (in the timed step the frozen-reference forward shares the SMs from a second stream, which would "
+                       "charge its CTAs' residency to these intervals); includes the graph-node gaps around each launch and "
+                       "lacks the programmatic-dependent-launch overlap, so slightly pessimistic"}
+    s_ach = s_by / (s_ms * 1e-3) / 1e9 if s_ms > 0 else 0.0
+    skinny = {"kernel": "lora_gemm_kernel skinny passes: t = s x A^T, u = s dy B, dA += u^T x, dB += dy^T t (rank-r side of "
+                        "every projection; arithmetic intensity <= 84 flop/B, SURVEY.md section 8d)",
+              "bound": "hbm", "achieved": round(s_ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
+              "frac": round(s_ach / peaks["hbm"], 4), "launches_per_step": s_n // n_inst,
+              "avg_launch_us": round(s_ms * 1e3 / max(s_n, 1), 2), "share_of_step": round(s_ms / n_inst / ms_per_step, 4),
+              "algorithmic_bytes": "operands read once + result written once per launch",
+              "note": "latency-bound: one 128-row tile per CTA walks the whole reduction (13 us per launch at any M)",
+              "by_launch": [r_ for r_ in rows if not is_main(r_["launch"])]}
     bucket.zero_()
 
     extra = {}
@@ -455,7 +488,8 @@ def run_b200(args):
                        "timing": ("eager launches" if args.no_graph else "micro-step replayed from one CUDA graph; optimizer "
                                   "boundary eager") + ", CUDA events around K steps, max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
-            "loss": round(loss_value, 6), "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
+            "lora_skinny_launches": skinny,
+            "loss": round(loss_value, 6), "peak_hbm_gb": peak_hbm_gb,
         }
         line.update(extra)
         if cpu is not None:

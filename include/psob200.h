@@ -371,12 +371,19 @@ PSOB200_API int psob200_lora_gemm(const psob200_gemm_args* args, void* stream);
  * them (nn.Linear weight [out,in]); no transposed copies are needed.  Leading dimensions are in elements,
  * multiples of 8 (so lora_b, t, u are stored with ld >= r rounded up to 8).  t/tt (forward) and u/ut (backward)
  * are caller-provided scratch; tt must be kept for the backward.  r <= 256.
- * backward_phases (backward only): 0 = everything; PSOB200_BWD_INPUT_GRAD = u (+ ut when ut != NULL) and dx only;
- * PSOB200_BWD_WEIGHT_GRAD = dA and dB only, from the ut / tt a previous INPUT_GRAD call left -- the two halves can then
- * run on different streams (nothing downstream of the layer waits for dA / dB).
+ * forward_phases / backward_phases: 0 = every launch of the sequence; else a mask of the launches to issue, so that a
+ * caller can put them on different streams or bracket each with its own events (outputs of the omitted launches must be
+ * in place from an earlier call): PSOB200_FWD_DOWN (t), PSOB200_FWD_MAIN (y); PSOB200_BWD_U (u, ut), PSOB200_BWD_DX,
+ * PSOB200_BWD_DA, PSOB200_BWD_DB.  Nothing downstream of a layer waits for dA / dB, hence PSOB200_BWD_WEIGHT_GRAD.
  */
-#define PSOB200_BWD_INPUT_GRAD 1
-#define PSOB200_BWD_WEIGHT_GRAD 2
+#define PSOB200_FWD_DOWN 1
+#define PSOB200_FWD_MAIN 2
+#define PSOB200_BWD_U 1
+#define PSOB200_BWD_DX 2
+#define PSOB200_BWD_DA 4
+#define PSOB200_BWD_DB 8
+#define PSOB200_BWD_INPUT_GRAD (PSOB200_BWD_U | PSOB200_BWD_DX)
+#define PSOB200_BWD_WEIGHT_GRAD (PSOB200_BWD_DA | PSOB200_BWD_DB)
 typedef struct psob200_lora_linear_args {
   const void* x;
   const void* w;
@@ -399,6 +406,7 @@ typedef struct psob200_lora_linear_args {
   int32_t bias_dtype;
   int32_t adapters_enabled;
   int32_t backward_phases;
+  int32_t forward_phases;
 } psob200_lora_linear_args;
 
 PSOB200_API int psob200_lora_linear_forward(const psob200_lora_linear_args* args, void* stream);

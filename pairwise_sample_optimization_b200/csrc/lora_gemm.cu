@@ -620,7 +620,8 @@ extern "C" int psob200_lora_linear_forward(const psob200_lora_linear_args* args,
   const bool lora = a.adapters_enabled != 0;
   if (lora && (!a.lora_a || !a.lora_b || !a.t || a.r <= 0 || a.r > kBNMax)) return PSOB200_ERR_INVALID_ARG;
   int rc;
-  if (lora) {  // t = scaling * x A^T  (+ its transpose, the K-major operand of the dB reduction)
+  const int fph = a.forward_phases == 0 ? (PSOB200_FWD_DOWN | PSOB200_FWD_MAIN) : a.forward_phases;
+  if (lora && (fph & PSOB200_FWD_DOWN)) {  // t = scaling * x A^T  (+ its transpose, the K-major operand of the dB reduction)
     psob200_gemm_args g = gemm_defaults(a.dtype);
     g.a1 = a.x; g.lda1 = a.ldx; g.b1 = a.lora_a; g.ldb1 = a.lda;
     g.M = a.M; g.N = a.r; g.K1 = a.K;
@@ -629,6 +630,7 @@ extern "C" int psob200_lora_linear_forward(const psob200_lora_linear_args* args,
     g.pdl = 1;  // the main pass below reads t only in its last k-blocks: let it start on the SMs this launch leaves idle
     if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
   }
+  if (!(fph & PSOB200_FWD_MAIN)) return PSOB200_OK;
   psob200_gemm_args g = gemm_defaults(a.dtype);
   g.a1 = a.x; g.lda1 = a.ldx; g.b1 = a.w; g.ldb1 = a.ldw;
   g.M = a.M; g.N = a.N; g.K1 = a.K;
@@ -647,9 +649,8 @@ extern "C" int psob200_lora_linear_backward(const psob200_lora_linear_args* args
   if (lora && a.d_lora_a && (!a.ut || !a.x)) return PSOB200_ERR_INVALID_ARG;
   if (lora && a.d_lora_b && !a.tt) return PSOB200_ERR_INVALID_ARG;
   int rc;
-  const bool do_input = a.backward_phases == 0 || (a.backward_phases & PSOB200_BWD_INPUT_GRAD);
-  const bool do_weight = a.backward_phases == 0 || (a.backward_phases & PSOB200_BWD_WEIGHT_GRAD);
-  const bool need_u = lora && do_input && (a.dx != nullptr || a.ut != nullptr || a.d_lora_a != nullptr);
+  const int ph = a.backward_phases == 0 ? (PSOB200_BWD_INPUT_GRAD | PSOB200_BWD_WEIGHT_GRAD) : a.backward_phases;
+  const bool need_u = lora && (ph & PSOB200_BWD_U) && (a.dx != nullptr || a.ut != nullptr || a.d_lora_a != nullptr);
   if (need_u) {  // u = scaling * dy B   (B [N,r] consumed reduction-major: no transposed copy)
     psob200_gemm_args g = gemm_defaults(a.dtype);
     g.a1 = a.dy; g.lda1 = a.lddy; g.b1 = a.lora_b; g.ldb1 = a.ldb; g.b_reduction_major = 1;
@@ -659,7 +660,7 @@ extern "C" int psob200_lora_linear_backward(const psob200_lora_linear_args* args
     g.pdl = a.dx != nullptr ? 1 : 0;
     if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
   }
-  if (a.dx != nullptr && do_input) {  // dx = dy W + u A   (W [N,K], A [r,K] reduction-major)
+  if (a.dx != nullptr && (ph & PSOB200_BWD_DX)) {  // dx = dy W + u A   (W [N,K], A [r,K] reduction-major)
     psob200_gemm_args g = gemm_defaults(a.dtype);
     g.a1 = a.dy; g.lda1 = a.lddy; g.b1 = a.w; g.ldb1 = a.ldw; g.b_reduction_major = 1;
     g.M = a.M; g.N = a.K; g.K1 = a.N;
@@ -667,7 +668,7 @@ extern "C" int psob200_lora_linear_backward(const psob200_lora_linear_args* args
     g.d = a.dx; g.ldd = a.lddx;
     if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
   }
-  if (lora && do_weight && a.d_lora_a != nullptr) {  // dA[r,K] += u^T x : D[K,r] = sum_m x[m,:]^T ut[:,m], written transposed
+  if (lora && (ph & PSOB200_BWD_DA) && a.d_lora_a != nullptr) {  // dA[r,K] += u^T x : D[K,r] = sum_m x[m,:]^T ut[:,m], written transposed
     psob200_gemm_args g = gemm_defaults(a.dtype);
     g.a1 = a.x; g.lda1 = a.ldx; g.a_reduction_major = 1; g.b1 = a.ut; g.ldb1 = a.ldut;
     g.M = a.K; g.N = a.r; g.K1 = a.M;
@@ -675,7 +676,7 @@ extern "C" int psob200_lora_linear_backward(const psob200_lora_linear_args* args
     g.pdl = a.d_lora_b != nullptr ? 1 : 0;  // dB below is independent of this launch: let the two overlap
     if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
   }
-  if (lora && do_weight && a.d_lora_b != nullptr) {  // dB[N,r] += dy^T t
+  if (lora && (ph & PSOB200_BWD_DB) && a.d_lora_b != nullptr) {  // dB[N,r] += dy^T t
     psob200_gemm_args g = gemm_defaults(a.dtype);
     g.a1 = a.dy; g.lda1 = a.lddy; g.a_reduction_major = 1; g.b1 = a.tt; g.ldb1 = a.ldtt;
     g.M = a.N; g.N = a.r; g.K1 = a.M;

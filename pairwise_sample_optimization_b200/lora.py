@@ -43,7 +43,8 @@ class LoraConfig:
     lora_dropout: float = 0.0
 
 
-# When a list is installed here, every projection call appends (start_event, end_event, flops, launches): the
+# When a list is installed here, every projection call issues its launches one at a time (psob200 forward_phases /
+# backward_phases) and appends (start_event, end_event, flops, algorithmic bytes, role, (M, K, N, r)) per LAUNCH: the
 # instrumented pass bench.py uses to attribute device time to the GEMM kernels.  None in normal operation.
 _TIMING = None
 
@@ -84,6 +85,16 @@ def _arm_wgrad_join(dev: torch.device) -> None:
         _WGRAD_SIDE["pending"].pop(dev, None)
 
     torch.autograd.Variable._execution_engine.queue_callback(join)
+
+
+def _timed_launch(fn, what: str, role: str, flops: float, nbytes: float, shape) -> None:
+    """Instrumented pass: ONE kernel launch between two events; appends (ev0, ev1, flops, algorithmic bytes, role, shape)."""
+    # external: inside a CUDA-graph capture the records become event-record nodes (timestamps of the last replay)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True)
+    ev0.record()
+    _lib.check(fn(), what)
+    ev1.record()
+    _TIMING.append((ev0, ev1, flops, nbytes, role, shape))
 
 
 def _ceil8(n: int) -> int:
@@ -216,16 +227,18 @@ class _LoraLinearFn(torch.autograd.Function):
             if want_wgrad:
                 tt = torch.empty(r, _ceil8(M), dtype=dtype, device=dev)
                 a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
-        if _TIMING is not None:
-            ev0 = torch.cuda.Event(enable_timing=True)
-            ev0.record()
-        rc = _lib.lib().psob200_lora_linear_forward(C.byref(a), _lib.current_stream(dev))
-        _lib.check(rc, "psob200_lora_linear_forward")
-        if _TIMING is not None:
-            ev1 = torch.cuda.Event(enable_timing=True)
-            ev1.record()
-            fl = 2.0 * M * K * N + (2.0 * M * r * (K + N) if enabled else 0.0)
-            _TIMING.append((ev0, ev1, fl, 2 if enabled else 1, ("fwd" if enabled else "fwd-ref", M, K, N)))
+        if _TIMING is None:
+            rc = _lib.lib().psob200_lora_linear_forward(C.byref(a), _lib.current_stream(dev))
+            _lib.check(rc, "psob200_lora_linear_forward")
+        else:  # instrumented pass: the same launches one by one, each between its own pair of events
+            eb = 2  # bytes per 16-bit element
+            roles = [(1, "t = s x A^T", 2.0 * M * r * K, eb * (M * K + r * K + M * r * (2 if tt is not None else 1)))] if enabled else []
+            roles.append((2, "y = x W^T + t B^T" if enabled else "y = x W^T (frozen reference)",
+                          2.0 * M * N * (K + (r if enabled else 0)), eb * (M * K + N * K + M * N + ((M + N) * r if enabled else 0))))
+            for mask, role, fl, by in roles:
+                a.forward_phases = mask
+                _timed_launch(lambda: _lib.lib().psob200_lora_linear_forward(C.byref(a), _lib.current_stream(dev)),
+                              "psob200_lora_linear_forward", role, fl, by, (M, K, N, r))
         ctx.layer, ctx.enabled, ctx.x_shape, ctx.x_dtype, ctx.want_wgrad = layer, enabled, x.shape, x.dtype, want_wgrad
         ctx.save_for_backward(x2, tt)
         return y.view(*x.shape[:-1], N)
@@ -273,36 +286,37 @@ class _LoraLinearFn(torch.autograd.Function):
                 a.d_lora_b, a.ld_db = gb.data_ptr(), gb.stride(0)
                 keep += [ut, ga, gb]
         if dx is not None or (ctx.enabled and a.d_lora_a):
-            if _TIMING is not None:
-                ev0 = torch.cuda.Event(enable_timing=True)
-                ev0.record()
-            side = _WGRAD_SIDE["enabled"] and bool(ctx.enabled and a.d_lora_a) and _TIMING is None
-            if side:
-                a.backward_phases = 1  # PSOB200_BWD_INPUT_GRAD: u (+ ut), dx
-            rc = _lib.lib().psob200_lora_linear_backward(C.byref(a), _lib.current_stream(dev))
-            _lib.check(rc, "psob200_lora_linear_backward")
+            wg = bool(ctx.enabled and a.d_lora_a)
+            side = _WGRAD_SIDE["enabled"] and wg and _TIMING is None
+            if _TIMING is not None:  # instrumented pass: one launch at a time, each between its own pair of events
+                eb = 2
+                roles = []
+                if ctx.enabled and (dx is not None or wg):
+                    roles.append((1, "u = s dy B", 2.0 * M * N * r, eb * (M * N + N * r + M * r * (2 if wg else 1))))
+                if dx is not None:
+                    roles.append((2, "dx = dy W + u A", 2.0 * M * K * (N + (r if ctx.enabled else 0)),
+                                  eb * (M * N + N * K + M * K + ((M + K) * r if ctx.enabled else 0))))
+                if wg:
+                    roles.append((4, "dA += u^T x", 2.0 * M * r * K, eb * (M * K + M * r) + 4 * r * K))
+                    roles.append((8, "dB += dy^T t", 2.0 * M * N * r, eb * (M * N + M * r) + 4 * N * r))
+                for mask, role, fl, by in roles:
+                    a.backward_phases = mask
+                    _timed_launch(lambda: _lib.lib().psob200_lora_linear_backward(C.byref(a), _lib.current_stream(dev)),
+                                  "psob200_lora_linear_backward", role, fl, by, (M, K, N, r))
+            else:
+                if side:
+                    a.backward_phases = 3  # PSOB200_BWD_INPUT_GRAD: u (+ ut), dx
+                rc = _lib.lib().psob200_lora_linear_backward(C.byref(a), _lib.current_stream(dev))
+                _lib.check(rc, "psob200_lora_linear_backward")
             if side:
                 st = _wgrad_side_stream(dev)
                 st.wait_stream(torch.cuda.current_stream(dev))
-                a.backward_phases = 2  # PSOB200_BWD_WEIGHT_GRAD: dA, dB
+                a.backward_phases = 12  # PSOB200_BWD_WEIGHT_GRAD: dA, dB
                 rc = _lib.lib().psob200_lora_linear_backward(C.byref(a), st.cuda_stream)
                 _lib.check(rc, "psob200_lora_linear_backward")
                 _WGRAD_SIDE["pending"].setdefault(dev, []).append((x2, tt, dy2, keep))  # alive until the join
                 keep = []
                 _arm_wgrad_join(dev)
-            if _TIMING is not None:
-                ev1 = torch.cuda.Event(enable_timing=True)
-                ev1.record()
-                wg = bool(ctx.enabled and a.d_lora_a)
-                fl = (2.0 * M * K * N if dx is not None else 0.0)
-                n_l = 1 if dx is not None else 0
-                if ctx.enabled and (dx is not None or wg):
-                    fl += 2.0 * M * N * r + (2.0 * M * r * K if dx is not None else 0.0)
-                    n_l += 1
-                if wg:
-                    fl += 2.0 * M * r * K + 2.0 * M * N * r
-                    n_l += 2
-                _TIMING.append((ev0, ev1, fl, n_l, ("bwd" + ("" if dx is not None else "-nodx"), M, K, N)))
         del keep
         if dx is not None:
             dx = dx.view(ctx.x_shape)
