@@ -81,13 +81,19 @@ __device__ __forceinline__ void load_bias32(const void* bias, long long n0, long
   }
 }
 
+// Epilogue mode (compile time): bits 0-1 = outputs (1: row-major d only, 2: transposed dt only, 3: whichever pointers are
+// set, checked at run time), bit 2 = a bias may be present.  The hot launches of the training step get exact modes so that
+// their instruction footprint stays small (see lora_gemm_kernel); mode 7 is the general case.
+constexpr int kEpiD = 1, kEpiDt = 2, kEpiAnyOut = 3, kEpiBias = 4, kEpiGeneral = 7;
+constexpr int kEpiBiasSameType = 8 | kEpiBias;  // the bias has the output's element type (nn.Linear in one dtype)
+
 // One 32-column chunk of one accumulator row: v[j] belongs to (row, n0 + j).
-template <typename TD, bool kAtomic>
+template <typename TD, bool kAtomic, int kMode>
 __device__ __forceinline__ void store_chunk(const GemmKernelParams& p, const float (&v)[32], long long row, long long n0,
                                             long long n_end) {
   if (row >= p.M) return;
   const long long nleft = n_end - n0;  // columns of this chunk that belong to this tile and exist
-  if (p.d != nullptr) {
+  if ((kMode & kEpiD) && ((kMode & 3) != kEpiAnyOut || p.d != nullptr)) {
     TD* dst = reinterpret_cast<TD*>(p.d) + row * p.ldd + n0;
     if constexpr (kAtomic) {
 #pragma unroll
@@ -111,7 +117,7 @@ __device__ __forceinline__ void store_chunk(const GemmKernelParams& p, const flo
         if (j < nleft) dst[j] = cvt_out<TD>(v[j]);
     }
   }
-  if (p.dt != nullptr) {  // lanes hold consecutive rows: every column is a coalesced store
+  if ((kMode & kEpiDt) && ((kMode & 3) != kEpiAnyOut || p.dt != nullptr)) {  // lanes hold consecutive rows: coalesced columns
     TD* dst = reinterpret_cast<TD*>(p.dt) + n0 * p.lddt + row;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -125,7 +131,7 @@ __device__ __forceinline__ void store_chunk(const GemmKernelParams& p, const flo
 
 // Drain one accumulator tile: TMEM -> registers (the load of chunk c+1 is in flight while chunk c is converted and
 // stored) -> alpha, bias -> global.
-template <typename TD, bool kAtomic>
+template <typename TD, bool kAtomic, int kMode>
 __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_t taddr, long long row, long long n_tile0,
                                               bool add_bias) {
   const int chunks = (p.bn + 31) / 32;
@@ -142,9 +148,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_
         ptx::tmem_ld_wait();
         if (cc + 1 < chunks) ptx::tmem_ld_32x32(taddr + (uint32_t)(cc + 1) * 32, raw[h ^ 1]);
         float v[32];
-        if (add_bias) {
+        if ((kMode & kEpiBias) && add_bias) {
           float b[32];
-          if (p.bias_dtype == PSOB200_F32) load_bias32<float>(p.bias, n0, p.N, b);
+          if constexpr ((kMode & 8) != 0) load_bias32<TD>(p.bias, n0, p.N, b);
+          else if (p.bias_dtype == PSOB200_F32) load_bias32<float>(p.bias, n0, p.N, b);
           else if (p.bias_dtype == PSOB200_BF16) load_bias32<__nv_bfloat16>(p.bias, n0, p.N, b);
           else load_bias32<__half>(p.bias, n0, p.N, b);
 #pragma unroll
@@ -153,13 +160,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(raw[h][j]);
         }
-        if (!(p.diag & 2)) store_chunk<TD, kAtomic>(p, v, row, n0, n_end);
+        if (!(p.diag & 2)) store_chunk<TD, kAtomic, kMode>(p, v, row, n0, n_end);
       }
     }
   }
   ptx::tmem_ld_wait();
 }
 
+// One instantiation per output type / accumulation mode: the four epilogues together made this kernel 259 KB of SASS, and
+// a launch that finds its code evicted from the instruction caches (any launch inside the training step: LayerNorm, SDPA,
+// cuBLAS kernels run in between) paid ~10 us for it (tools/diag_cold.py: 15.7 us back to back, 26.6 us with three other
+// kernels in between, only 18.4 us with the OPERANDS evicted instead).
+template <typename TD, bool kAtomic, int kMode>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
                  const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
@@ -326,10 +338,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kBNMax;
-      if (p.atomic) epilogue_tile<float, true>(p, taddr, row, n_tile0, add_bias);
-      else if (p.d_dtype == PSOB200_F32) epilogue_tile<float, false>(p, taddr, row, n_tile0, add_bias);
-      else if (p.d_dtype == PSOB200_BF16) epilogue_tile<__nv_bfloat16, false>(p, taddr, row, n_tile0, add_bias);
-      else epilogue_tile<__half, false>(p, taddr, row, n_tile0, add_bias);
+      epilogue_tile<TD, kAtomic, kMode>(p, taddr, row, n_tile0, add_bias);
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
@@ -499,11 +508,21 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
         ma2 = ma1;
         mb2 = mb1;
       }
-      static std::atomic<bool> configured2{false};
-      if (!configured2.load(std::memory_order_acquire)) {
-        const cudaError_t e = cudaFuncSetAttribute(lora_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm2SmemBytes);
+      typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmKernelParams);
+      // 0: general (fp32 output, or a bias of another type); then per 16-bit type: bias of the same type, no bias
+      const bool bias_other = p.bias != nullptr && p.bias_dtype != p.d_dtype;
+      const int variant = (p.d_dtype == PSOB200_F32 || bias_other) ? (p.d_dtype == PSOB200_F32 ? 0 : (p.d_dtype == PSOB200_BF16 ? 1 : 2))
+                                                                   : ((p.d_dtype == PSOB200_BF16 ? 3 : 5) + (p.bias != nullptr ? 0 : 1));
+      static const KernelFn kernels2[7] = {
+          lora_gemm2_kernel<float, kEpiD | kEpiBias>, lora_gemm2_kernel<__nv_bfloat16, kEpiD | kEpiBias>,
+          lora_gemm2_kernel<__half, kEpiD | kEpiBias>,
+          lora_gemm2_kernel<__nv_bfloat16, kEpiD | kEpiBiasSameType>, lora_gemm2_kernel<__nv_bfloat16, kEpiD>,
+          lora_gemm2_kernel<__half, kEpiD | kEpiBiasSameType>, lora_gemm2_kernel<__half, kEpiD>};
+      static std::atomic<bool> configured2[7];
+      if (!configured2[variant].load(std::memory_order_acquire)) {
+        const cudaError_t e = cudaFuncSetAttribute(kernels2[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm2SmemBytes);
         if (e != cudaSuccess) return consume_launch_error("configure lora_gemm2_kernel", e);
-        configured2.store(true, std::memory_order_release);
+        configured2[variant].store(true, std::memory_order_release);
       }
       const long long max_pairs = sms / 2;
       const unsigned grid = 2u * (unsigned)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
@@ -519,7 +538,7 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
       }
-      const cudaError_t e = cudaLaunchKernelEx(&cfg, lora_gemm2_kernel, ma1, mb1, ma2, mb2, p);
+      const cudaError_t e = cudaLaunchKernelEx(&cfg, kernels2[variant], ma1, mb1, ma2, mb2, p);
       return consume_launch_error("launch lora_gemm2_kernel", e);
     }
   }
@@ -580,11 +599,29 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
     mb2 = mb1;
   }
 
-  static std::atomic<bool> configured{false};
-  if (!configured.load(std::memory_order_acquire)) {
-    const cudaError_t e = cudaFuncSetAttribute(lora_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmKernelParams);
+  // exact epilogue modes for the launches of the training step, the general kernel for everything else
+  const int outs = (p.d != nullptr ? kEpiD : 0) | (p.dt != nullptr ? kEpiDt : 0);
+  const bool has_bias = p.bias != nullptr;
+  int variant;
+  if (p.atomic) variant = has_bias ? 0 : (outs == kEpiD ? 1 : (outs == kEpiDt ? 2 : 0));
+  else if (p.d_dtype == PSOB200_F32) variant = 3;
+  else {
+    const int base = p.d_dtype == PSOB200_BF16 ? 4 : 8;
+    variant = base + (has_bias ? (outs == kEpiD && p.bias_dtype == p.d_dtype ? 1 : 0) : (outs == kEpiD ? 2 : 3));
+  }
+  static const KernelFn kernels[12] = {
+      lora_gemm_kernel<float, true, kEpiGeneral>, lora_gemm_kernel<float, true, kEpiD>, lora_gemm_kernel<float, true, kEpiDt>,
+      lora_gemm_kernel<float, false, kEpiGeneral>,
+      lora_gemm_kernel<__nv_bfloat16, false, kEpiGeneral>, lora_gemm_kernel<__nv_bfloat16, false, kEpiD | kEpiBiasSameType>,
+      lora_gemm_kernel<__nv_bfloat16, false, kEpiD>, lora_gemm_kernel<__nv_bfloat16, false, kEpiAnyOut>,
+      lora_gemm_kernel<__half, false, kEpiGeneral>, lora_gemm_kernel<__half, false, kEpiD | kEpiBiasSameType>,
+      lora_gemm_kernel<__half, false, kEpiD>, lora_gemm_kernel<__half, false, kEpiAnyOut>};
+  static std::atomic<bool> configured[12];
+  if (!configured[variant].load(std::memory_order_acquire)) {
+    const cudaError_t e = cudaFuncSetAttribute(kernels[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
     if (e != cudaSuccess) return consume_launch_error("configure lora_gemm_kernel", e);
-    configured.store(true, std::memory_order_release);
+    configured[variant].store(true, std::memory_order_release);
   }
   const long long total = (long long)p.m_tiles * p.n_tiles * p.splits;
   const unsigned grid = (unsigned)(total < sms ? total : sms);
@@ -600,7 +637,7 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, lora_gemm_kernel, ma1, mb1, ma2, mb2, p);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[variant], ma1, mb1, ma2, mb2, p);
   return consume_launch_error("launch lora_gemm_kernel", e);
 }
 

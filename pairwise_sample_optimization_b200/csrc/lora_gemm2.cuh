@@ -64,6 +64,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 }  // namespace ptx
 
+template <typename TD, int kMode>  // one instantiation per output type / bias presence (code size: see lora_gemm_kernel)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 lora_gemm2_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
                   const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
@@ -213,9 +214,7 @@ lora_gemm2_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kBNMax;
-      if (p.d_dtype == PSOB200_F32) epilogue_tile<float, false>(p, taddr, row, n_tile0, add_bias);
-      else if (p.d_dtype == PSOB200_BF16) epilogue_tile<__nv_bfloat16, false>(p, taddr, row, n_tile0, add_bias);
-      else epilogue_tile<__half, false>(p, taddr, row, n_tile0, add_bias);
+      epilogue_tile<TD, false, kMode>(p, taddr, row, n_tile0, add_bias);
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_leader(&tmem_empty_bar[acc]);
