@@ -49,6 +49,23 @@ def test_argument_validation_without_gpu(built_lib):
     args = _lib.OnlinePsoArgs()
     args.B, args.N = 0, 16
     assert lib.psob200_online_pso_loss_grad(C.byref(sched), C.byref(args), None) == -1
+    # entry points added later in the round: rejected before any CUDA call
+    assert lib.psob200_geglu_forward(None, None) == -1 and lib.psob200_geglu_backward(None, None) == -1
+    g = _lib.GegluArgs()
+    g.proj, g.out, g.M, g.I, g.ld_proj, g.ld_out, g.dtype = 16, 32, 4, 10, 20, 10, _lib._DTYPES[torch.bfloat16]
+    assert lib.psob200_geglu_forward(C.byref(g), None) == -5  # half width 10 is not a multiple of 16 bytes
+    g.I, g.ld_proj, g.ld_out, g.proj = 16, 32, 16, 8
+    assert lib.psob200_geglu_forward(C.byref(g), None) == -3  # misaligned pointer
+    assert lib.psob200_flat_allreduce_sumsq(None, None) == -1
+    x = _lib.FlatAllreduceArgs()
+    x.grad_multicast, x.sumsq_multicast, x.n, x.rank, x.world, x.scale = 16, 64, 1024, 2, 2, 0.5
+    assert lib.psob200_flat_allreduce_sumsq(C.byref(x), None) == -1  # rank outside the group
+    x.rank, x.n = 1, 1022
+    assert lib.psob200_flat_allreduce_sumsq(C.byref(x), None) == -5  # 128-bit multimem accesses need n % 4 == 0
+    o = _lib.FlatAdamwArgs()
+    o.param = o.grad = o.exp_avg = o.exp_avg_sq = o.workspace = 16
+    o.n, o.step, o.n_sumsq_parts = 8, 1, 2  # pieces announced but no pointer to them
+    assert lib.psob200_flat_adamw_step(C.byref(o), None) == -1
 
 
 def test_product_path_has_no_cpu_fallback(built_lib):
