@@ -58,7 +58,7 @@ def set_timing_sink(sink) -> None:
 # boundary), so their two launches can leave the critical path: with ``set_wgrad_stream(True)`` they are issued on a second
 # CUDA stream (ordered after the layer's u / dx launches) and joined back once, at the end of the backward pass, by an
 # autograd-engine callback.  Works eagerly and under CUDA-graph capture (the fork / join become graph edges).
-_WGRAD_SIDE = {"enabled": False, "streams": {}, "pending": {}, "armed": set()}
+_WGRAD_SIDE = {"enabled": False, "streams": {}, "pending": {}, "armed": {}}  # armed: device -> id of the backward pass
 
 
 def set_wgrad_stream(enabled: bool) -> None:
@@ -75,12 +75,14 @@ def _wgrad_side_stream(dev: torch.device) -> torch.cuda.Stream:
 def _arm_wgrad_join(dev: torch.device) -> None:
     """Queue (once per backward pass) the callback that makes the caller's stream wait for the side stream and releases
     the operands the side launches were still reading."""
-    if dev in _WGRAD_SIDE["armed"]:
+    task = torch._C._current_graph_task_id()
+    if _WGRAD_SIDE["armed"].get(dev) == task:
         return
-    _WGRAD_SIDE["armed"].add(dev)
+    # a different id means the previous backward pass never reached its callback (it raised): arm again
+    _WGRAD_SIDE["armed"][dev] = task
 
     def join():
-        _WGRAD_SIDE["armed"].discard(dev)
+        _WGRAD_SIDE["armed"].pop(dev, None)
         torch.cuda.current_stream(dev).wait_stream(_wgrad_side_stream(dev))
         _WGRAD_SIDE["pending"].pop(dev, None)
 
