@@ -126,3 +126,21 @@ def test_lora_checkpoint_wire_format_round_trip(built_lib, tmp_path):
     lora.add_adapter(c, lora.LoraConfig(r=8, lora_alpha=8))
     with pytest.raises(ValueError):
         checkpoint.load_lora_weights(path, c)
+
+
+def test_host_logic_of_the_late_additions(built_lib):
+    """CPU-checkable parts of the pieces added late in the round: the exchange refuses to exist without a process group, the
+    GEGLU installer finds the feed-forward modules of the fixture, the product path still refuses CPU tensors."""
+    import pytest
+    import torch
+    from fixtures import sdxl_unet
+    from pairwise_sample_optimization_b200 import _lib, feed_forward, lora
+    with pytest.raises(_lib.Psob200Error):
+        lora.SymmetricGradExchange()  # no torch.distributed group initialised in this process
+    unet = sdxl_unet.UNet2DConditionModel(sdxl_unet.tiny_config())
+    n_blocks = sum(1 for m in unet.modules() if type(m).__name__ == "BasicTransformerBlock")
+    assert feed_forward.install_fused_geglu(unet) == n_blocks > 0
+    with pytest.raises(_lib.Psob200Error):
+        feed_forward.geglu(torch.randn(2, 16))
+    lora.set_wgrad_stream(True)
+    lora.set_wgrad_stream(False)
