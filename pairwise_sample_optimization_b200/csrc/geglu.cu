@@ -8,6 +8,8 @@
 // streaming work: forward reads 2 I and writes I elements per row, backward reads 3 I and writes 2 I.
 //
 // Arithmetic in fp32 (exact erf GELU, torch's default `approximate="none"`), one rounding to the storage type.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace psob200 {
@@ -173,16 +175,42 @@ static int geglu_check(const psob200_geglu_args& a, bool bwd) {
   return PSOB200_OK;
 }
 
-static dim3 geglu_grid(const psob200_geglu_args& a) {
+// One wave exactly: never more CTAs than fit at once (first version: 8 per SM assumed and rounded UP -- 1190 CTAs on 1184 slots
+// ran the forward as two waves, and the backward, limited to 5 CTAs per SM by registers, as 1.6).
+template <typename Kernel>
+static dim3 geglu_grid(const psob200_geglu_args& a, Kernel kernel) {
   const long long bx = (a.I + kGegluColThreads * 8 - 1) / (kGegluColThreads * 8);
   int sms = psob200_device_sm_count();
   if (sms <= 0) sms = 148;
-  long long by = ((long long)sms * 8 + bx - 1) / bx;  // 8 resident 256-thread CTAs per SM: one wave
+  static std::atomic<int> cached{0};  // per kernel instantiation (this function is a template): queried once
+  int per_sm = cached.load(std::memory_order_relaxed);
+  if (per_sm <= 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGegluThreads, 0) != cudaSuccess || per_sm <= 0) {
+      cudaGetLastError();
+      per_sm = 4;
+    }
+    cached.store(per_sm, std::memory_order_relaxed);
+  }
+  long long by = (long long)sms * per_sm / bx;  // rounded down
   const long long row_blocks = (a.M + 2 * kGegluRows - 1) / (2 * kGegluRows);  // two rows per thread per iteration
   if (by > row_blocks) by = row_blocks;
   if (by > 65535) by = 65535;
   if (by < 1) by = 1;
   return dim3((unsigned)bx, (unsigned)by);
+}
+
+template <typename T>
+static void launch_geglu_fwd(const psob200_geglu_args& a, cudaStream_t st) {
+  const dim3 grid = geglu_grid(a, geglu_fwd_kernel<T>);
+  geglu_fwd_kernel<T><<<grid, kGegluThreads, 0, st>>>(reinterpret_cast<const T*>(a.proj), reinterpret_cast<T*>(a.out), a.M, a.I,
+                                                       a.ld_proj, a.ld_out);
+}
+
+template <typename T>
+static void launch_geglu_bwd(const psob200_geglu_args& a, cudaStream_t st) {
+  const dim3 grid = geglu_grid(a, geglu_bwd_kernel<T>);
+  geglu_bwd_kernel<T><<<grid, kGegluThreads, 0, st>>>(reinterpret_cast<const T*>(a.proj), reinterpret_cast<const T*>(a.dout),
+                                                       reinterpret_cast<T*>(a.dproj), a.M, a.I, a.ld_proj, a.ld_dout, a.ld_dproj);
 }
 
 }  // namespace psob200
@@ -195,16 +223,9 @@ extern "C" int psob200_geglu_forward(const psob200_geglu_args* args, void* strea
   const int rc = geglu_check(a, false);
   if (rc != PSOB200_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const dim3 grid = geglu_grid(a);
-  if (a.dtype == PSOB200_BF16)
-    geglu_fwd_kernel<__nv_bfloat16><<<grid, kGegluThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a.proj),
-                                                                     reinterpret_cast<__nv_bfloat16*>(a.out), a.M, a.I, a.ld_proj, a.ld_out);
-  else if (a.dtype == PSOB200_F16)
-    geglu_fwd_kernel<__half><<<grid, kGegluThreads, 0, st>>>(reinterpret_cast<const __half*>(a.proj), reinterpret_cast<__half*>(a.out),
-                                                              a.M, a.I, a.ld_proj, a.ld_out);
-  else
-    geglu_fwd_kernel<float><<<grid, kGegluThreads, 0, st>>>(reinterpret_cast<const float*>(a.proj), reinterpret_cast<float*>(a.out),
-                                                             a.M, a.I, a.ld_proj, a.ld_out);
+  if (a.dtype == PSOB200_BF16) launch_geglu_fwd<__nv_bfloat16>(a, st);
+  else if (a.dtype == PSOB200_F16) launch_geglu_fwd<__half>(a, st);
+  else launch_geglu_fwd<float>(a, st);
   return consume_launch_error("launch geglu_fwd_kernel", cudaSuccess);
 }
 
@@ -214,17 +235,8 @@ extern "C" int psob200_geglu_backward(const psob200_geglu_args* args, void* stre
   const int rc = geglu_check(a, true);
   if (rc != PSOB200_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const dim3 grid = geglu_grid(a);
-  if (a.dtype == PSOB200_BF16)
-    geglu_bwd_kernel<__nv_bfloat16><<<grid, kGegluThreads, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(a.proj), reinterpret_cast<const __nv_bfloat16*>(a.dout),
-        reinterpret_cast<__nv_bfloat16*>(a.dproj), a.M, a.I, a.ld_proj, a.ld_dout, a.ld_dproj);
-  else if (a.dtype == PSOB200_F16)
-    geglu_bwd_kernel<__half><<<grid, kGegluThreads, 0, st>>>(reinterpret_cast<const __half*>(a.proj),
-                                                              reinterpret_cast<const __half*>(a.dout), reinterpret_cast<__half*>(a.dproj),
-                                                              a.M, a.I, a.ld_proj, a.ld_dout, a.ld_dproj);
-  else
-    geglu_bwd_kernel<float><<<grid, kGegluThreads, 0, st>>>(reinterpret_cast<const float*>(a.proj), reinterpret_cast<const float*>(a.dout),
-                                                             reinterpret_cast<float*>(a.dproj), a.M, a.I, a.ld_proj, a.ld_dout, a.ld_dproj);
+  if (a.dtype == PSOB200_BF16) launch_geglu_bwd<__nv_bfloat16>(a, st);
+  else if (a.dtype == PSOB200_F16) launch_geglu_bwd<__half>(a, st);
+  else launch_geglu_bwd<float>(a, st);
   return consume_launch_error("launch geglu_bwd_kernel", cudaSuccess);
 }
