@@ -9,10 +9,14 @@ package ``pairwise_sample_optimization_b200`` must not import this package.
 What is in here (each function cites the reference file:line it follows;
 paths are relative to ``/root/reference``):
 
-* ``reference_loader``  -- executes the reference's own two step files
-  *verbatim from /root/reference* under a tiny ``diffusers`` import stub.  Only
-  usable in the build container (the GPU box has no /root/reference); it is
-  what pins the restatement (``oracle/make_golden.py`` -> ``tests/golden``).
+* ``reference_loader``  -- executes the reference's own code *verbatim from
+  /root/reference*: the two step files under a tiny ``diffusers`` import stub,
+  and -- cut out of the trainer files at run time, since the trainers cannot be
+  imported -- the micro-step loss lines of both online trainers (turbo :810-850,
+  dmd2 :812-854), their ``sample_compare`` / ``compare`` functions and the
+  DreamBooth trainer's loss lines (:1846-1935).  Only usable in the build
+  container (the GPU box has no /root/reference); it is what pins the
+  restatement (``oracle/make_golden.py`` -> ``tests/golden``).
 * ``schedules``  -- the diffusers==0.27.0 scheduler constants the path reads
   (third-party, absent from /root/reference; restated from the published
   formula, anchored on sigma(999)=14.6146).
@@ -27,9 +31,12 @@ paths are relative to ``/root/reference``):
 Parity pinning status: the reference ships NO tests, golden vectors or
 fixtures, so the pin is "outputs of the reference itself
 run here": ``tests/golden/*.npz`` were produced by ``oracle/make_golden.py``
-calling the verbatim reference functions, and ``tests/test_oracle_golden.py``
-checks the restatement against them.  The inline losses exist only as trainer
-code that cannot be imported (needs diffusers/peft/accelerate); they are
-restated line by line and cross-checked against autograd + the fp64 closed
-form -- that part is "parity pinned to a restatement", stated in DESIGN.md.
+executing the reference's own step functions AND the trainers' own loss lines
+(see ``reference_loader``), with the restatements in ``steps`` / ``losses``
+asserted bit-identical (loss and autograd gradients), and
+``tests/test_oracle_golden.py`` re-checks both against the fixtures.  What stays
+"parity unpinned" is the arithmetic of the un-vendored third-party packages
+(diffusers 0.27.0 schedule constants, peft 0.11.1 ``lora.Linear``, diffusers
+``AttnProcessor2_0`` -- ``schedules`` / ``lora``): restated from the published
+behaviour and anchored on the reference's call sites and on sigma(999)=14.6146.
 """

@@ -8,12 +8,13 @@ What produces each number:
   * log-probs / prev_samples of ``turbo_*`` and ``dmd_*`` cases: the reference's own
     ``turbo_step_with_logprob`` / ``distilled_step_with_logprob`` loaded verbatim by
     ``oracle.reference_loader`` (fp32, CPU).
-  * ``online_*`` cases: the verbatim step functions called four times exactly like the
-    trainers do (turbo trainer :810-837, dmd2 trainer :812-843) followed by the inline loss
-    restated in ``oracle.losses.online_pso_loss`` (:844-850) and ``loss.backward()``;
-    gradients are torch autograd through the reference functions.
-  * ``dreambooth_*`` cases: restated loss (the trainer cannot be imported) + autograd.
-    Pinned to the restatement only.
+  * ``online_*`` cases: the trainer's OWN lines executed verbatim (turbo trainer :810-850, dmd2 trainer
+    :812-854: four step-with-logprob calls, ``sample_compare`` / ``compare``, the clamped ratios and the
+    inline loss -- cut out of the trainer file at run time by ``reference_loader.trainer_loss_block``) and
+    ``loss.backward()``; gradients are torch autograd through the reference's code.  The restatement
+    ``oracle.losses.online_micro_step`` must reproduce loss and gradients bit for bit (asserted here).
+  * ``dreambooth_*`` cases: likewise the DreamBooth trainer's lines :1846-1935 executed verbatim
+    (``reference_loader.trainer_dreambooth_block``), restatement asserted bit-identical.
   * ``*_fp64`` arrays: the fp64 closed form (``oracle.losses.*_closed_form``), stored so the
     GPU tests can judge fp32 kernels against the truth rather than the reference's fp32 noise.
 
@@ -130,6 +131,19 @@ def _online_case(name, kind, B, shape, seed, pred_noise, tie_every, full_inputs,
                                          d["next_latents"], d["timesteps"], d["human_prefer"], beta, eps,
                                          step_ratio=d["step_ratio"], step_fns=fn)
     loss.backward()
+    # the same numbers from the trainer's own lines: rewards chosen so that its compare function yields human_prefer
+    h = d["human_prefer"]
+    r0 = torch.where(h[:, 0] < 0, torch.zeros(B), torch.where(h[:, 0] > 0, torch.ones(B), torch.full((B,), 0.5)))
+    r1 = 1.0 - r0  # ties (dmd2 only: compare -> [0, 0]) have r0 == r1 == 0.5
+    mk = lambda k, r: {"timesteps": d["timesteps"][k][:, None], "latents": d["latents"][k][:, None],
+                       "next_latents": d["next_latents"][k][:, None], "rewards": r[:, None] if kind == "turbo" else r}
+    if kind == "dmd" or not tie_every:  # the turbo trainer's sample_compare has no tie outcome
+        pred_v = [p.clone().requires_grad_(True) for p in d["noise_pred"]]
+        loss_v, h_v = rl.trainer_loss_block(kind)(d["sched"], pred_v, d["noise_ref_pred"], mk(0, r0), mk(1, r1), 0, beta, eps,
+                                                  d["step_ratio"])
+        loss_v.backward()
+        assert torch.equal(h_v, h) and torch.equal(loss_v, loss), (name, loss_v.item(), loss.item())
+        assert all(torch.equal(a.grad, b.grad) for a, b in zip(pred_v, pred)), name
     cf = losses.online_closed_form(kind, d["sched"], d["noise_pred"], d["noise_ref_pred"], d["latents"],
                                    d["next_latents"], d["timesteps"], d["human_prefer"], beta, eps,
                                    step_ratio=d["step_ratio"])
@@ -180,6 +194,11 @@ def _dreambooth_case(name, b, shape, seed, loss_type, beta, nu, lam):
     loss, lw, ll, logits = losses.dreambooth_pso_loss(mp, d["ref_pred"], d["noisy"], d["x0"], d["sigmas"],
                                                       loss_type, beta, nu, lam)
     loss.backward()
+    mp_v = d["model_pred"].clone().requires_grad_(True)
+    loss_v, lw_v, ll_v, logits_v = rl.trainer_dreambooth_block()(mp_v, d["ref_pred"], d["noisy"], d["x0"], d["sigmas"], loss_type,
+                                                                  beta, nu, lam)
+    loss_v.backward()
+    assert torch.equal(loss_v, loss) and torch.equal(mp_v.grad, mp.grad) and torch.equal(logits_v, logits), name
     cf = losses.dreambooth_closed_form(d["model_pred"], d["ref_pred"], d["noisy"], d["x0"], d["sigmas"],
                                        loss_type, beta, nu, lam)
     np.savez_compressed(
