@@ -13,8 +13,10 @@ paths are relative to ``/root/reference``):
   /root/reference*: the two step files under a tiny ``diffusers`` import stub,
   and -- cut out of the trainer files at run time, since the trainers cannot be
   imported -- the micro-step loss lines of both online trainers (turbo :810-850,
-  dmd2 :812-854), their ``sample_compare`` / ``compare`` functions and the
-  DreamBooth trainer's loss lines (:1846-1935).  Only usable in the build
+  dmd2 :812-854), their ``sample_compare`` / ``compare`` functions, the
+  DreamBooth trainer's loss lines (:1846-1935) and the denoising loops of the
+  two sampler pipelines (sdxl_turbo_with_logprob.py :112-151,
+  sdxl_dmd_with_logprob.py :109-164).  Only usable in the build
   container (the GPU box has no /root/reference); it is what pins the
   restatement (``oracle/make_golden.py`` -> ``tests/golden``).
 * ``schedules``  -- the diffusers==0.27.0 scheduler constants the path reads

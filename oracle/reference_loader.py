@@ -199,3 +199,46 @@ def trainer_dreambooth_block():
 
     run.source_span = ("train_pso_sdxl_turbo_dreambooth.py", start + 1, end)
     return run
+
+
+def pipeline_denoising_loop(kind: str):
+    """The denoising loop of the reference's sampler pipeline, verbatim: sdxl_turbo_with_logprob.py from
+    ``all_latents = [latents]`` to the line before ``## vae decode`` (:111-149) / sdxl_dmd_with_logprob.py likewise
+    (:108-162, with the file's own ``_get_x0_from_noise``).  The pipeline files import diffusers' pipeline classes at module
+    level, so the loop is cut out and executed with the names it uses: the reference's own step function, a caller-supplied
+    ``unet(latent_input, t) -> noise_pred`` behind the pipeline's call signature, the scheduler, the generator.
+
+    Returns ``run(unet, noise_scheduler, latents, generator, num_inference_steps, timesteps=None)`` ->
+    turbo: ``(latents, all_latents, all_log_probs, all_model_input_latents)``; dmd: ``(x0_pred, all_latents, all_log_probs)``.
+    ``latents`` is what the pipeline holds when the loop starts (already multiplied by ``init_noise_sigma``)."""
+    fname = "sdxl_turbo_with_logprob.py" if kind == "turbo" else "sdxl_dmd_with_logprob.py"
+    with open(os.path.join(_PATCH_DIR, fname)) as f:
+        lines = f.read().split("\n")
+    start = next(i for i, l in enumerate(lines) if l.strip() == "all_latents = [latents]")
+    end = next(i for i in range(start, len(lines)) if lines[i].strip().startswith("## vae decode"))
+    code = compile(_dedent(lines[start:end]), f"<reference {fname}:{start + 1}-{end}>", "exec")
+    ns0 = {"torch": torch}
+    if kind == "dmd":
+        d0 = next(i for i, l in enumerate(lines) if l.startswith("def _get_x0_from_noise("))
+        d1 = next(i for i in range(d0 + 1, len(lines)) if lines[i].startswith("def ") or lines[i].startswith("@"))
+        exec(compile("\n".join(lines[d0:d1]) + "\n", f"<reference {fname}:{d0 + 1}-{d1}>", "exec"), ns0)
+    step_fn = turbo_step_with_logprob() if kind == "turbo" else distilled_step_with_logprob()
+    step_name = "turbo_step_with_logprob" if kind == "turbo" else "distilled_step_with_logprob"
+
+    def run(unet, noise_scheduler, latents, generator, num_inference_steps, timesteps=None):
+        def unet_call(x, t, *args, **kwargs):  # the pipeline's two call conventions: [0] of a tuple / .sample
+            out = unet(x, t)
+            return (out,) if kwargs.get("return_dict") is False else types.SimpleNamespace(sample=out)
+
+        ns = dict(ns0)
+        ns.update({step_name: step_fn, "unet": unet_call, "noise_scheduler": noise_scheduler, "latents": latents,
+                   "timesteps": noise_scheduler.timesteps if timesteps is None else timesteps, "generator": generator,
+                   "num_inference_steps": num_inference_steps, "batch_size": latents.shape[0],
+                   "prompt_embeds": torch.zeros(1), "unet_added_conditions": None})
+        exec(code, ns)
+        if kind == "turbo":
+            return ns["latents"], ns["all_latents"], ns["all_log_probs"], ns["all_model_input_latents"]
+        return ns["x0_pred"], ns["all_latents"], ns["all_log_probs"]
+
+    run.source_span = (fname, start + 1, end)
+    return run
