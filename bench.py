@@ -33,6 +33,17 @@ Numbers on the JSON line:
                         algorithmic bytes against the measured HBM copy bandwidth.
   loss_kernel_roofline / lora_gemm_large : the two kernel-level figures of BASELINE config 5 (fused loss+grad kernel at 256
                         pairs x 128x128 latents against the HBM roofline; the fused base+LoRA GEMM at M = 18944).
+  sampler_kernel_roofline : step_logprob_kernel (sampling mode) at 256 x 4x128x128 bf16 against the HBM roofline.
+  gpu_eager_baseline  : the reference's flow on THIS GPU with stock torch kernels -- the same fixture and batch, stock
+                        nn.Linear + the peft-style LoRA module (3 cuBLAS GEMMs + scale + add per projection), 4 separate UNet
+                        forwards, 4 step-with-logprob calls, inline loss, autograd -- eager and (where it captures) replayed
+                        from a CUDA graph: the honest "reference on this box" figure.
+  lora_projection_vs_cublas : one LoRA-wrapped projection forward + backward, this library against 3 x cuBLAS + scale + add
+                        under autograd, at the three in-step shapes of the workload.
+  gate / grad_norm    : fraction of (pair, branch) clamp gates that were open in the timed step and the gradient norm of the
+                        last optimizer boundary (a closed gate would make the backward vacuous).
+  exchange_check      : N > 1: the gradient exchange of this run against ncclAllReduce(AVG) on a copy, outside the timed region.
+  turbo64             : a short run of BASELINE configs[1] appended after the main timing (value, ms_per_step, roofline).
   cpu_baseline        : the oracle port of the reference's PyTorch path (fp32, same UNet architecture) on this box's host
                         cores, one micro-step of ONE pair (bounded sample), N = 1 / rank 0 only.
 `--impl reference` times that oracle port as the reference arm (the reference is Python that needs diffusers / peft /
@@ -180,7 +191,7 @@ def graph_timed(fn, reps, per_graph=2):
 
 
 # ----------------------------------------------------------------------------------------------- kernel-level figures
-def loss_kernel_roofline(pso, dev, peaks, ncu_traffic):
+def loss_kernel_roofline(pso, dev, peaks):
     """Fused loss+grad kernel alone at the top of the config-5 sweep: 256 pairs of 4x128x128 bf16 latents (DMD2 shapes);
     inputs (336 MB) exceed L2.  Algorithmic bytes = 10 N sizeof(bf16) per pair."""
     import types
@@ -201,8 +212,9 @@ def loss_kernel_roofline(pso, dev, peaks, ncu_traffic):
     ms = graph_timed(call, 20, per_graph=1)
     alg = 10 * n * 2 * B
     ach = alg / (ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic("pair_loss_grad_tmem_kernel@256x4x128x128_bf16")
     return {"kernel": "pair_loss_grad_tmem_kernel<bf16,bf16,ref>", "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"],
-            "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4), "traffic": ncu_traffic,
+            "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4), "traffic": traffic, "traffic_source": traffic_src,
             "workload": "256 pairs x 4x128x128 bf16 (BASELINE config 5 top of sweep)", "algorithmic_bytes_per_launch": alg,
             "avg_launch_us": round(ms * 1e3, 2), "peak_source": peaks["source"]}
 
@@ -225,10 +237,447 @@ def lora_gemm_large(dev, peaks):
 
 
 # ----------------------------------------------------------------------------------------------- b200 arm
+def ncu_traffic(key):
+    """(bytes per launch, source) of a committed `ncu --set full` capture (profiles/ncu_traffic.json), else (None, None)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            e = json.load(f).get(key)
+        return (e["bytes"], e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def config_block(args, name):
+    """The `config` object of the JSON line: names the WORKLOAD only, so that both arms print the same object."""
+    conf = CONFIGS[name]
+    return {"workload": conf["workload"] if not args.tiny else "TINY fixture (debug run, not the benchmark)", "name": name,
+            "pairs_per_gpu_per_step": args.pairs, "latent_shape": [4, conf["latent_hw"], conf["latent_hw"]],
+            "lora_rank": conf["rank"], "beta": 50.0, "eps": 0.1, "accum": ACCUM}
+
+
+def make_scheduler(kind, dev=None):
+    sched = turbo_scheduler() if kind == "turbo" else dmd_scheduler()
+    if dev is not None:
+        for k, v in list(vars(sched).items()):
+            setattr(sched, k, v.to(dev))
+    return sched
+
+
+class B200Arm:
+    """One workload configuration on this repo's kernels: model, flat optimizer, static device batch, captured micro-step."""
+
+    def __init__(self, args, name, dev, rank, world, L):
+        import pairwise_sample_optimization_b200 as pso
+        from fixtures import micro_step, sdxl_unet
+        from pairwise_sample_optimization_b200 import lora
+        self.args, self.name, self.dev, self.rank, self.world, self.L = args, name, dev, rank, world, L
+        self.pso, self.lora, self.micro_step = pso, lora, micro_step
+        conf = CONFIGS[name]
+        self.kind, self.hw, self.r = conf["kind"], conf["latent_hw"], conf["rank"]
+        self.B = args.pairs
+        # ---- model: random-init SDXL-architecture UNet in bf16, LoRA on to_q/to_k/to_v/to_out.0
+        torch.manual_seed(1234)  # same base weights on every rank (as a checkpoint would give)
+        cfg = sdxl_unet.tiny_config() if args.tiny else sdxl_unet.sdxl_config()
+        with torch.device(dev):
+            unet = sdxl_unet.UNet2DConditionModel(cfg)
+        unet = unet.to(torch.bfloat16).requires_grad_(False)
+        wrapped = lora.add_adapter(unet, lora.LoraConfig(r=self.r, lora_alpha=self.r))
+        for m in wrapped:  # the reference starts from B = 0; use a small non-zero B so every adapter GEMM does real work
+            torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
+        unet.set_attn_processor(lora.PSOAttnProcessor2_0())
+        if args.fused_geglu:  # the feed-forward's gated GELU on one fused kernel each way (outside SURVEY section 8's rows)
+            from pairwise_sample_optimization_b200 import feed_forward
+            feed_forward.install_fused_geglu(unet)
+        lora.set_wgrad_stream(args.wgrad_stream)
+        unet.train()
+        if args.grad_checkpointing:
+            unet.enable_gradient_checkpointing()  # turbo trainer :358
+        self.unet, self.cfg = unet, cfg
+        # parameters, gradients and Adam moments of all 1120 adapter matrices live in four flat fp32 buffers: the optimizer
+        # boundary is one exchange + two launches (clip + AdamW + zero_grad + 16-bit operand refresh).  Data-parallel exchange:
+        # one kernel of ours per rank over the NVLink multicast mapping (in-switch reduction fused with the norm pass of
+        # clip_grad_norm_); `--exchange nccl` (or a group without multicast support) = one NCCL all-reduce
+        opt_kw = dict(lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_grad_norm=1.0)
+        self.opt, self.exchange_kind = None, "none (1 GPU)"
+        if world > 1 and args.exchange == "multimem":
+            try:
+                self.opt = lora.FusedLoRAOptimizer(unet, exchange=lora.SymmetricGradExchange(), **opt_kw)
+                self.exchange_kind = "multimem.ld_reduce/st kernel fused with the gradient-norm pass (NVLink SHARP), no NCCL call"
+            except Exception as e:  # no NVSwitch multicast on this box: same on every rank
+                print(f"[bench] symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+        if self.opt is None:
+            self.opt = lora.FusedLoRAOptimizer(unet, **opt_kw)
+            if world > 1:
+                self.exchange_kind = "one NCCL all-reduce of the flat gradient"
+        self.bucket = self.opt.bucket
+        self.sched = make_scheduler(self.kind)
+        pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
+        host = micro_step.synth_batch(self.B, self.hw, cfg.cross_attention_dim, pooled, 100 + rank,
+                                      getattr(self.sched, "sigmas", None), dtype=torch.bfloat16, kind=self.kind)
+        if not args.separate_forwards:
+            host = micro_step.batched_view(host)
+        self.host = {k: v.pin_memory() for k, v in host.items()}
+        self.d = {k: v.to(dev) for k, v in self.host.items()}
+        self.fwd_bwd = micro_step.product_micro_step if args.separate_forwards else micro_step.product_micro_step_batched
+        self.ref_stream = torch.cuda.Stream() if (args.overlap_reference and not args.separate_forwards) else None
+        self.graph = self.static_loss = self.side = None
+        self.launches_per_micro = 0
+
+    # ---- one micro-step (turbo trainer :771-861 / dmd2 trainer :773-864)
+    def micro(self, batch, overlap=True, **extra):
+        kw = {"ref_stream": self.ref_stream} if (self.ref_stream is not None and overlap) else {}
+        return self.fwd_bwd(self.pso, self.lora, self.unet, batch, self.sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM,
+                            kind=self.kind, **kw, **extra)
+
+    def optimizer_boundary(self, i):
+        if (i + 1) % ACCUM == 0:  # turbo trainer :858-861 (sync_gradients): exchange, clip, AdamW, zero_grad
+            self.opt.all_reduce()
+            self.opt.step()
+
+    def capture(self):
+        # warm up eagerly on a side stream (also fills every host-side cache), then capture ONE micro-step: forward(s),
+        # fused loss+grad kernel, backward with in-place accumulation into the flat bucket.  Replays need no Python.
+        self.side = torch.cuda.Stream()
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            for _ in range(3):
+                self.micro(self.d)
+        torch.cuda.current_stream().wait_stream(self.side)
+        torch.cuda.synchronize()
+        self.pso.check_status(self.dev)
+        self.bucket.zero_()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = self.L.psob200_launch_count()
+        with torch.cuda.graph(self.graph, stream=self.side):
+            self.static_loss = self.micro(self.d)
+        self.launches_per_micro = self.L.psob200_launch_count() - n0  # kernels of this library inside the captured micro-step
+        self.bucket.zero_()
+
+    def step(self, i):
+        if self.graph is not None:
+            self.graph.replay()  # the captured micro-step reads the static device batch `d`
+            loss = self.static_loss
+        else:
+            loss = self.micro(self.d)
+        self.optimizer_boundary(i)
+        return loss
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms: float) -> float:
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def timed(self, K, W):
+        """Exactly K steps, inputs resident in HBM, CUDA events, max over ranks."""
+        for i in range(W):
+            self.step(i)
+        self.optimizer_boundary(ACCUM - 1)  # one untimed optimizer boundary: first exchange, kernels loaded
+        self.pso.check_status(self.dev)
+        self.bucket.zero_()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        launches0 = self.L.psob200_launch_count()
+        with ClockSampler(self.dev.index) as clocks:
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+            ev0.record()
+            marks[0].record()
+            for i in range(K):
+                loss = self.step(i)
+                marks[i + 1].record()
+            ev1.record()
+            self.barrier()
+        launches = self.L.psob200_launch_count() - launches0 + K * self.launches_per_micro
+        per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(K)]
+        ms_per_step = self.max_over_ranks(ev0.elapsed_time(ev1)) / K
+        out = {"value": self.world * self.B / (ms_per_step * 1e-3), "ms_per_step": ms_per_step, "per_step": per_step,
+               "launches": int(launches), "clocks": clocks.summary(), "loss": float(loss.item()) * ACCUM}
+        if K >= ACCUM:  # at least one optimizer boundary inside the timed region: its (pre-clip) gradient norm
+            out["grad_norm"] = float(self.opt.grad_norm.item())
+        return out
+
+    def e2e(self, K):
+        """The same K steps with the step's inputs copied from pinned host memory and the loss read back, every step."""
+        loss_pinned = torch.empty((), dtype=torch.float32).pin_memory()
+        h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+
+        def e2e_step(i):
+            for k, v in self.host.items():
+                self.d[k].copy_(v, non_blocking=True)
+            loss = self.step(i)
+            loss_pinned.copy_(loss.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(loss_pinned)
+        self.bucket.zero_()
+        e2e_step(0)
+        self.bucket.zero_()
+        self.barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        e2e_ms = self.max_over_ranks((time.perf_counter() - t0) * 1e3)
+        self.barrier()
+        self.bucket.zero_()
+        return {"value": round(self.world * self.B * K / (e2e_ms * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms / K, 3)}
+
+    def gate(self):
+        """One eager micro-step (untimed) with the loss kernel's per-pair statistics: how many clamp gates were open."""
+        self.bucket.zero_()
+        _, stats = self.micro(self.d, return_stats=True) if not self.args.separate_forwards else (None, None)
+        self.bucket.zero_()
+        if stats is None:
+            return None
+        delta = stats[:, 4:6].double()  # log pi_theta - log pi_ref per branch
+        h = self.d["human_prefer"].double()
+        ratio = torch.exp(delta)
+        open_ = ((ratio >= 1 - 0.1) & (ratio <= 1 + 0.1) & (h != 0)).double()
+        return {"open_fraction": round(float(open_.mean().item()), 4), "pair_branches": int(open_.numel()),
+                "max_abs_log_ratio": round(float(delta.abs().max().item()), 5),
+                "note": "a (pair, branch) contributes gradient only while 1-eps <= pi_theta/pi_ref <= 1+eps (turbo :844-845)"}
+
+    def instrumented(self, ms_per_step, peaks):
+        """Roofline of the dominant kernel of ours: instrumented pass, ONE launch between each pair of events."""
+        lora = self.lora
+        self.bucket.zero_()
+        sink = []
+        lora.set_timing_sink(sink)
+        if self.graph is None:
+            self.micro(self.d, overlap=False)
+        else:
+            # captured like the timed step, with the event records as graph nodes: an eager pass is host-bound (the GPU idles
+            # between a record and the launch behind it) and would charge host latency to the kernels
+            self.side.wait_stream(torch.cuda.current_stream())
+            inst_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(inst_graph, stream=self.side):  # the stream the step was warmed up and captured on
+                self.micro(self.d, overlap=False)  # one stream: a launch's interval must not include waiting for the other stream's CTAs
+            for _ in range(2):
+                inst_graph.replay()  # the events keep the timestamps of the last replay
+        lora.set_timing_sink(None)
+        torch.cuda.synchronize()
+        is_main = lambda role: role.startswith("y =") or role.startswith("dx =") or role.startswith("qkv") or role.startswith("kv")
+        agg = {True: [0.0, 0.0, 0.0, 0], False: [0.0, 0.0, 0.0, 0]}  # ms, flops, bytes, launches
+        by_shape = {}
+        for ev0, ev1, fl, by, role, shape in sink:
+            ms = ev0.elapsed_time(ev1)
+            a_ = agg[is_main(role)]
+            a_[0] += ms; a_[1] += fl; a_[2] += by; a_[3] += 1
+            t = by_shape.setdefault((role,) + tuple(shape), [0.0, 0, 0.0, 0.0])
+            t[0] += ms; t[1] += 1; t[2] += fl; t[3] += by
+        m_ms, m_fl, m_by, m_n = agg[True]
+        s_ms, s_fl, s_by, s_n = agg[False]
+        ach = m_fl / (m_ms * 1e-3) / 1e12 if m_ms > 0 else 0.0
+        rows = [{"launch": k[0], "M": k[1], "K": k[2], "N": k[3], "r": k[4], "launches_per_step": v[1],
+                 "avg_us": round(v[0] * 1e3 / v[1], 2), "ms_per_step": round(v[0], 2),
+                 **({"tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1)} if is_main(k[0]) else
+                    {"gbs": round(v[3] / (v[0] * 1e-3) / 1e9, 1)})}
+                for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])]
+        traffic, traffic_src = ncu_traffic("lora_gemm2_kernel@M8192_K1280+64_N1280_bf16") if self.name == "dmd128" else (None, None)
+        roofline = {"kernel": "lora_gemm2_kernel / lora_gemm_kernel main passes: y = x W^T + b + t B^T, dx = dy W + u A (tcgen05, "
+                              "frozen weight + adapter in one pass) over the 560 LoRA-wrapped projections",
+                    "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": round(ach / peaks["tf_sustained"], 4), "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "launches_per_step": m_n, "avg_launch_us": round(m_ms * 1e3 / max(m_n, 1), 2),
+                    "share_of_step": round(m_ms / ms_per_step, 4), "flops_per_step": m_fl,
+                    "algorithmic_flops": "2 M N (K + r) per launch (r = 0 for the frozen-reference pass)",
+                    "by_launch": [r_ for r_ in rows if is_main(r_["launch"])],
+                    "how": "one CUDA-event pair around EVERY launch (psob200 forward_phases / backward_phases issue the launches of "
+                           "a projection one at a time; event records captured as graph nodes) in one extra replayed step on ONE "
+                           "stream (in the timed step the frozen-reference forward shares the SMs from a second stream, which would "
+                           "charge its CTAs' residency to these intervals); includes the graph-node gaps around each launch and "
+                           "lacks the programmatic-dependent-launch overlap, so slightly pessimistic"}
+        s_ach = s_by / (s_ms * 1e-3) / 1e9 if s_ms > 0 else 0.0
+        skinny = {"kernel": "lora_gemm_kernel skinny passes: t = s x A^T, u = s dy B, dA += u^T x, dB += dy^T t (rank-r side of "
+                            "every projection; arithmetic intensity <= 84 flop/B, SURVEY.md section 8d)",
+                  "bound": "hbm", "achieved": round(s_ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                  "frac": round(s_ach / peaks["hbm"], 4), "launches_per_step": s_n,
+                  "avg_launch_us": round(s_ms * 1e3 / max(s_n, 1), 2), "share_of_step": round(s_ms / ms_per_step, 4),
+                  "algorithmic_bytes": "operands read once + result written once per launch",
+                  "by_launch": [r_ for r_ in rows if not is_main(r_["launch"])]}
+        self.bucket.zero_()
+        return roofline, skinny
+
+    def exchange_check(self):
+        """N > 1, outside the timed region: this run's gradient exchange (the multimem kernel, or NCCL with `--exchange nccl`)
+        against ncclAllReduce(AVG) on a copy of the same per-rank data."""
+        import torch.distributed as dist
+        opt, dev = self.opt, self.dev
+        flat = self.bucket.flat
+        g = torch.Generator(device=dev).manual_seed(4242 + self.rank)
+        src = torch.randn(flat.numel(), device=dev, generator=g) * (1.0 + self.rank)
+        want = src.clone()
+        dist.all_reduce(want, op=dist.ReduceOp.AVG)
+        flat.copy_(src)
+        del src
+        opt.all_reduce()
+        torch.cuda.synchronize()
+        max_rel = float(((flat - want).abs().max() / want.abs().max()).item())
+        bits = flat.view(torch.int32)
+        hi, lo = bits.clone(), bits.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        bitwise = bool(torch.equal(hi, lo))
+        del hi, lo
+        want_norm = float(torch.linalg.vector_norm(want.double()).item())
+        norm_rel = None
+        if opt.exchange is not None:  # the sum of squares the fused kernel left for clip_grad_norm_, one part per rank
+            ex = opt.exchange
+            parts = ex.buffer[ex.n:ex.n + 2 * ex.world].view(torch.float64)
+            norm_rel = abs(float(parts.sum().sqrt().item()) - want_norm) / want_norm
+            ex.buffer[ex.n:].zero_()
+            opt._parts_ready = False
+        flat.zero_()
+        self.barrier()
+        worst = torch.tensor([max_rel, 0.0 if bitwise else 1.0, norm_rel or 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        return {"against": "ncclAllReduce(AVG) of the same per-rank gradients (seeded N(0,(1+rank)^2)), outside the timed region",
+                "exchange": self.exchange_kind, "elements": int(flat.numel()), "max_rel_err": float(worst[0].item()),
+                "bitwise_equal_across_ranks": bool(worst[1].item() == 0.0),
+                "norm_rel_err": (float(worst[2].item()) if norm_rel is not None else None)}
+
+    def close(self):
+        self.lora.set_wgrad_stream(False)
+        self.graph = self.static_loss = None
+        self.unet = self.opt = self.bucket = self.d = self.host = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def sampler_kernel_roofline(dev, peaks):
+    """step_logprob_kernel in sampling mode (x' = mu + s noise, log-prob, next scaled UNet input) alone: 256 samples of
+    4x128x128 bf16, Euler-ancestral schedule.  Algorithmic bytes per sample = 3 N read (prediction, latent, noise) + 2 N written
+    (next latent, next scaled input)."""
+    from pairwise_sample_optimization_b200 import _lib, runtime, step_ops
+    B, n = 256, 4 * 128 * 128
+    g = torch.Generator(device=dev).manual_seed(11)
+    mk = lambda: torch.randn(B, 4, 128, 128, device=dev, generator=g).bfloat16()
+    pred, x, noise = mk(), mk(), mk()
+    ts = torch.tensor([999, 749, 499], device=dev)[torch.randint(0, 3, (B,), device=dev)]
+    sched = runtime.turbo_schedule(make_scheduler("turbo", dev), dev, _lib.ts_dtype_code(ts))
+    ms = graph_timed(lambda: step_ops.step_forward(sched, pred, x, ts, noise=noise, want_scaled_next=True), 20, per_graph=1)
+    alg = 5 * n * 2 * B
+    ach = alg / (ms * 1e-3) / 1e9
+    traffic, src = ncu_traffic("step_logprob_kernel@256x4x128x128_bf16_sampling")
+    return {"kernel": "step_logprob_kernel<bf16> sampling mode + fused next-input scaling", "bound": "hbm", "achieved": round(ach, 1),
+            "peak": peaks["hbm"], "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4), "traffic": traffic, "traffic_source": src,
+            "workload": "256 samples x 4x128x128 bf16", "algorithmic_bytes_per_launch": alg,
+            "avg_launch_us": round(ms * 1e3, 2), "peak_source": peaks["source"]}
+
+
+def lora_projection_vs_cublas(dev, shapes, r):
+    """One LoRA-wrapped projection, forward + backward (dX, dA, dB), through this library's public module against the stock
+    lowering (F.linear x 3 + scale + add under autograd = what peft's lora.Linear runs on cuBLAS); CUDA events around graph replays."""
+    from pairwise_sample_optimization_b200 import lora
+    g = torch.Generator(device=dev).manual_seed(5)
+    rn = lambda *s, sc=1.0: (torch.randn(*s, device=dev, generator=g) * sc).bfloat16()
+    rows = []
+    for (M, K, N) in shapes:
+        x, dy = rn(M, K), rn(M, N)
+        lay = lora.LoRALinear(torch.nn.Linear(K, N, bias=True, device=dev, dtype=torch.bfloat16), r, r)
+        with torch.no_grad():
+            lay.lora_B["default"].weight.normal_(std=0.02)
+        w, b = lay.base_layer.weight, lay.base_layer.bias
+        xg = x.clone().requires_grad_(True)
+        xa = x.clone().requires_grad_(True)
+        Ap = lay.lora_A["default"].weight.detach().bfloat16().clone().requires_grad_(True)
+        Bp = lay.lora_B["default"].weight.detach().bfloat16().clone().requires_grad_(True)
+
+        def ours():
+            lay(xg).backward(dy)
+
+        def stock():
+            F = torch.nn.functional
+            (F.linear(xa, w, b) + F.linear(F.linear(xa, Ap), Bp) * 1.0).backward(dy)
+        t_o, t_s = graph_timed(ours, 10) * 1e3, graph_timed(stock, 10) * 1e3
+        rows.append({"M": M, "K": K, "N": N, "r": r, "ours_fwd_bwd_us": round(t_o, 1), "cublas_fwd_bwd_us": round(t_s, 1),
+                     "speedup": round(t_s / t_o, 3)})
+    return rows
+
+
+def gpu_eager_baseline(args, name, dev, host, reps=4):
+    """The reference's micro-step on THIS GPU with stock torch kernels: same architecture, same base weights (seed), same batch;
+    stock nn.Linear + the peft-style LoRA module (oracle/lora.py: 3 cuBLAS GEMMs + scale + add), 4 separate forwards, the four
+    step-with-logprob calls + inline loss restated in oracle/, autograd backward.  oracle/ is checker code: it is executed here
+    only as a reported BASELINE, never on the product path.  bf16 weights AND bf16 adapters, activations resident (no gradient
+    checkpointing): both more favourable to the baseline than the reference's shipped recipe."""
+    from fixtures import micro_step, sdxl_unet
+    from oracle import lora as olora, losses as olosses
+    conf = CONFIGS[name]
+    kind, r = conf["kind"], conf["rank"]
+    torch.manual_seed(1234)
+    cfg = sdxl_unet.tiny_config() if args.tiny else sdxl_unet.sdxl_config()
+    with torch.device(dev):
+        unet = sdxl_unet.UNet2DConditionModel(cfg)
+    unet = unet.to(torch.bfloat16).requires_grad_(False)
+    wrapped = olora.oracle_add_adapter(unet, r, r)
+    for m in wrapped:
+        torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
+        m.lora_A.to(torch.bfloat16); m.lora_B.to(torch.bfloat16)
+    unet.train()
+    sched = make_scheduler(kind, dev)
+    d = {k: v.to(dev) for k, v in host.items()}
+
+    def one():
+        for m in wrapped:
+            m.lora_A["default"].weight.grad = None
+            m.lora_B["default"].weight.grad = None
+        return micro_step.oracle_micro_step(olora, olosses, unet, d, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM, kind=kind)
+
+    def timed(fn, n):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        torch.cuda.synchronize()
+        evs[0].record()
+        for i in range(n):
+            fn()
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        return statistics.mean(evs[i].elapsed_time(evs[i + 1]) for i in range(n))
+    for _ in range(2):
+        loss = one()
+    ms_eager = timed(one, reps)
+    B = args.pairs
+    out = {"kind": "torch-eager on this GPU: stock nn.Linear + peft-style LoRA module (3 cuBLAS GEMMs + scale + add), 4 forwards, "
+                   "~340-launch loss chain, autograd; bf16, activations resident",
+           "value": round(B / (ms_eager * 1e-3), 3), "unit": UNIT, "ms_per_step": round(ms_eager, 2), "steps": reps,
+           "loss": round(float(loss.item()) * ACCUM, 6)}
+    try:  # the same step replayed from a CUDA graph (no host launch latency): only where the flow has no host sync (DMD2)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            one()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            one()
+        graph.replay()
+        ms_graph = timed(graph.replay, reps)
+        out["graph_replayed"] = {"value": round(B / (ms_graph * 1e-3), 3), "ms_per_step": round(ms_graph, 2)}
+        del graph
+    except Exception as e:
+        torch.cuda.synchronize()
+        out["graph_replayed"] = {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
+    del unet, wrapped
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     import pairwise_sample_optimization_b200 as pso
-    from fixtures import micro_step, sdxl_unet
-    from pairwise_sample_optimization_b200 import _lib, lora
+    from pairwise_sample_optimization_b200 import _lib
 
     rank, world, local = dist_env()
     if args.gpus != world and world > 1:
@@ -241,255 +690,76 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    B, K, W = args.pairs, args.steps, max(args.warmup, 3)
+    K, W = args.steps, max(args.warmup, 3)
     peaks = measured_peaks()
-    conf = CONFIGS[args.config]
-    KIND, LATENT_HW, RANK = conf["kind"], conf["latent_hw"], conf["rank"]
 
-    # ---- model: random-init SDXL-architecture UNet in bf16, LoRA rank 8 on to_q/to_k/to_v/to_out.0
-    torch.manual_seed(1234)  # same base weights on every rank (as a checkpoint would give)
-    cfg = sdxl_unet.tiny_config() if args.tiny else sdxl_unet.sdxl_config()
-    with torch.device(dev):
-        unet = sdxl_unet.UNet2DConditionModel(cfg)
-    unet = unet.to(torch.bfloat16).requires_grad_(False)
-    wrapped = lora.add_adapter(unet, lora.LoraConfig(r=RANK, lora_alpha=RANK))
-    for m in wrapped:  # the reference starts from B = 0; use a small non-zero B so every adapter GEMM does real work
-        torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
-    unet.set_attn_processor(lora.PSOAttnProcessor2_0())
-    if args.fused_geglu:  # the feed-forward's gated GELU on one fused kernel each way (outside SURVEY section 8's rows)
-        from pairwise_sample_optimization_b200 import feed_forward
-        feed_forward.install_fused_geglu(unet)
-    lora.set_wgrad_stream(args.wgrad_stream)
-    unet.train()
-    if args.grad_checkpointing:
-        unet.enable_gradient_checkpointing()  # turbo trainer :358
-    # parameters, gradients and Adam moments of all 1120 adapter matrices live in four flat fp32 buffers: the optimizer
-    # boundary is one all-reduce + two launches (clip + AdamW + zero_grad + 16-bit operand refresh)
-    # data-parallel exchange: one kernel of ours per rank over the NVLink multicast mapping (in-switch reduction fused with the
-    # norm pass of clip_grad_norm_); `--exchange nccl` (or a group without multicast support) = one NCCL all-reduce
-    opt_kw = dict(lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_grad_norm=1.0)
-    opt, exchange_kind = None, "none (1 GPU)"
-    if world > 1 and args.exchange == "multimem":
-        try:
-            opt = lora.FusedLoRAOptimizer(unet, exchange=lora.SymmetricGradExchange(), **opt_kw)
-            exchange_kind = "multimem.ld_reduce/st kernel fused with the gradient-norm pass (NVLink SHARP), no NCCL call"
-        except Exception as e:  # no NVSwitch multicast on this box: same on every rank
-            print(f"[bench] symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
-    if opt is None:
-        opt = lora.FusedLoRAOptimizer(unet, **opt_kw)
-        if world > 1:
-            exchange_kind = "one NCCL all-reduce of the flat gradient"
-    bucket = opt.bucket
-    sched = turbo_scheduler() if KIND == "turbo" else dmd_scheduler()
-    pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
-    host = micro_step.synth_batch(B, LATENT_HW, cfg.cross_attention_dim, pooled, 100 + rank, getattr(sched, "sigmas", None),
-                                  dtype=torch.bfloat16, kind=KIND)
-    if not args.separate_forwards:
-        host = micro_step.batched_view(host)
-    host = {k: v.pin_memory() for k, v in host.items()}
-    d = {k: v.to(dev) for k, v in host.items()}
-    fwd_bwd = micro_step.product_micro_step if args.separate_forwards else micro_step.product_micro_step_batched
-
-    ref_stream = torch.cuda.Stream() if (args.overlap_reference and not args.separate_forwards) else None
-
-    def micro(batch, overlap=True):
-        kw = {"ref_stream": ref_stream} if (ref_stream is not None and overlap) else {}
-        return fwd_bwd(pso, lora, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM, kind=KIND, **kw)
-
-    def optimizer_boundary(i):
-        if (i + 1) % ACCUM == 0:  # turbo trainer :858-861 (sync_gradients): all-reduce, clip, AdamW, zero_grad
-            opt.all_reduce()
-            opt.step()
-
-    graph = None
-    static_loss = None
-    launches_per_micro = 0
-
-    def step(i, batch):
-        if graph is not None:
-            graph.replay()  # the captured micro-step reads the static device batch `d`
-            loss = static_loss
-        else:
-            loss = micro(batch)
-        optimizer_boundary(i)
-        return loss
-
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms: float) -> float:
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
-
+    arm = B200Arm(args, args.config, dev, rank, world, L)
     if not args.no_graph:
-        # warm up eagerly on a side stream (also fills every host-side cache), then capture ONE micro-step: forward(s),
-        # fused loss+grad kernel, backward with in-place accumulation into the flat bucket.  Replays need no Python.
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for i in range(3):
-                micro(d)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        pso.check_status(dev)
-        bucket.zero_()
-        graph = torch.cuda.CUDAGraph()
-        n0 = L.psob200_launch_count()
-        with torch.cuda.graph(graph, stream=side):
-            static_loss = micro(d)
-        launches_per_micro = L.psob200_launch_count() - n0  # kernels of this library inside the captured micro-step
-        bucket.zero_()
-    for i in range(W):
-        loss = step(i, d)
-    optimizer_boundary(ACCUM - 1)  # one untimed optimizer boundary: AdamW state allocation, first NCCL all-reduce
-    pso.check_status(dev)
-    bucket.zero_()
-
-    # ---- timed region: exactly K steps, inputs resident in HBM
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    launches0 = L.psob200_launch_count()
-    with ClockSampler(local) as clocks:
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
-        ev0.record()
-        marks[0].record()
-        for i in range(K):
-            loss = step(i, d)
-            marks[i + 1].record()
-        ev1.record()
-        barrier()
-    launches = L.psob200_launch_count() - launches0 + K * launches_per_micro
-    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(K)]
-    ms_per_step = max_over_ranks(ev0.elapsed_time(ev1)) / K
-    value = world * B / (ms_per_step * 1e-3)
-    loss_value = float(loss.item()) * ACCUM
-
-    # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, every step
-    loss_pinned = torch.empty((), dtype=torch.float32).pin_memory()
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
-
-    def e2e_step(i):
-        for k, v in host.items():
-            d[k].copy_(v, non_blocking=True)
-        loss = step(i, d)
-        loss_pinned.copy_(loss.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(loss_pinned)
-    bucket.zero_()
-    e2e_step(0)
-    bucket.zero_()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-    barrier()
-    e2e = {"value": round(world * B * K / (e2e_ms * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-           "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms / K, 3)}
-
-    # ---- roofline of the dominant kernel of ours: instrumented pass, ONE launch between each pair of events
+        arm.capture()
+    t = arm.timed(K, W)
+    e2e = arm.e2e(K)
     peak_hbm_gb = round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2)  # before the second (instrumented) graph
-    bucket.zero_()
-    sink = []
-    n_inst = 1
-    lora.set_timing_sink(sink)
-    if args.no_graph:
-        micro(d, overlap=False)
-    else:
-        # captured like the timed step, with the event records as graph nodes: an eager pass is host-bound (the GPU idles
-        # between a record and the launch behind it) and would charge host latency to the kernels
-        side.wait_stream(torch.cuda.current_stream())
-        inst_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(inst_graph, stream=side):  # the stream the step was warmed up and captured on
-            micro(d, overlap=False)  # one stream: a launch's interval must not include waiting for the other stream's CTAs
-        for _ in range(2):
-            inst_graph.replay()  # the events keep the timestamps of the last replay
-    lora.set_timing_sink(None)
-    torch.cuda.synchronize()
-    is_main = lambda role: role.startswith("y =") or role.startswith("dx =")
-    agg = {True: [0.0, 0.0, 0.0, 0], False: [0.0, 0.0, 0.0, 0]}  # ms, flops, bytes, launches
-    by_shape = {}
-    for ev0, ev1, fl, by, role, shape in sink:
-        ms = ev0.elapsed_time(ev1)
-        a_ = agg[is_main(role)]
-        a_[0] += ms; a_[1] += fl; a_[2] += by; a_[3] += 1
-        t = by_shape.setdefault((role,) + tuple(shape), [0.0, 0, 0.0, 0.0])
-        t[0] += ms; t[1] += 1; t[2] += fl; t[3] += by
-    m_ms, m_fl, m_by, m_n = agg[True]
-    s_ms, s_fl, s_by, s_n = agg[False]
-    ach = m_fl / (m_ms * 1e-3) / 1e12 if m_ms > 0 else 0.0
-    rows = [{"launch": k[0], "M": k[1], "K": k[2], "N": k[3], "r": k[4], "launches_per_step": v[1] // n_inst,
-             "avg_us": round(v[0] * 1e3 / v[1], 2), "ms_per_step": round(v[0] / n_inst, 2),
-             **({"tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1)} if is_main(k[0]) else
-                {"gbs": round(v[3] / (v[0] * 1e-3) / 1e9, 1)})}
-            for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])]
-    roofline = {"kernel": "lora_gemm2_kernel / lora_gemm_kernel main passes: y = x W^T + b + t B^T, dx = dy W + u A (tcgen05, "
-                          "frozen weight + adapter in one pass) over the 560 LoRA-wrapped projections",
-                "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / peaks["tf_sustained"], 4), "traffic": None,
-                "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "launches_per_step": m_n // n_inst, "avg_launch_us": round(m_ms * 1e3 / max(m_n, 1), 2),
-                "share_of_step": round(m_ms / n_inst / ms_per_step, 4), "flops_per_step": m_fl / n_inst,
-                "algorithmic_flops": "2 M N (K + r) per launch (r = 0 for the frozen-reference pass)",
-                "by_launch": [r_ for r_ in rows if is_main(r_["launch"])],
-                "how": "one CUDA-event pair around EVERY launch (psob200 forward_phases / backward_phases issue the launches of "
-                       "a projection one at a time; event records captured as graph nodes) in one extra replayed step on ONE "
-                       "stream (in the timed step the frozen-reference forward shares the SMs from a second stream, which would "
-                       "charge its CTAs' residency to these intervals); includes the graph-node gaps around each launch and "
-                       "lacks the programmatic-dependent-launch overlap, so slightly pessimistic"}
-    s_ach = s_by / (s_ms * 1e-3) / 1e9 if s_ms > 0 else 0.0
-    skinny = {"kernel": "lora_gemm_kernel skinny passes: t = s x A^T, u = s dy B, dA += u^T x, dB += dy^T t (rank-r side of "
-                        "every projection; arithmetic intensity <= 84 flop/B, SURVEY.md section 8d)",
-              "bound": "hbm", "achieved": round(s_ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
-              "frac": round(s_ach / peaks["hbm"], 4), "launches_per_step": s_n // n_inst,
-              "avg_launch_us": round(s_ms * 1e3 / max(s_n, 1), 2), "share_of_step": round(s_ms / n_inst / ms_per_step, 4),
-              "algorithmic_bytes": "operands read once + result written once per launch",
-              "note": "latency-bound: one 128-row tile per CTA walks the whole reduction (13 us per launch at any M)",
-              "by_launch": [r_ for r_ in rows if not is_main(r_["launch"])]}
-    bucket.zero_()
-
+    roofline, skinny = arm.instrumented(t["ms_per_step"], peaks)
+    gate = arm.gate()
     extra = {}
+    if world > 1:
+        extra["exchange_check"] = arm.exchange_check()
+    run_details = {"parallelism": f"dp{world} (pairs sharded; one exchange of the flat LoRA gradient per {ACCUM} steps)",
+                   "gradient_exchange": arm.exchange_kind,
+                   "activations": ("recomputed in the backward (gradient checkpointing, as the reference)" if args.grad_checkpointing
+                                   else "resident in HBM (no gradient checkpointing: same gradients, no recompute forward)"),
+                   "weight_gradients": "dA / dB launches on a side stream" if args.wgrad_stream else "in stream order",
+                   "feed_forward": "fused GEGLU kernels" if args.fused_geglu else "stock torch GEGLU",
+                   "l2_policy": "working set larger than L2 (5.1 GB of bf16 weights streamed every forward)",
+                   "forwards": "4 separate (as the reference)" if args.separate_forwards else
+                               "win+lose batched: 1 policy + 1 reference forward of batch 2B" +
+                               (", reference forward on a second stream" if arm.ref_stream is not None else ""),
+                   "timing": ("eager launches" if args.no_graph else "micro-step replayed from one CUDA graph; optimizer "
+                              "boundary eager") + ", CUDA events around K steps, max over ranks"}
+    host_batch = {k: v.clone() for k, v in arm.host.items()}
+    arm.close()
+    del arm
+
     if rank == 0 and not args.no_kernel_figures:
-        extra["loss_kernel_roofline"] = loss_kernel_roofline(pso, dev, peaks, args.ncu_traffic)
+        extra["loss_kernel_roofline"] = loss_kernel_roofline(pso, dev, peaks)
+        extra["sampler_kernel_roofline"] = sampler_kernel_roofline(dev, peaks)
         extra["lora_gemm_large"] = lora_gemm_large(dev, peaks)
+        if args.config == "dmd128" and not args.tiny:
+            extra["lora_projection_vs_cublas"] = lora_projection_vs_cublas(
+                dev, [(8192, 1280, 1280), (32768, 640, 640), (616, 2048, 1280)], CONFIGS[args.config]["rank"])
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        eager = gpu_eager_baseline(args, args.config, dev, host_batch)
+        eager["ratio_ours_over_eager"] = round(t["value"] / eager["value"], 3)
+        if "value" in eager.get("graph_replayed", {}):
+            eager["ratio_ours_over_graph_replayed"] = round(t["value"] / eager["graph_replayed"]["value"], 3)
+        extra["gpu_eager_baseline"] = eager
+    if world == 1 and args.config == "dmd128" and not args.no_turbo64 and not args.tiny:
+        # configs[1], short: the latency-bound regime (M = 2048 launches), driver-visible next to the headline configuration
+        arm2 = B200Arm(args, "turbo64", dev, rank, world, L)
+        if not args.no_graph:
+            arm2.capture()
+        t2 = arm2.timed(6, 3)
+        r2, s2 = arm2.instrumented(t2["ms_per_step"], peaks)
+        for blk in (r2, s2):
+            blk.pop("how", None); blk.pop("by_launch", None)
+        extra["turbo64"] = {"config": config_block(args, "turbo64"), "value": round(t2["value"], 3), "unit": UNIT, "steps": 6,
+                            "warmup": 3, "ms_per_step": round(t2["ms_per_step"], 3), "gpu_launches": t2["launches"],
+                            "loss": round(t2["loss"], 6), "roofline": r2, "lora_skinny_launches": s2}
+        arm2.close()
+        del arm2
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        del unet, opt, bucket
-        torch.cuda.empty_cache()
         cpu = cpu_reference(args, reps=1, warmup=0)
     if rank == 0:
         line = {
-            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": round(ms_per_step, 3), "ms_per_step_each": [round(v, 1) for v in per_step],
+            "metric": METRIC, "value": round(t["value"], 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(t["ms_per_step"], 3), "ms_per_step_each": [round(v, 1) for v in t["per_step"]],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": conf["workload"] if not args.tiny else "TINY fixture (debug run, not the benchmark)",
-                       "name": args.config,
-                       "pairs_per_gpu_per_step": B, "latent_shape": [4, LATENT_HW, LATENT_HW], "lora_rank": RANK,
-                       "beta": 50.0, "eps": 0.1, "accum": ACCUM,
-                       "parallelism": f"dp{world} (pairs sharded; one exchange of the flat LoRA gradient per {ACCUM} steps)",
-                       "gradient_exchange": exchange_kind,
-                       "activations": ("recomputed in the backward (gradient checkpointing, as the reference)" if args.grad_checkpointing
-                                       else "resident in HBM (no gradient checkpointing: same gradients, no recompute forward)"),
-                       "weight_gradients": "dA / dB launches on a side stream" if args.wgrad_stream else "in stream order",
-                       "feed_forward": "fused GEGLU kernels" if args.fused_geglu else "stock torch GEGLU",
-                       "l2_policy": "working set larger than L2 (5.1 GB of bf16 weights streamed every forward)",
-                       "forwards": "4 separate (as the reference)" if args.separate_forwards else
-                                   "win+lose batched: 1 policy + 1 reference forward of batch 2B" +
-                                   (", reference forward on a second stream" if ref_stream is not None else ""),
-                       "timing": ("eager launches" if args.no_graph else "micro-step replayed from one CUDA graph; optimizer "
-                                  "boundary eager") + ", CUDA events around K steps, max over ranks"},
-            "gpu_launches": int(launches), "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
+            "config": config_block(args, args.config), "run_details": run_details,
+            "gpu_launches": t["launches"], "clocks": t["clocks"], "e2e": e2e, "roofline": roofline,
             "lora_skinny_launches": skinny,
-            "loss": round(loss_value, 6), "peak_hbm_gb": peak_hbm_gb,
+            "loss": round(t["loss"], 6), "grad_norm": t.get("grad_norm"), "gate": gate, "peak_hbm_gb": peak_hbm_gb,
         }
         line.update(extra)
         if cpu is not None:
@@ -593,11 +863,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
             "steps": len(times), "steps_requested": K, "warmup": W, "ms_per_step": round(ms, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CONFIGS[args.config]["workload"] + " -- oracle port of the reference's PyTorch path on the "
-                                   "host cores", "name": args.config,
-                       "pairs_per_step": pairs,
-                       "latent_shape": [4, CONFIGS[args.config]["latent_hw"], CONFIGS[args.config]["latent_hw"]],
-                       "lora_rank": CONFIGS[args.config]["rank"], "beta": 50.0, "eps": 0.1},
+            "config": config_block(args, args.config),
+            "run_details": {"arm": "oracle port of the reference's PyTorch path on the host cores (fp32, gradient checkpointing "
+                                   "on as the reference ships it)", "pairs_per_step_sample": pairs},
             "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "loss": round(res, 6)}
@@ -634,9 +902,8 @@ def main():
     ap.add_argument("--no-fused-geglu", dest="fused_geglu", action="store_false", default=True,
                     help="leave the feed-forward's GEGLU on the stock torch kernels")
     ap.add_argument("--tiny", action="store_true", help="debug: the 32/64-channel fixture instead of the SDXL architecture")
-    ap.add_argument("--ncu-traffic", type=float, default=311483648.0,
-                    help="dram__bytes_read.sum + dram__bytes_write.sum per launch of the loss kernel, from the committed "
-                         "ncu --set full capture profiles/r01_pair_loss_tmem_ncu_raw.txt (268.56 MB + 42.92 MB)")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager-on-this-GPU baseline")
+    ap.add_argument("--no-turbo64", action="store_true", help="skip the short configs[1] block after the main timing")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

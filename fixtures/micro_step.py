@@ -83,7 +83,7 @@ def batched_view(batch):
 
 
 def product_micro_step_batched(pso, lora, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0, ref_stream=None,
-                               kind="turbo"):
+                               kind="turbo", return_stats=False):
     """Same micro-step with ONE policy forward and ONE frozen-reference forward of batch 2B (``batched_view``).
     With ``ref_stream`` the no-grad reference forward is issued on a second CUDA stream: it is independent of the policy
     forward, and most kernels of a batch-8 forward leave SMs idle, so the two overlap (inside a captured CUDA graph the
@@ -107,11 +107,13 @@ def product_micro_step_batched(pso, lora, unet, batch, sched, *, beta=50.0, eps=
             ref = unet(batch["input_latents_01"], batch["timesteps_01"], batch["prompt_embeds_01"], added_cond_kwargs=cond).sample
         lora.enable_adapters(unet)
     ts = batch["timesteps"]
-    loss = pso.pso_pair_loss(pol[:B], pol[B:], ref[:B], ref[B:], batch["latents_0"], batch["latents_1"],
-                             batch["next_latents_0"], batch["next_latents_1"], ts, ts, batch["human_prefer"],
-                             scheduler=sched, beta=beta, eps=eps, loss_scale=loss_scale, **_loss_kind(kind))
+    out = pso.pso_pair_loss(pol[:B], pol[B:], ref[:B], ref[B:], batch["latents_0"], batch["latents_1"],
+                            batch["next_latents_0"], batch["next_latents_1"], ts, ts, batch["human_prefer"],
+                            scheduler=sched, beta=beta, eps=eps, loss_scale=loss_scale, return_stats=return_stats,
+                            **_loss_kind(kind))
+    loss = out[0] if return_stats else out
     loss.backward()
-    return loss
+    return out
 
 
 def oracle_micro_step(olora, olosses, unet, batch, sched, *, beta=50.0, eps=0.1, loss_scale=1.0, kind="turbo"):

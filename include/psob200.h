@@ -421,6 +421,12 @@ PSOB200_API int psob200_lora_linear_backward(const psob200_lora_linear_args* arg
  *   g     = grad * grad_scale * coef   (grad_scale folds the 1/world of a summed all-reduce, or 1)
  * operand (may be NULL): 16-bit copy of the updated parameters, same flat layout.  norm_out (may be NULL): float[1].
  * workspace: 16 bytes, 16-byte aligned, zero-initialised once; left zeroed.  step: 1-based optimizer step count.
+ * Overflow handling (fp16 loss scaling: accelerate's GradScaler around T:857-860, mixed_precision="fp16" T:126): grad_scale
+ * is the UNSCALE factor (1 / loss scale, times 1 / world for a summed all-reduce).  When the norm is not finite the whole
+ * update is SKIPPED -- parameters, moments and operand copies untouched, the gradient still zeroed (the trainer calls
+ * zero_grad either way, T:861) -- norm_out receives the non-finite norm and found_inf (may be NULL: float[1]) 1.0f, else
+ * 0.0f.  step_dev (may be NULL: int64[1] on the device, starts at 0): when given, the bias corrections use *step_dev + 1
+ * and the counter advances only for applied updates, so that a skipped step does not age the moments (`step` is then ignored).
  */
 typedef struct psob200_flat_adamw_args {
   float* param;
@@ -438,6 +444,8 @@ typedef struct psob200_flat_adamw_args {
    * address) by psob200_flat_allreduce_sumsq -- the norm launch is skipped; the pieces are left zeroed. */
   int32_t n_sumsq_parts;
   double* sumsq_parts;
+  float* found_inf;
+  long long* step_dev;
 } psob200_flat_adamw_args;
 
 PSOB200_API int psob200_flat_adamw_step(const psob200_flat_adamw_args* args, void* stream);

@@ -94,7 +94,8 @@ class FlatAdamwArgs(C.Structure):
     _fields_ = [("param", _fp), ("grad", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("operand", _vp), ("norm_out", _fp),
                 ("workspace", _vp), ("n", C.c_int64), ("step", C.c_int64), ("lr", C.c_float), ("beta1", C.c_float),
                 ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float), ("max_grad_norm", C.c_float),
-                ("grad_scale", C.c_float), ("operand_dtype", C.c_int32), ("n_sumsq_parts", C.c_int32), ("sumsq_parts", _vp)]
+                ("grad_scale", C.c_float), ("operand_dtype", C.c_int32), ("n_sumsq_parts", C.c_int32), ("sumsq_parts", _vp),
+                ("found_inf", _fp), ("step_dev", _vp)]
 
 
 class FlatAllreduceArgs(C.Structure):
@@ -196,6 +197,31 @@ def require_cuda(*tensors: torch.Tensor) -> torch.device:
         elif t.device != dev:
             raise Psob200Error(f"tensors on different devices: {dev} and {t.device}")
     return dev
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(device: torch.device):
+    """Context for a C-ABI call: the library launches on the calling thread's CURRENT device (and keys its per-device
+    caches by it), so a call on tensors of another device must switch first.  Free when the device is already current."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    return _NO_GUARD if idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+
+def launch(device: torch.device, name: str, *args) -> None:
+    """One C-ABI call on ``device`` (made current for the call if it is not), raising on a non-zero return code."""
+    with on_device(device):
+        rc = getattr(lib(), name)(*args)
+    check(rc, name)
 
 
 def current_stream(device: torch.device) -> int:

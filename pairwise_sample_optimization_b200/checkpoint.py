@@ -22,6 +22,7 @@ import torch
 from .lora import LoRALinear
 
 WEIGHT_NAME = "pytorch_lora_weights.safetensors"
+OPTIMIZER_NAME = "optimizer.safetensors"  # accelerate writes optimizer.bin next to the model files (save_state, turbo :889)
 _TARGETS = ("to_q", "to_k", "to_v", "to_out.0")
 
 
@@ -91,3 +92,50 @@ def load_lora_weights(path: str, unet: torch.nn.Module, strict: bool = True) -> 
         raise KeyError(f"missing keys: {missing[:4]}{'...' if len(missing) > 4 else ''}; "
                        f"unexpected keys: {list(sd)[:4]}{'...' if len(sd) > 4 else ''}")
     return loaded
+
+
+# ----------------------------------------------------------------------------------------------- optimizer state
+def save_optimizer_state(save_directory: str, optimizer, name: str = OPTIMIZER_NAME) -> str:
+    """The resumable part of ``accelerator.save_state`` (turbo :886-889) for ``lora.FusedLoRAOptimizer``: fp32 master
+    parameters, both AdamW moments, the count of applied updates and the hyper-parameters, in one safetensors file."""
+    import json
+    from safetensors.torch import save_file
+    os.makedirs(save_directory, exist_ok=True)
+    sd = optimizer.state_dict()
+    tensors = {k: sd[k].to("cpu").contiguous() for k in ("flat_param", "exp_avg", "exp_avg_sq")}
+    meta = {"format": "pt", "step": str(sd["step"]), "step_calls": str(sd["step_calls"]), "hyper": json.dumps(sd["hyper"]),
+            "layout": json.dumps(sd["layout"])}
+    path = os.path.join(save_directory, name)
+    save_file(tensors, path, metadata=meta)
+    return path
+
+
+def load_optimizer_state(path: str, optimizer, load_hyper: bool = True) -> None:
+    """Inverse of ``save_optimizer_state`` (``accelerator.load_state`` through the hook registered at turbo :398): restores moments, step count and the
+    master parameters (hence the adapters and their 16-bit operand copies)."""
+    import json
+    from safetensors import safe_open
+    if os.path.isdir(path):
+        path = os.path.join(path, OPTIMIZER_NAME)
+    with safe_open(path, framework="pt", device="cpu") as f:
+        meta = f.metadata()
+        sd = {k: f.get_tensor(k) for k in ("flat_param", "exp_avg", "exp_avg_sq")}
+    sd["step"], sd["step_calls"] = int(meta["step"]), int(meta["step_calls"])
+    sd["hyper"], sd["layout"] = json.loads(meta["hyper"]), json.loads(meta["layout"])
+    optimizer.load_state_dict(sd, load_hyper=load_hyper)
+
+
+def save_state(save_directory: str, unet: torch.nn.Module, optimizer=None) -> None:
+    """``accelerator.save_state(dir)`` as the trainers use it (turbo :886-889): adapters in the diffusers wire format (the
+    save hook, :361-379) and, next to them, the optimizer state."""
+    save_lora_weights(save_directory, unet)
+    if optimizer is not None:
+        save_optimizer_state(save_directory, optimizer)
+
+
+def load_state(save_directory: str, unet: torch.nn.Module, optimizer=None) -> None:
+    """``accelerator.load_state(dir)``.  With an optimizer its fp32 master parameters win (they ARE the adapters); without,
+    only the adapter file is read."""
+    load_lora_weights(save_directory, unet)
+    if optimizer is not None:
+        load_optimizer_state(save_directory, optimizer)

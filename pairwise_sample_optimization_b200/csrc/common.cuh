@@ -9,9 +9,31 @@
 
 #include "../../include/psob200.h"
 
+#include <atomic>
+
 namespace cg = cooperative_groups;
 
 namespace psob200 {
+
+// ---------------------------------------------------------------------------------------------
+// Host-side caches of per-DEVICE facts (SM count, occupancy, "MaxDynamicSharedMemorySize already raised for this kernel"):
+// keyed by the ordinal of the calling thread's current device -- the device the launch goes to -- so that a process which
+// drives several GPUs configures every kernel on each of them (cudaFuncSetAttribute is per device).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) {
+    cudaGetLastError();
+    d = 0;
+  }
+  return (d >= 0 && d < kMaxDevices) ? d : kMaxDevices - 1;
+}
+template <typename T>
+struct PerDevice {  // static storage: zero-initialised
+  std::atomic<T> v[kMaxDevices];
+  std::atomic<T>& here() { return v[device_slot()]; }
+};
 
 // ---------------------------------------------------------------------------------------------
 // 8-element (one "chunk") vector access.  bf16/fp16: one 128-bit transaction; fp32: two.

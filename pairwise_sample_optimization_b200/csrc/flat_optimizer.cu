@@ -82,6 +82,8 @@ flat_allreduce_sumsq_kernel(float* mc, double* mc_sumsq_slot, long long lo, long
 
 struct AdamParams {
   float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, max_norm, grad_scale;
+  float* found_inf;
+  long long* step_dev;
 };
 
 template <typename TO>
@@ -92,20 +94,33 @@ flat_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restric
   double sumsq = ws[0];
   for (int r = 0; r < n_parts; ++r) sumsq += parts[r];  // per-rank slices of the fused exchange (same order on every rank)
   const float norm = (float)sqrt(sumsq) * a.grad_scale;
+  // a non-finite norm (overflowed fp16 gradients, or a NaN anywhere: fminf would silently drop it) skips the whole update,
+  // as GradScaler.step does; torch's clip_grad_norm_ would instead smear the NaN over every parameter
+  const bool skip = !(norm <= 3.4028234e38f);
   const float coef = a.max_norm > 0.f ? fminf(1.f, a.max_norm / (norm + 1e-6f)) * a.grad_scale : a.grad_scale;
+  float bc1 = a.bc1, bc2_sqrt = a.bc2_sqrt;
+  if (a.step_dev != nullptr) {  // device-side step count: read by every thread before the last block advances it
+    const double t = (double)(*a.step_dev + 1);
+    bc1 = (float)(1.0 - pow((double)a.beta1, t));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)a.beta2, t));
+  }
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float gi = g[i] * coef;
-    float pi = p[i] * (1.f - a.lr * a.weight_decay);          // decoupled weight decay
-    const float mi = fmaf(1.f - a.beta1, gi - m[i], m[i]);    // exp_avg.lerp_(g, 1 - beta1)
-    const float vi = fmaf(a.beta2, v[i], (1.f - a.beta2) * gi * gi);
-    const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
-    pi -= (a.lr / a.bc1) * (mi / denom);
-    p[i] = pi;
-    m[i] = mi;
-    v[i] = vi;
-    g[i] = 0.f;                                               // optimizer.zero_grad()
-    if (op != nullptr) Vec8<TO>::store1(op + i, pi);          // the GEMM kernels' 16-bit operand copy
+  if (skip) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) g[i] = 0.f;
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float gi = g[i] * coef;
+      float pi = p[i] * (1.f - a.lr * a.weight_decay);          // decoupled weight decay
+      const float mi = fmaf(1.f - a.beta1, gi - m[i], m[i]);    // exp_avg.lerp_(g, 1 - beta1)
+      const float vi = fmaf(a.beta2, v[i], (1.f - a.beta2) * gi * gi);
+      const float denom = sqrtf(vi) / bc2_sqrt + a.eps;
+      pi -= (a.lr / bc1) * (mi / denom);
+      p[i] = pi;
+      m[i] = mi;
+      v[i] = vi;
+      g[i] = 0.f;                                               // optimizer.zero_grad()
+      if (op != nullptr) Vec8<TO>::store1(op + i, pi);          // the GEMM kernels' 16-bit operand copy
+    }
   }
   // the last block to finish publishes the norm and leaves the workspace zeroed for the next boundary
   __shared__ unsigned ticket;
@@ -117,6 +132,8 @@ flat_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restric
   __syncthreads();
   if (ticket == gridDim.x - 1 && threadIdx.x == 0) {
     if (norm_out != nullptr) *norm_out = norm;
+    if (a.found_inf != nullptr) *a.found_inf = skip ? 1.f : 0.f;
+    if (a.step_dev != nullptr && !skip) *a.step_dev += 1;  // every block has read it: this is the last one to finish
     ws[0] = 0.0;
     *reinterpret_cast<unsigned*>(ws + 1) = 0u;
     for (int r = 0; r < n_parts; ++r) parts[r] = 0.0;  // local copy only: peers zero theirs; next use is behind a barrier
@@ -130,12 +147,13 @@ using namespace psob200;
 extern "C" int psob200_flat_adamw_step(const psob200_flat_adamw_args* args, void* stream) {
   if (args == nullptr) return PSOB200_ERR_INVALID_ARG;
   const psob200_flat_adamw_args& o = *args;
-  if (!o.param || !o.grad || !o.exp_avg || !o.exp_avg_sq || !o.workspace || o.n <= 0 || o.step <= 0)
+  if (!o.param || !o.grad || !o.exp_avg || !o.exp_avg_sq || !o.workspace || o.n <= 0 || (o.step <= 0 && !o.step_dev))
     return PSOB200_ERR_INVALID_ARG;
   if (o.operand && o.operand_dtype != PSOB200_BF16 && o.operand_dtype != PSOB200_F16) return PSOB200_ERR_DTYPE;
   if (!aligned16(o.grad) || !aligned16(o.workspace)) return PSOB200_ERR_ALIGNMENT;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static std::atomic<int> sms{0};
+  static PerDevice<int> sms_dev;
+  std::atomic<int>& sms = sms_dev.here();
   int n_sm = sms.load(std::memory_order_relaxed);
   if (n_sm <= 0) {
     n_sm = psob200_device_sm_count();
@@ -157,6 +175,8 @@ extern "C" int psob200_flat_adamw_step(const psob200_flat_adamw_args* args, void
   a.bc2_sqrt = (float)std::sqrt(1.0 - std::pow((double)o.beta2, (double)o.step));
   a.max_norm = o.max_grad_norm;
   a.grad_scale = o.grad_scale;
+  a.found_inf = o.found_inf;
+  a.step_dev = o.step_dev;
   blocks = (o.n + kOptThreads - 1) / kOptThreads;
   if (blocks > n_sm * 8) blocks = n_sm * 8;
   if (o.operand == nullptr || o.operand_dtype == PSOB200_BF16)

@@ -182,7 +182,8 @@ static dim3 geglu_grid(const psob200_geglu_args& a, Kernel kernel) {
   const long long bx = (a.I + kGegluColThreads * 8 - 1) / (kGegluColThreads * 8);
   int sms = psob200_device_sm_count();
   if (sms <= 0) sms = 148;
-  static std::atomic<int> cached{0};  // per kernel instantiation (this function is a template): queried once
+  static PerDevice<int> cached_dev;  // per kernel instantiation (this function is a template) and device: queried once
+  std::atomic<int>& cached = cached_dev.here();
   int per_sm = cached.load(std::memory_order_relaxed);
   if (per_sm <= 0) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGegluThreads, 0) != cudaSuccess || per_sm <= 0) {

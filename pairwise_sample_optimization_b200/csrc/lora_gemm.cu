@@ -411,7 +411,8 @@ static int make_map(CUtensorMap* map, const void* ptr, long long rows, long long
 }
 
 static int gemm_sm_count() {
-  static std::atomic<int> cached{0};
+  static PerDevice<int> per_device;
+  std::atomic<int>& cached = per_device.here();
   int v = cached.load(std::memory_order_relaxed);
   if (v > 0) return v;
   int dev = 0, n = 0;
@@ -529,11 +530,12 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
           lora_gemm2_kernel<__half, kEpiD | kEpiBias>,
           lora_gemm2_kernel<__nv_bfloat16, kEpiD | kEpiBiasSameType>, lora_gemm2_kernel<__nv_bfloat16, kEpiD>,
           lora_gemm2_kernel<__half, kEpiD | kEpiBiasSameType>, lora_gemm2_kernel<__half, kEpiD>};
-      static std::atomic<bool> configured2[7];
-      if (!configured2[variant].load(std::memory_order_acquire)) {
+      static PerDevice<bool> configured2_dev[7];
+      std::atomic<bool>& conf2 = configured2_dev[variant].here();
+      if (!conf2.load(std::memory_order_acquire)) {
         const cudaError_t e = cudaFuncSetAttribute(kernels2[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm2SmemBytes);
         if (e != cudaSuccess) return consume_launch_error("configure lora_gemm2_kernel", e);
-        configured2[variant].store(true, std::memory_order_release);
+        conf2.store(true, std::memory_order_release);
       }
       const long long max_pairs = sms / 2;
       const unsigned grid = 2u * (unsigned)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
@@ -628,11 +630,12 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
       lora_gemm_kernel<__nv_bfloat16, false, kEpiD>, lora_gemm_kernel<__nv_bfloat16, false, kEpiAnyOut>,
       lora_gemm_kernel<__half, false, kEpiGeneral>, lora_gemm_kernel<__half, false, kEpiD | kEpiBiasSameType>,
       lora_gemm_kernel<__half, false, kEpiD>, lora_gemm_kernel<__half, false, kEpiAnyOut>};
-  static std::atomic<bool> configured[12];
-  if (!configured[variant].load(std::memory_order_acquire)) {
+  static PerDevice<bool> configured_dev[12];
+  std::atomic<bool>& conf1 = configured_dev[variant].here();
+  if (!conf1.load(std::memory_order_acquire)) {
     const cudaError_t e = cudaFuncSetAttribute(kernels[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
     if (e != cudaSuccess) return consume_launch_error("configure lora_gemm_kernel", e);
-    configured[variant].store(true, std::memory_order_release);
+    conf1.store(true, std::memory_order_release);
   }
   const long long total = (long long)p.m_tiles * p.n_tiles * p.splits;
   const unsigned grid = (unsigned)(total < sms ? total : sms);

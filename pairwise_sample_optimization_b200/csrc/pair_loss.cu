@@ -322,8 +322,9 @@ __global__ void __launch_bounds__(kMaxThreads) pair_loss_grad_kernel(const PairK
 
 // ----------------------------------------------------------------------------------------------
 template <typename K>
-static int ensure_dynamic_smem(K kern, size_t smem, std::atomic<size_t>& configured, const char* what) {
-  if (smem <= configured.load(std::memory_order_acquire)) return PSOB200_OK;
+static int ensure_dynamic_smem(K kern, size_t smem, PerDevice<size_t>& per_device, const char* what) {
+  std::atomic<size_t>& configured = per_device.here();  // 0 = untouched on this device: the 48 KB default applies
+  if (smem <= 48 * 1024 || smem <= configured.load(std::memory_order_acquire)) return PSOB200_OK;
   cudaFuncAttributes fa;
   cudaError_t e = cudaFuncGetAttributes(&fa, kern);
   if (e != cudaSuccess) return consume_launch_error(what, e);
@@ -338,7 +339,7 @@ static int ensure_dynamic_smem(K kern, size_t smem, std::atomic<size_t>& configu
 template <typename TP, typename TL, bool HAS_REF, int W>
 static int launch_pair_inst(const PairKernelArgs& ka, int threads, int cluster, size_t smem, cudaStream_t stream) {
   auto kern = pair_loss_grad_kernel<TP, TL, HAS_REF, W>;
-  static std::atomic<size_t> configured{48 * 1024};
+  static PerDevice<size_t> configured;
   const int rc = ensure_dynamic_smem(kern, smem, configured, "configure pair_loss_grad_kernel");
   if (rc != PSOB200_OK) return rc;
   const cudaError_t e = launch_cluster(kern, dim3((unsigned)(ka.B * cluster)), dim3(threads), smem, stream,
@@ -349,9 +350,10 @@ static int launch_pair_inst(const PairKernelArgs& ka, int threads, int cluster, 
 // Clusters of `cluster` CTAs that can be co-resident for this kernel (cached per instantiation and cluster size).
 template <typename K>
 static int max_active_clusters(K kern, int threads, size_t smem, int cluster, int sm_count, int ctas_per_sm,
-                               std::atomic<int>* cache) {
+                               PerDevice<int>* per_device) {
   int idx = cluster == 1 ? 0 : cluster == 2 ? 1 : cluster == 4 ? 2 : 3;
-  int v = cache[idx].load(std::memory_order_relaxed);
+  std::atomic<int>& slot = per_device[idx].here();
+  int v = slot.load(std::memory_order_relaxed);
   if (v > 0) return v;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(sm_count * ctas_per_sm / cluster * cluster));
@@ -369,7 +371,7 @@ static int max_active_clusters(K kern, int threads, size_t smem, int cluster, in
     cudaGetLastError();
     n = sm_count * ctas_per_sm / cluster;  // optimistic fallback: the grid is still correct, only less balanced
   }
-  cache[idx].store(n, std::memory_order_relaxed);
+  slot.store(n, std::memory_order_relaxed);
   return n;
 }
 
@@ -378,8 +380,8 @@ static int launch_pair_tma_inst(const PairKernelArgs& ka, int cluster, int sm_co
   auto kern = pair_loss_grad_tma_kernel<TP, TL, HAS_REF>;
   using Cfg = TmaCfg<TP, TL, HAS_REF>;
   constexpr size_t smem = Cfg::kSmemBytes;
-  static std::atomic<size_t> configured{48 * 1024};
-  static std::atomic<int> active[4];
+  static PerDevice<size_t> configured;
+  static PerDevice<int> active[4];
   const int rc = ensure_dynamic_smem(kern, smem, configured, "configure pair_loss_grad_tma_kernel");
   if (rc != PSOB200_OK) return rc;
   long long clusters = max_active_clusters(kern, kTmaThreads, smem, cluster, sm_count, 1, active);
@@ -394,8 +396,8 @@ static int launch_pair_tmem_inst(const PairKernelArgs& ka, int cluster, int sm_c
   auto kern = pair_loss_grad_tmem_kernel<TP, TL, HAS_REF>;
   using Cfg = V3Cfg<TP, TL, HAS_REF>;
   constexpr size_t smem = Cfg::kSmemBytes;
-  static std::atomic<size_t> configured{48 * 1024};
-  static std::atomic<int> active[4];
+  static PerDevice<size_t> configured;
+  static PerDevice<int> active[4];
   const int rc = ensure_dynamic_smem(kern, smem, configured, "configure pair_loss_grad_tmem_kernel");
   if (rc != PSOB200_OK) return rc;
   long long clusters = max_active_clusters(kern, Cfg::kThreads, smem, cluster, sm_count, 1, active);
@@ -496,7 +498,8 @@ static int launch_pair(PairKernelArgs ka, bool has_ref, int32_t pred_dtype, int3
 }
 
 static int cached_sm_count() {
-  static std::atomic<int> cached{0};
+  static PerDevice<int> per_device;
+  std::atomic<int>& cached = per_device.here();
   int v = cached.load(std::memory_order_relaxed);
   if (v > 0) return v;
   int dev = 0, n = 0;

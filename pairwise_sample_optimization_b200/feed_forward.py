@@ -34,7 +34,7 @@ class _GegluFn(torch.autograd.Function):
         a = _lib.GegluArgs()
         a.proj, a.out, a.M, a.I = p2.data_ptr(), out.data_ptr(), p2.shape[0], inner
         a.ld_proj, a.ld_out, a.dtype = p2.stride(0), inner, _lib.dtype_code(p2)
-        _lib.check(_lib.lib().psob200_geglu_forward(C.byref(a), _lib.current_stream(dev)), "psob200_geglu_forward")
+        _lib.launch(dev, "psob200_geglu_forward", C.byref(a), _lib.current_stream(dev))
         ctx.save_for_backward(p2)
         ctx.shape = proj.shape
         return out.view(*proj.shape[:-1], inner)
@@ -52,7 +52,7 @@ class _GegluFn(torch.autograd.Function):
         a = _lib.GegluArgs()
         a.proj, a.dout, a.dproj, a.M, a.I = p2.data_ptr(), d2.data_ptr(), dproj.data_ptr(), p2.shape[0], inner
         a.ld_proj, a.ld_dout, a.ld_dproj, a.dtype = p2.stride(0), d2.stride(0), 2 * inner, _lib.dtype_code(p2)
-        _lib.check(_lib.lib().psob200_geglu_backward(C.byref(a), _lib.current_stream(p2.device)), "psob200_geglu_backward")
+        _lib.launch(p2.device, "psob200_geglu_backward", C.byref(a), _lib.current_stream(p2.device))
         return dproj.view(ctx.shape)
 
 

@@ -87,7 +87,6 @@ def lora_gemm(a1, b1, a2=None, b2=None, *, bias=None, alpha: float = 1.0, out=No
     g.a_reduction_major = int(a_reduction_major)
     g.accumulate = int(accumulate)
     g.split_k, g.tune_bn, g.diag, g.pdl = int(split_k), int(tune_bn), int(diag), int(pdl)
-    rc = _lib.lib().psob200_lora_gemm(C.byref(g), _lib.current_stream(dev))
-    _lib.check(rc, "psob200_lora_gemm")
+    _lib.launch(dev, "psob200_lora_gemm", C.byref(g), _lib.current_stream(dev))
     del keep
     return out, out_t

@@ -89,12 +89,14 @@ def _arm_wgrad_join(dev: torch.device) -> None:
     torch.autograd.Variable._execution_engine.queue_callback(join)
 
 
-def _timed_launch(fn, what: str, role: str, flops: float, nbytes: float, shape) -> None:
+def _timed_launch(dev, fn, what: str, role: str, flops: float, nbytes: float, shape) -> None:
     """Instrumented pass: ONE kernel launch between two events; appends (ev0, ev1, flops, algorithmic bytes, role, shape)."""
     # external: inside a CUDA-graph capture the records become event-record nodes (timestamps of the last replay)
     ev0, ev1 = torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True)
     ev0.record()
-    _lib.check(fn(), what)
+    with _lib.on_device(dev):
+        rc = fn()
+    _lib.check(rc, what)
     ev1.record()
     _TIMING.append((ev0, ev1, flops, nbytes, role, shape))
 
@@ -230,8 +232,7 @@ class _LoraLinearFn(torch.autograd.Function):
                 tt = torch.empty(r, _ceil8(M), dtype=dtype, device=dev)
                 a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
         if _TIMING is None:
-            rc = _lib.lib().psob200_lora_linear_forward(C.byref(a), _lib.current_stream(dev))
-            _lib.check(rc, "psob200_lora_linear_forward")
+            _lib.launch(dev, "psob200_lora_linear_forward", C.byref(a), _lib.current_stream(dev))
         else:  # instrumented pass: the same launches one by one, each between its own pair of events
             eb = 2  # bytes per 16-bit element
             roles = [(1, "t = s x A^T", 2.0 * M * r * K, eb * (M * K + r * K + M * r * (2 if tt is not None else 1)))] if enabled else []
@@ -239,7 +240,7 @@ class _LoraLinearFn(torch.autograd.Function):
                           2.0 * M * N * (K + (r if enabled else 0)), eb * (M * K + N * K + M * N + ((M + N) * r if enabled else 0))))
             for mask, role, fl, by in roles:
                 a.forward_phases = mask
-                _timed_launch(lambda: _lib.lib().psob200_lora_linear_forward(C.byref(a), _lib.current_stream(dev)),
+                _timed_launch(dev, lambda: _lib.lib().psob200_lora_linear_forward(C.byref(a), _lib.current_stream(dev)),
                               "psob200_lora_linear_forward", role, fl, by, (M, K, N, r))
         ctx.layer, ctx.enabled, ctx.x_shape, ctx.x_dtype, ctx.want_wgrad = layer, enabled, x.shape, x.dtype, want_wgrad
         ctx.save_for_backward(x2, tt)
@@ -303,19 +304,17 @@ class _LoraLinearFn(torch.autograd.Function):
                     roles.append((8, "dB += dy^T t", 2.0 * M * N * r, eb * (M * N + M * r) + 4 * N * r))
                 for mask, role, fl, by in roles:
                     a.backward_phases = mask
-                    _timed_launch(lambda: _lib.lib().psob200_lora_linear_backward(C.byref(a), _lib.current_stream(dev)),
+                    _timed_launch(dev, lambda: _lib.lib().psob200_lora_linear_backward(C.byref(a), _lib.current_stream(dev)),
                                   "psob200_lora_linear_backward", role, fl, by, (M, K, N, r))
             else:
                 if side:
                     a.backward_phases = 3  # PSOB200_BWD_INPUT_GRAD: u (+ ut), dx
-                rc = _lib.lib().psob200_lora_linear_backward(C.byref(a), _lib.current_stream(dev))
-                _lib.check(rc, "psob200_lora_linear_backward")
+                _lib.launch(dev, "psob200_lora_linear_backward", C.byref(a), _lib.current_stream(dev))
             if side:
                 st = _wgrad_side_stream(dev)
                 st.wait_stream(torch.cuda.current_stream(dev))
                 a.backward_phases = 12  # PSOB200_BWD_WEIGHT_GRAD: dA, dB
-                rc = _lib.lib().psob200_lora_linear_backward(C.byref(a), st.cuda_stream)
-                _lib.check(rc, "psob200_lora_linear_backward")
+                _lib.launch(dev, "psob200_lora_linear_backward", C.byref(a), st.cuda_stream)
                 _WGRAD_SIDE["pending"].setdefault(dev, []).append((x2, tt, dy2, keep))  # alive until the join
                 keep = []
                 _arm_wgrad_join(dev)
@@ -330,10 +329,21 @@ class _LoraLinearFn(torch.autograd.Function):
 def _grad_buffer(p: torch.nn.Parameter) -> torch.Tensor:
     """fp32 accumulation target of a LoRA parameter: ``p.grad`` itself for fp32 parameters (a view of the flat
     bucket once ``LoRAGradBucket`` is attached), else a side buffer ``p.grad32`` folded in by ``finalize_grads``."""
+    view = getattr(p, "_psob200_grad_view", None)  # set by LoRAGradBucket: this parameter's slice of the flat buffer
     if p.dtype == torch.float32:
+        if view is not None:
+            if p.grad is None:  # zero_grad(set_to_none=True) / `p.grad = None` detached it: the slice is still the target
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                raise _lib.Psob200Error("param.grad was replaced by a tensor that is not this parameter's view of the flat LoRA "
+                                        "gradient bucket: the exchange / clip / optimizer would read stale zeros.  Zero "
+                                        "gradients with LoRAGradBucket.zero_grad() / FusedLoRAOptimizer.zero_grad().")
+            return view
         if p.grad is None:
             p.grad = torch.zeros_like(p)
         return p.grad
+    if view is not None:
+        return view
     g = getattr(p, "grad32", None)
     if g is None:
         g = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
@@ -413,6 +423,7 @@ class LoRAGradBucket:
             self.offsets.append(off)
             off += n
             self.views.append(v)
+            p._psob200_grad_view = v  # _grad_buffer re-attaches it if the trainer sets p.grad = None
             if p.dtype == torch.float32:
                 p.grad = v
             else:
@@ -420,6 +431,15 @@ class LoRAGradBucket:
 
     def zero_(self) -> None:
         self.flat.zero_()
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """``optimizer.zero_grad()`` for the flat bucket: zeroes IN PLACE and keeps every ``param.grad`` a view of the flat
+        buffer (``set_to_none`` is accepted for signature compatibility and ignored: detaching the views would make the
+        exchange and the optimizer read zeros)."""
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            if p.dtype == torch.float32:
+                p.grad = v
 
     def all_reduce(self, group=None, async_op: bool = False):
         """Average the flat gradient over the data-parallel ranks with ONE collective."""
@@ -494,8 +514,7 @@ class SymmetricGradExchange:
         a.sumsq_multicast = self.handle.multicast_ptr + 4 * self.n
         a.n, a.rank, a.world, a.scale = self.n, self.rank, self.world, 1.0 / self.world
         self.handle.barrier(channel=0)  # every rank's backward has finished accumulating into its copy
-        rc = _lib.lib().psob200_flat_allreduce_sumsq(C.byref(a), _lib.current_stream(dev))
-        _lib.check(rc, "psob200_flat_allreduce_sumsq")
+        _lib.launch(dev, "psob200_flat_allreduce_sumsq", C.byref(a), _lib.current_stream(dev))
         self.handle.barrier(channel=1)  # every slice (and every norm slot) has landed everywhere
 
 
@@ -525,8 +544,13 @@ class FusedLoRAOptimizer:
         self.flat_operand = torch.zeros(flat.numel(), dtype=op_dtype, device=flat.device)
         self.workspace = torch.zeros(2, dtype=torch.float64, device=flat.device)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=flat.device)
+        # fp16 loss scaling (accelerate's GradScaler, turbo :126 / :857-860): `grad_scale` is the unscale factor of the next
+        # step(); a non-finite norm skips the update on the device, sets `found_inf` and does not advance `step_dev`
+        self.found_inf = torch.zeros(1, dtype=torch.float32, device=flat.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=flat.device)  # applied updates (bias correction)
+        self.grad_scale = 1.0
         self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
-        self.step_count = 0
+        self.step_count = 0  # step() calls (host side, no sync); applied updates are counted in `step_dev`
         self._unbacked = []  # adapter matrices whose operand copy needs a padded pitch (rank not a multiple of 8)
         by_param = {}
         for lay in self.layers:
@@ -564,18 +588,59 @@ class FusedLoRAOptimizer:
         a.norm_out, a.workspace = self.grad_norm.data_ptr(), self.workspace.data_ptr()
         a.n, a.step = self.flat_param.numel(), self.step_count
         a.lr, a.beta1, a.beta2, a.eps = self.lr, self.betas[0], self.betas[1], self.eps
-        a.weight_decay, a.max_grad_norm, a.grad_scale = self.weight_decay, self.max_grad_norm, 1.0
+        a.weight_decay, a.max_grad_norm, a.grad_scale = self.weight_decay, self.max_grad_norm, float(self.grad_scale)
+        a.found_inf, a.step_dev = self.found_inf.data_ptr(), self.step_dev.data_ptr()
         if self._parts_ready:  # the fused exchange already produced the sum of squares, one piece per rank
             a.n_sumsq_parts, a.sumsq_parts = self.exchange.world, self.exchange.sumsq_parts_ptr
             self._parts_ready = False
-        rc = _lib.lib().psob200_flat_adamw_step(C.byref(a), _lib.current_stream(self.flat_param.device))
-        _lib.check(rc, "psob200_flat_adamw_step")
+        _lib.launch(self.flat_param.device, "psob200_flat_adamw_step", C.byref(a), _lib.current_stream(self.flat_param.device))
+        self._refresh_unbacked()
+        return self.grad_norm
+
+    def _refresh_unbacked(self) -> None:
         for lay, which, dt in self._unbacked:  # padded-pitch copies: re-made in place by the layer itself
             hit = lay._op_cache.get((which, dt))
             if hit is not None:
                 hit[0] = -1
             lay._operand(which, dt)
-        return self.grad_norm
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """In-place zero of the flat gradient (``step()`` already leaves it zeroed); ``param.grad`` stays a bucket view."""
+        self.bucket.zero_grad(set_to_none)
+
+    # ---- checkpoint / resume (accelerator.save_state / load_state, turbo :889: the AdamW moments and step count travel too)
+    def state_dict(self) -> dict:
+        """Everything a resumed run needs for bit-identical continuation: the fp32 master parameters, both Adam moments,
+        the count of applied updates (one host sync) and the hyper-parameters.  Tensors are clones on the optimizer's device."""
+        return {"flat_param": self.flat_param.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "step": int(self.step_dev.item()), "step_calls": int(self.step_count),
+                "hyper": {"lr": self.lr, "beta1": self.betas[0], "beta2": self.betas[1], "eps": self.eps,
+                          "weight_decay": self.weight_decay, "max_grad_norm": self.max_grad_norm},
+                "layout": {"numel": int(self.flat_param.numel()), "offsets": [int(o) for o in self.bucket.offsets],
+                           "shapes": [list(p.shape) for p in self.bucket.params]}}
+
+    def load_state_dict(self, sd: dict, load_hyper: bool = True) -> None:
+        """Inverse of ``state_dict()``.  The parameters live in ``flat_param`` (every adapter ``weight`` is a view of it), so
+        loading also restores the adapters; the 16-bit operand copies the GEMM kernels read are refreshed; the gradient is zeroed."""
+        lay = sd["layout"]
+        if lay["numel"] != self.flat_param.numel() or list(lay["offsets"]) != [int(o) for o in self.bucket.offsets] or \
+                [list(x) for x in lay["shapes"]] != [list(p.shape) for p in self.bucket.params]:
+            raise _lib.Psob200Error("optimizer state was saved for a different adapter layout (rank / target modules differ)")
+        dev = self.flat_param.device
+        with torch.no_grad():
+            self.flat_param.copy_(sd["flat_param"].to(dev))
+            self.exp_avg.copy_(sd["exp_avg"].to(dev))
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"].to(dev))
+            self.step_dev.fill_(int(sd["step"]))
+            self.flat_operand.copy_(self.flat_param)  # what psob200_flat_adamw_step would have left
+        self.step_count = int(sd.get("step_calls", sd["step"]))
+        if load_hyper:
+            h = sd["hyper"]
+            self.lr, self.betas, self.eps = h["lr"], (h["beta1"], h["beta2"]), h["eps"]
+            self.weight_decay, self.max_grad_norm = h["weight_decay"], h["max_grad_norm"]
+        self._refresh_unbacked()
+        self.bucket.zero_grad()
+        self._parts_ready = False
 
 
 # ----------------------------------------------------------------------------------------------- attention processor

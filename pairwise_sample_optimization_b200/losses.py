@@ -25,7 +25,8 @@ def sample_compare(a: torch.Tensor, b: torch.Tensor, generator=None) -> torch.Te
     idx = torch.randint(0, num_rewards, (bs,), device=a.device, generator=generator)
     pa = a.gather(1, idx[:, None]).squeeze(1)
     pb = b.gather(1, idx[:, None]).squeeze(1)
-    s = torch.where(pa <= pb, 1.0, -1.0).to(torch.float)
+    # explicit masks like the reference's (a_dom = pa <= pb, b_dom = pb < pa): a NaN reward satisfies neither -> [0, 0]
+    s = (pa <= pb).to(torch.float) - (pb < pa).to(torch.float)
     return torch.stack([-s, s], dim=1)
 
 
@@ -54,9 +55,8 @@ def _apply_upstream(grads, grad_out, dev):
     (a no-op launch when it is exactly 1)."""
     go = grad_out.detach().reshape(1).to(torch.float32)
     for g in grads:
-        rc = _lib.lib().psob200_scale_inplace_by_device_scalar(g.data_ptr(), g.numel(), _lib.dtype_code(g),
+        _lib.launch(dev, "psob200_scale_inplace_by_device_scalar", g.data_ptr(), g.numel(), _lib.dtype_code(g),
                                                                go.data_ptr(), _lib.current_stream(dev))
-        _lib.check(rc, "psob200_scale_inplace_by_device_scalar")
 
 
 class _OnlinePsoLoss(torch.autograd.Function):
@@ -103,8 +103,7 @@ class _OnlinePsoLoss(torch.autograd.Function):
         a.pred_dtype, a.latent_dtype = _lib.dtype_code(pred0), _lib.dtype_code(keep[2])
         a.beta, a.eps, a.loss_scale = float(beta), float(eps), float(loss_scale)
         a.tune_threads, a.tune_cluster = tune
-        rc = _lib.lib().psob200_online_pso_loss_grad(sched.ref(), C.byref(a), _lib.current_stream(dev))
-        _lib.check(rc, "psob200_online_pso_loss_grad")
+        _lib.launch(dev, "psob200_online_pso_loss_grad", sched.ref(), C.byref(a), _lib.current_stream(dev))
         ctx.save_for_backward(grad0, grad1)
         ctx.dev = dev
         ctx.used = False
@@ -198,8 +197,7 @@ class _DreamboothPsoLoss(torch.autograd.Function):
         a.beta_pso, a.neg_defactor = float(beta_pso), float(neg_defactor)
         a.prior_loss_weight, a.loss_scale = float(prior_loss_weight), float(loss_scale)
         a.tune_threads, a.tune_cluster = tune
-        rc = _lib.lib().psob200_dreambooth_pso_loss_grad(C.byref(a), _lib.current_stream(dev))
-        _lib.check(rc, "psob200_dreambooth_pso_loss_grad")
+        _lib.launch(dev, "psob200_dreambooth_pso_loss_grad", C.byref(a), _lib.current_stream(dev))
         del rp, tg, sg
         ctx.save_for_backward(grad)
         ctx.dev = dev

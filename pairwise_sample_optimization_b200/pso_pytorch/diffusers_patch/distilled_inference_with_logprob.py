@@ -19,7 +19,8 @@ def _get_x0_from_noise(sample, model_output, alphas_cumprod, timestep):
     """x0 = (sample - sqrt(1-abar_t) * model_output) / sqrt(abar_t)   (:36-42)."""
     dev = _lib.require_cuda(sample, model_output)
     ts = runtime.timesteps_on(timestep, dev)
-    return step_ops.x0_from_noise(runtime.device_table(alphas_cumprod, dev), model_output, sample, ts)
+    return step_ops.x0_from_noise(runtime.device_table(alphas_cumprod, dev), model_output, sample, ts,
+                                  table_dtype=alphas_cumprod.dtype)
 
 
 def distilled_step_with_logprob(self, model_output, timestep, prev_timestep, sample, eta: float = 0.0,

@@ -85,7 +85,8 @@ def sdxl_dmd_pipeline_with_logprob(
                 all_log_probs.append(log_prob)
             else:                                                                                              # :154-162
                 x0_pred = step_ops.x0_from_noise(runtime.device_table(noise_scheduler.alphas_cumprod, dev),
-                                                 noise_pred, latents, ts)
+                                                 noise_pred, latents, ts,
+                                                 table_dtype=noise_scheduler.alphas_cumprod.dtype)  # fp32 like DS:36-42
                 all_latents.append(x0_pred)
 
         if not output_type == "latent":

@@ -69,8 +69,7 @@ def step_forward(sched: runtime.ScheduleDesc, model_output, sample, ts, ts_prev=
             scaled = torch.empty_like(prev_out)
             args.scaled_next_out = scaled.data_ptr()
     args.tune_threads, args.tune_cluster = tune
-    rc = _lib.lib().psob200_step_logprob(sched.ref(), C.byref(args), _lib.current_stream(dev))
-    _lib.check(rc, "psob200_step_logprob")
+    _lib.launch(dev, "psob200_step_logprob", sched.ref(), C.byref(args), _lib.current_stream(dev))
     del keep
     return log_prob, prev_out, scaled
 
@@ -90,8 +89,7 @@ def step_backward(sched: runtime.ScheduleDesc, model_output, sample, prev_sample
     grad = torch.empty(model_output.shape, dtype=model_output.dtype, device=dev)
     args.grad_model_output = grad.data_ptr()
     args.status = runtime.status_word(dev).data_ptr()
-    rc = _lib.lib().psob200_step_logprob_backward(sched.ref(), C.byref(args), _lib.current_stream(dev))
-    _lib.check(rc, "psob200_step_logprob_backward")
+    _lib.launch(dev, "psob200_step_logprob_backward", sched.ref(), C.byref(args), _lib.current_stream(dev))
     del keep, ps, glp
     return grad
 
@@ -114,19 +112,21 @@ class StepLogProb(torch.autograd.Function):
         return grad, None, None, None, None, None, None
 
 
-def x0_from_noise(alphas_cumprod_dev, model_output, sample, ts, out_dtype=None):
-    """psob200_dmd_x0_from_noise: distilled_inference_with_logprob.py:36-42."""
+def x0_from_noise(alphas_cumprod_dev, model_output, sample, ts, out_dtype=None, table_dtype=torch.float32):
+    """psob200_dmd_x0_from_noise: distilled_inference_with_logprob.py:36-42.  The result type follows torch's promotion in
+    the reference expression: ``alphas_cumprod[t].reshape(-1,1,1,1)`` is a 4-D tensor, so its dtype (``table_dtype``: fp32
+    for every diffusers scheduler) takes part -- 16-bit latents and predictions still give an fp32 ``x0`` (the final DMD2
+    latent that goes to the VAE, sdxl_dmd_with_logprob.py:158-162)."""
     dev = _lib.require_cuda(model_output, sample)
     n = _sample_numel(model_output)
     mo, sa = model_output.contiguous(), sample.contiguous()
-    out_dtype = out_dtype or torch.promote_types(mo.dtype, sa.dtype)
+    out_dtype = out_dtype or torch.promote_types(torch.promote_types(mo.dtype, sa.dtype), table_dtype)
     out = torch.empty(mo.shape, dtype=out_dtype, device=dev)
-    rc = _lib.lib().psob200_dmd_x0_from_noise(
+    _lib.launch(dev, "psob200_dmd_x0_from_noise",
         alphas_cumprod_dev.data_ptr(), alphas_cumprod_dev.numel(), mo.data_ptr(), sa.data_ptr(), ts.data_ptr(),
         _lib.ts_dtype_code(ts), 1 if ts.numel() == 1 and mo.shape[0] > 1 else mo.shape[0], out.data_ptr(),
         mo.shape[0], n, _lib.dtype_code(mo), _lib.dtype_code(sa), _lib.dtype_code(out),
         runtime.status_word(dev).data_ptr(), _lib.current_stream(dev))
-    _lib.check(rc, "psob200_dmd_x0_from_noise")
     return out
 
 
@@ -135,7 +135,6 @@ def scale(t: torch.Tensor, factor: float, out_dtype=None) -> torch.Tensor:
     dev = _lib.require_cuda(t)
     t = t.contiguous()
     out = torch.empty(t.shape, dtype=out_dtype or t.dtype, device=dev)
-    rc = _lib.lib().psob200_scale(t.data_ptr(), out.data_ptr(), t.numel(), float(factor), _lib.dtype_code(t),
+    _lib.launch(dev, "psob200_scale", t.data_ptr(), out.data_ptr(), t.numel(), float(factor), _lib.dtype_code(t),
                                   _lib.dtype_code(out), _lib.current_stream(dev))
-    _lib.check(rc, "psob200_scale")
     return out

@@ -101,3 +101,8 @@ def test_compare_host_logic_matches_oracle():
     got = pso.sample_compare(a, b, generator=torch.Generator().manual_seed(5))
     idx = torch.randint(0, 3, (64,), generator=torch.Generator().manual_seed(5))
     assert torch.equal(got, losses.sample_compare(a, b, reward_indices=idx))
+    # a NaN reward satisfies neither `a <= b` nor `b < a`: the reference leaves that row [0, 0] (turbo :401-416)
+    a[3], b[7] = float("nan"), float("nan")
+    got = pso.sample_compare(a, b, generator=torch.Generator().manual_seed(5))
+    assert torch.equal(got, losses.sample_compare(a, b, reward_indices=idx))
+    assert got[3].tolist() == [0.0, 0.0] and got[7].tolist() == [0.0, 0.0]

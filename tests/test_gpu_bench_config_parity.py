@@ -1,0 +1,167 @@
+"""Parity of the configuration bench.py actually TIMES: ``product_micro_step_batched`` (win + lose rows in
+one forward of batch 2B) + the frozen-reference forward on a second stream + the dA / dB launches on the weight-gradient side
+stream + the fused GEGLU kernels, captured in ONE CUDA graph and replayed, with the fused optimizer boundary
+(``FusedLoRAOptimizer.step``: clip + AdamW + zero_grad + 16-bit operand refresh) between replays.
+
+1. tiny fixture (BASELINE config 1) against the reference's flow restated on the CPU in fp32 (``oracle_micro_step``: 4
+   forwards, 4 step-with-logprob calls, inline loss, autograd) -- replay 1, optimizer boundary, replay 2 with the UPDATED
+   adapters; same tolerances as test_gpu_unet_step.py.
+2. full SDXL-architecture fixture, one pair of 128x128 latents, rank 64 (the bench's dmd128 shapes): the graph-replayed batched
+   step against the plain eager 4-forward ``product_micro_step`` on the same weights: loss 1e-3 relative, cosine of the flat
+   adapter gradient >= 0.999.
+"""
+import copy
+
+import pytest
+import torch
+
+from fixtures import micro_step, sdxl_unet
+from oracle import lora as olora, losses as olosses, schedules
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods(built_lib):
+    import pairwise_sample_optimization_b200 as pso
+    from pairwise_sample_optimization_b200 import feed_forward, lora
+    return pso, lora, feed_forward
+
+
+def _flat_grads(layers):
+    return torch.cat([torch.cat([m.lora_A["default"].weight.grad.flatten(), m.lora_B["default"].weight.grad.flatten()])
+                      for m in layers]).double().cpu()
+
+
+def _capture(pso, lora, unet, d, sched, ref_stream, **kw):
+    """Exactly bench.py's capture: eager warm-up on a side stream, then ONE micro-step into a CUDA graph."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            micro_step.product_micro_step_batched(pso, lora, unet, d, sched, ref_stream=ref_stream, **kw)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        loss = micro_step.product_micro_step_batched(pso, lora, unet, d, sched, ref_stream=ref_stream, **kw)
+    return graph, loss
+
+
+@pytest.mark.parametrize("kind", ["turbo", "dmd"])
+def test_graph_replayed_bench_configuration_vs_oracle_across_an_optimizer_boundary(mods, kind):
+    pso, lora, feed_forward = mods
+    r, B = 4, 2
+    torch.manual_seed(0)
+    cfg = sdxl_unet.tiny_config()
+    base = sdxl_unet.UNet2DConditionModel(cfg).to(torch.bfloat16)
+    cpu = copy.deepcopy(base).float()
+    gpu = copy.deepcopy(base).cuda()
+    wo = olora.oracle_add_adapter(cpu, r, r)
+    wg = lora.add_adapter(gpu, lora.LoraConfig(r=r, lora_alpha=r))
+    g = torch.Generator().manual_seed(1)
+    for mo, mg in zip(wo, wg):
+        A = (torch.randn(mo.lora_A["default"].weight.shape, generator=g) * (1.0 / r)).bfloat16().float()
+        Bm = (torch.randn(mo.lora_B["default"].weight.shape, generator=g) * 0.03).bfloat16().float()
+        with torch.no_grad():
+            mo.lora_A["default"].weight.copy_(A); mo.lora_B["default"].weight.copy_(Bm)
+            mg.lora_A["default"].weight.copy_(A); mg.lora_B["default"].weight.copy_(Bm)
+    cpu.train(); gpu.train()
+    gpu.set_attn_processor(lora.PSOAttnProcessor2_0())
+    assert feed_forward.install_fused_geglu(gpu) > 0
+    lora.set_wgrad_stream(True)
+    try:
+        # lr large enough that one AdamW step moves every adapter element by ~1e-2: replay 2 must see the new operands
+        opt = lora.FusedLoRAOptimizer(gpu, lr=1e-2, weight_decay=0.0, max_grad_norm=1e9)
+        sched = schedules.turbo_scheduler(4) if kind == "turbo" else schedules.dmd_scheduler()
+        batch = micro_step.synth_batch(B, 64, cfg.cross_attention_dim, 32, 5, getattr(sched, "sigmas", None), kind=kind)
+        keep32 = ("human_prefer", "time_ids")
+        d = {k: (v.cuda().bfloat16() if v.is_floating_point() and k not in keep32 else v.cuda()) for k, v in batch.items()}
+        d = micro_step.batched_view(d)
+        batch = {k: (v.bfloat16().float() if v.is_floating_point() and k not in keep32 else v) for k, v in batch.items()}
+        kw = dict(beta=5.0, eps=0.9, kind=kind)
+        graph, static_loss = _capture(pso, lora, gpu, d, sched, torch.cuda.Stream(), **kw)
+        losses_seen = []
+        for replay in range(2):
+            opt.bucket.zero_()
+            graph.replay()
+            torch.cuda.synchronize()
+            pso.check_status()
+            for m in wo:
+                m.lora_A["default"].weight.grad = None
+                m.lora_B["default"].weight.grad = None
+            loss_o = micro_step.oracle_micro_step(olora, olosses, cpu, batch, sched, **kw)
+            loss_g = float(static_loss.item())
+            losses_seen.append(loss_g)
+            assert abs(loss_g - loss_o.item()) <= 2e-2 * abs(loss_o.item()), (replay, loss_g, loss_o.item())
+            flat_o, flat_g = _flat_grads(wo), _flat_grads(wg)
+            assert flat_o.abs().max() > 0, "vacuous: the clamp gate closed and every gradient is zero"
+            cos = torch.dot(flat_o, flat_g) / (flat_o.norm() * flat_g.norm())
+            assert cos.item() >= 0.98, (replay, cos.item())
+            worst = (flat_o - flat_g).abs().max().item() / flat_o.abs().max().item()
+            assert worst <= 1e-1, (replay, worst)
+            # the bucket IS the gradient the optimizer boundary consumes
+            assert abs(opt.bucket.flat.double().norm().item() - flat_g.norm().item()) <= 1e-6 * flat_g.norm().item()
+            if replay == 0:
+                before = opt.flat_param.clone()
+                opt.step()  # clip + AdamW + zero_grad + operand refresh, eager, between replays (as bench.py)
+                torch.cuda.synchronize()
+                assert float(opt.bucket.flat.abs().max()) == 0.0
+                moved = (opt.flat_param - before).abs().max().item()
+                assert moved > 1e-3, moved
+                # the oracle continues from what the GEMM kernels now read: the refreshed 16-bit operand copies
+                for mo, mg in zip(wo, wg):
+                    with torch.no_grad():
+                        mo.lora_A["default"].weight.copy_(mg._operand("a", torch.bfloat16).float().cpu())
+                        mo.lora_B["default"].weight.copy_(mg._operand("b", torch.bfloat16).float().cpu())
+        assert losses_seen[0] != losses_seen[1], "the replayed graph did not see the updated adapter operands"
+    finally:
+        lora.set_wgrad_stream(False)
+
+
+def test_full_sdxl_fixture_graph_replayed_batched_step_vs_eager_separate_forwards(mods):
+    pso, lora, feed_forward = mods
+    B, r, hw = 1, 64, 128
+    torch.manual_seed(1234)
+    cfg = sdxl_unet.sdxl_config()
+    with torch.device("cuda"):
+        unet = sdxl_unet.UNet2DConditionModel(cfg)
+    unet = unet.to(torch.bfloat16).requires_grad_(False)
+    wrapped = lora.add_adapter(unet, lora.LoraConfig(r=r, lora_alpha=r))
+    assert len(wrapped) == 560
+    for m in wrapped:
+        torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
+    unet.set_attn_processor(lora.PSOAttnProcessor2_0())
+    unet.train()
+    opt = lora.FusedLoRAOptimizer(unet)
+    sched = schedules.dmd_scheduler()
+    pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
+    host = micro_step.synth_batch(B, hw, cfg.cross_attention_dim, pooled, 100, None, dtype=torch.bfloat16, kind="dmd")
+    d = micro_step.batched_view({k: v.cuda() for k, v in host.items()})
+    kw = dict(beta=50.0, eps=0.1, kind="dmd")
+    # arm 1: the plain eager flow, 4 forwards of batch B, stock GEGLU, weight gradients in stream order
+    lora.set_wgrad_stream(False)
+    opt.bucket.zero_()
+    loss_ref = micro_step.product_micro_step(pso, lora, unet, d, sched, **kw)
+    torch.cuda.synchronize()
+    flat_ref = opt.bucket.flat.double().cpu().clone()
+    loss_ref = float(loss_ref.item())
+    assert flat_ref.abs().max() > 0, "vacuous: every gradient is zero"
+    # arm 2: what bench.py times
+    assert feed_forward.install_fused_geglu(unet) == 70
+    lora.set_wgrad_stream(True)
+    try:
+        graph, static_loss = _capture(pso, lora, unet, d, sched, torch.cuda.Stream(), **kw)
+        for replay in range(2):
+            opt.bucket.zero_()
+            graph.replay()
+            torch.cuda.synchronize()
+            pso.check_status()
+            loss_g = float(static_loss.item())
+            flat_g = opt.bucket.flat.double().cpu()
+            assert abs(loss_g - loss_ref) <= 1e-3 * abs(loss_ref), (replay, loss_g, loss_ref)
+            cos = (torch.dot(flat_ref, flat_g) / (flat_ref.norm() * flat_g.norm())).item()
+            assert cos >= 0.999, (replay, cos)
+            assert abs(flat_g.norm().item() / flat_ref.norm().item() - 1.0) <= 2e-2
+    finally:
+        lora.set_wgrad_stream(False)

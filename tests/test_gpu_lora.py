@@ -286,3 +286,114 @@ def test_weight_gradients_on_the_side_stream_are_identical(L):
             assert _rel(g, w.double().cpu()) <= 2e-6
     finally:
         L.set_wgrad_stream(False)
+
+
+# ----------------------------------------------------------------------------------------------- round-2 additions
+def _attn_with_opt(L, r=8, seed=3, **kw):
+    torch.manual_seed(seed)
+    attn = _Attention(640, 2048, 10, 64).to(device="cuda", dtype=torch.bfloat16)
+    wrapped = L.add_adapter(attn, L.LoraConfig(r=r, lora_alpha=r))
+    for m in wrapped:
+        torch.nn.init.normal_(m.lora_B["default"].weight, std=0.05)
+    opt = L.FusedLoRAOptimizer(attn, lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0, **kw)
+    return attn, wrapped, opt
+
+
+def test_optimizer_state_round_trip_resumes_bit_identically(L, tmp_path):
+    """accelerator.save_state / load_state (turbo :889) also carry the AdamW moments and the step count: a run resumed from
+    checkpoint.save_state continues exactly like the uninterrupted one (the state used to be lost)."""
+    from pairwise_sample_optimization_b200 import checkpoint
+    attn, _, opt = _attn_with_opt(L)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    grads = [torch.randn(opt.bucket.flat.numel(), device="cuda", generator=g) * 0.02 for _ in range(4)]
+    for k in range(2):
+        opt.bucket.flat.copy_(grads[k])
+        opt.step()
+    checkpoint.save_state(str(tmp_path), attn, opt)
+    attn2, wrapped2, opt2 = _attn_with_opt(L, seed=99)  # different adapters, fresh moments
+    assert not torch.equal(opt2.flat_param, opt.flat_param)
+    checkpoint.load_state(str(tmp_path), attn2, opt2)
+    assert int(opt2.step_dev.item()) == 2 and torch.equal(opt2.flat_param, opt.flat_param)
+    assert torch.equal(opt2.exp_avg, opt.exp_avg) and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq)
+    for m in wrapped2:  # the 16-bit operands the GEMM kernels read follow the loaded parameters
+        for which, lin in (("a", m.lora_A["default"]), ("b", m.lora_B["default"])):
+            assert torch.equal(m._operand(which, torch.bfloat16), lin.weight.detach().to(torch.bfloat16))
+    for k in (2, 3):
+        for o in (opt, opt2):
+            o.bucket.flat.copy_(grads[k])
+            o.step()
+    assert torch.equal(opt2.flat_param, opt.flat_param) and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq)
+    # a checkpoint of another layout is refused
+    _, _, opt3 = _attn_with_opt(L, r=4)
+    with pytest.raises(Exception):
+        checkpoint.load_optimizer_state(str(tmp_path), opt3)
+
+
+def test_zero_grad_set_to_none_keeps_the_flat_bucket_attached(L):
+    """torch's default zero_grad(set_to_none=True) sets param.grad = None; the weight-gradient kernels must keep writing into
+    the parameter's slice of the flat bucket (they used to accumulate into private tensors, silently)."""
+    attn, wrapped, opt = _attn_with_opt(L)
+    for p in L.lora_parameters(attn):
+        p.grad = None
+    x = _mk((2, 64, 640), 9).cuda().requires_grad_(True)
+    attn.to_q(x).float().square().mean().backward()
+    assert float(opt.bucket.flat.abs().max()) > 0.0
+    pa = wrapped[0].lora_A["default"].weight
+    q = [m for m in wrapped if m is attn.to_q][0]
+    assert q.lora_A["default"].weight.grad.data_ptr() == q.lora_A["default"].weight._psob200_grad_view.data_ptr()
+    opt.zero_grad(set_to_none=True)
+    assert float(opt.bucket.flat.abs().max()) == 0.0 and pa.grad is not None
+    # a foreign tensor in param.grad is an error, not a silent no-op
+    q.lora_A["default"].weight.grad = torch.zeros_like(q.lora_A["default"].weight)
+    with pytest.raises(Exception, match="flat LoRA gradient bucket"):
+        attn.to_q(x).float().square().mean().backward()
+
+
+def test_nonfinite_gradient_norm_skips_the_update_and_grad_scale_unscales(L):
+    """fp16 loss scaling (accelerate's GradScaler around turbo :857-860): grad_scale unscales inside the fused step; an
+    overflowed (inf / NaN) gradient skips the whole update, reports found_inf and does not advance the step count."""
+    attn, _, opt = _attn_with_opt(L)
+    _, _, ref = _attn_with_opt(L)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    grad = torch.randn(opt.bucket.flat.numel(), device="cuda", generator=g) * 0.01
+    scale = 1024.0
+    opt.bucket.flat.copy_(grad * scale)
+    opt.grad_scale = 1.0 / scale
+    ref.bucket.flat.copy_(grad)
+    n1, n2 = opt.step().clone(), ref.step().clone()
+    assert abs(n1.item() - n2.item()) <= 1e-6 * n2.item() and float(opt.found_inf) == 0.0
+    assert (opt.flat_param - ref.flat_param).abs().max().item() <= 1e-7
+    before = (opt.flat_param.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.flat_operand.clone())
+    for bad in (float("inf"), float("nan")):
+        opt.bucket.flat.copy_(grad * scale)
+        opt.bucket.flat[12345] = bad
+        norm = opt.step()
+        assert not torch.isfinite(norm).item() and float(opt.found_inf) == 1.0 and int(opt.step_dev.item()) == 1
+        assert float(opt.bucket.flat.abs().max()) == 0.0  # zero_grad still happens
+        for a, b in zip(before, (opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.flat_operand)):
+            assert torch.equal(a, b)
+    # the next finite step continues with bias corrections of step 2 -- same as the run that never overflowed
+    for o, s in ((opt, scale), (ref, 1.0)):
+        o.bucket.flat.copy_(grad * s)
+        o.step()
+    assert (opt.flat_param - ref.flat_param).abs().max().item() <= 1e-7 and float(opt.found_inf) == 0.0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_tensors_on_a_second_device_launch_there(L):
+    """Per-device kernel configuration + device guard: cuda:1 tensors while cuda:0 is current."""
+    assert torch.cuda.current_device() == 0
+    dt = torch.bfloat16
+    lay0 = _layer(L, 640, 640, 8, True, dt, 1)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(640, 640, bias=True).to(device="cuda:1", dtype=dt)
+    lay1 = L.LoRALinear(lin, 8, 8)
+    with torch.no_grad():
+        lay1.lora_B["default"].weight.normal_(std=0.05)
+    x = _mk((2, 300, 640), 7, 1.0, dt)
+    y0 = lay0(x.cuda())  # configures the kernels on device 0 first
+    y1 = lay1(x.to("cuda:1"))
+    want = torch.nn.functional.linear(x.to("cuda:1").float(), lin.weight.float(), lin.bias.float()) + \
+        (x.to("cuda:1").float() @ lay1.lora_A["default"].weight.t()) @ lay1.lora_B["default"].weight.t()
+    assert y1.device.index == 1 and y0.device.index == 0
+    assert (y1.float() - want).abs().max().item() <= 2e-2 * want.abs().max().item()

@@ -80,6 +80,15 @@ def test_distilled_step_vs_reference_fixture(pso, golden_dir):
     x0 = pso._get_x0_from_noise(_c(g["sample"]), _c(g["model_output_sampling"]), sched.alphas_cumprod,
                                 torch.tensor([249, 249, 249], device="cuda"))
     np.testing.assert_allclose(x0.cpu().numpy(), g["x0_last_step"], rtol=2e-6, atol=2e-6)
+    # the reference's expression promotes with the fp32 [B,1,1,1] alphas_cumprod gather (DS:36-42): 16-bit latents and
+    # predictions still give an fp32 x0 -- the final DMD2 latent is not rounded to bf16 before the VAE
+    x0h = pso._get_x0_from_noise(_c(g["sample"]).bfloat16(), _c(g["model_output_sampling"]).bfloat16(), sched.alphas_cumprod,
+                                 torch.tensor([249, 249, 249], device="cuda"))
+    assert x0h.dtype == torch.float32
+    want = osteps.x0_from_noise(torch.from_numpy(g["sample"]).bfloat16(), torch.from_numpy(g["model_output_sampling"]).bfloat16(),
+                               sched.alphas_cumprod.cpu(), torch.tensor([249] * 3))
+    assert want.dtype == torch.float32
+    np.testing.assert_allclose(x0h.cpu().numpy(), want.numpy(), rtol=2e-6, atol=2e-6)
     with pytest.raises(ValueError):  # DS:115-119
         pso.distilled_step_with_logprob(sched, e, t, tp, _c(g["sample"]), generator=torch.Generator(device="cuda"),
                                         prev_sample=prev)
