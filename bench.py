@@ -77,6 +77,12 @@ CONFIGS = {
                "workload": "BASELINE configs[2] per-GPU slice: SDXL-DMD2 " + _COMMON + ", LoRA rank 64, 128x128 latents (1024 px)"},
     "turbo64": {"kind": "turbo", "latent_hw": 64, "rank": 8,
                 "workload": "BASELINE configs[1]: SDXL-Turbo " + _COMMON + ", LoRA rank 8, 64x64 latents (512 px)"},
+    # configs[3]: train_pso_sdxl_turbo_dreambooth.py:1720-1964; a "pair" = one (win, lose) image pair = 2 rows of the 2b-row batch
+    "dreambooth64": {"kind": "dreambooth", "latent_hw": 64, "rank": 4,
+                     "workload": "BASELINE configs[3]: SDXL-Turbo DreamBooth-style PSO micro-step (1 policy + 1 frozen-reference "
+                                 "UNet forward of 2b rows, fused DreamBooth-PSO loss+grad [pso, beta 5, neg_defactor 0.1, prior 0.5], "
+                                 "backward), random-init SDXL-architecture UNet, bf16, LoRA rank 4, 64x64 latents (512 px), "
+                                 "optimizer step every 4 micro-steps"},
 }
 
 
@@ -251,9 +257,23 @@ def ncu_traffic(key):
 def config_block(args, name):
     """The `config` object of the JSON line: names the WORKLOAD only, so that both arms print the same object."""
     conf = CONFIGS[name]
-    return {"workload": conf["workload"] if not args.tiny else "TINY fixture (debug run, not the benchmark)", "name": name,
-            "pairs_per_gpu_per_step": args.pairs, "latent_shape": [4, conf["latent_hw"], conf["latent_hw"]],
-            "lora_rank": conf["rank"], "beta": 50.0, "eps": 0.1, "accum": ACCUM}
+    out = {"workload": conf["workload"] if not args.tiny else "TINY fixture (debug run, not the benchmark)", "name": name,
+           "pairs_per_gpu_per_step": args.pairs, "latent_shape": [4, conf["latent_hw"], conf["latent_hw"]],
+           "lora_rank": conf["rank"]}
+    out.update({"loss_type": "pso", "beta_pso": 5.0, "neg_defactor": 0.1, "prior_loss_weight": 0.5, "accum": 4}
+               if conf["kind"] == "dreambooth" else {"beta": 50.0, "eps": 0.1, "accum": ACCUM})
+    return out
+
+
+def dreambooth_scheduler():
+    """EulerDiscreteScheduler as constructed (no set_timesteps): timesteps 999..0, sigmas descending + [0] (restated; the
+    anchored copy is oracle/schedules.py::dreambooth_scheduler; dreambooth trainer :1235-1237, :1675-1685)."""
+    import types
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float64) ** 2
+    ac = torch.cumprod(1.0 - betas, dim=0)
+    sig = (((1 - ac) / ac) ** 0.5).flip(0)
+    return types.SimpleNamespace(timesteps=torch.arange(999, -1, -1, dtype=torch.float32),
+                                 sigmas=torch.cat([sig, torch.zeros(1, dtype=torch.float64)]).float())
 
 
 def make_scheduler(kind, dev=None):
@@ -311,12 +331,18 @@ class B200Arm:
             if world > 1:
                 self.exchange_kind = "one NCCL all-reduce of the flat gradient"
         self.bucket = self.opt.bucket
-        self.sched = make_scheduler(self.kind)
+        self.accum = 4 if self.kind == "dreambooth" else ACCUM  # pso_dog.sh: gradient_accumulation_steps 4
         pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
-        host = micro_step.synth_batch(self.B, self.hw, cfg.cross_attention_dim, pooled, 100 + rank,
-                                      getattr(self.sched, "sigmas", None), dtype=torch.bfloat16, kind=self.kind)
-        if not args.separate_forwards:
-            host = micro_step.batched_view(host)
+        if self.kind == "dreambooth":
+            self.sched = dreambooth_scheduler()
+            host = micro_step.synth_dreambooth_batch(self.B, self.hw, cfg.cross_attention_dim, pooled, 100 + rank, self.sched,
+                                                     dtype=torch.bfloat16)
+        else:
+            self.sched = make_scheduler(self.kind)
+            host = micro_step.synth_batch(self.B, self.hw, cfg.cross_attention_dim, pooled, 100 + rank,
+                                          getattr(self.sched, "sigmas", None), dtype=torch.bfloat16, kind=self.kind)
+            if not args.separate_forwards:
+                host = micro_step.batched_view(host)
         self.host = {k: v.pin_memory() for k, v in host.items()}
         self.d = {k: v.to(dev) for k, v in self.host.items()}
         self.fwd_bwd = micro_step.product_micro_step if args.separate_forwards else micro_step.product_micro_step_batched
@@ -327,11 +353,15 @@ class B200Arm:
     # ---- one micro-step (turbo trainer :771-861 / dmd2 trainer :773-864)
     def micro(self, batch, overlap=True, **extra):
         kw = {"ref_stream": self.ref_stream} if (self.ref_stream is not None and overlap) else {}
+        if self.kind == "dreambooth":  # dreambooth trainer :1812-1953 (pso_dog.sh: beta_pso 5, prior_loss_weight 0.5)
+            return self.micro_step.product_dreambooth_micro_step(self.pso, self.lora, self.unet, batch, loss_type="pso",
+                                                                 beta_pso=5.0, neg_defactor=0.1, prior_loss_weight=0.5,
+                                                                 loss_scale=1.0 / self.accum, **kw, **extra)
         return self.fwd_bwd(self.pso, self.lora, self.unet, batch, self.sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM,
                             kind=self.kind, **kw, **extra)
 
     def optimizer_boundary(self, i):
-        if (i + 1) % ACCUM == 0:  # turbo trainer :858-861 (sync_gradients): exchange, clip, AdamW, zero_grad
+        if (i + 1) % self.accum == 0:  # turbo trainer :858-861 (sync_gradients): exchange, clip, AdamW, zero_grad
             self.opt.all_reduce()
             self.opt.step()
 
@@ -381,7 +411,7 @@ class B200Arm:
         """Exactly K steps, inputs resident in HBM, CUDA events, max over ranks."""
         for i in range(W):
             self.step(i)
-        self.optimizer_boundary(ACCUM - 1)  # one untimed optimizer boundary: first exchange, kernels loaded
+        self.optimizer_boundary(self.accum - 1)  # one untimed optimizer boundary: first exchange, kernels loaded
         self.pso.check_status(self.dev)
         self.bucket.zero_()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -400,8 +430,8 @@ class B200Arm:
         per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(K)]
         ms_per_step = self.max_over_ranks(ev0.elapsed_time(ev1)) / K
         out = {"value": self.world * self.B / (ms_per_step * 1e-3), "ms_per_step": ms_per_step, "per_step": per_step,
-               "launches": int(launches), "clocks": clocks.summary(), "loss": float(loss.item()) * ACCUM}
-        if K >= ACCUM:  # at least one optimizer boundary inside the timed region: its (pre-clip) gradient norm
+               "launches": int(launches), "clocks": clocks.summary(), "loss": float(loss.item()) * self.accum}
+        if K >= self.accum:  # at least one optimizer boundary inside the timed region: its (pre-clip) gradient norm
             out["grad_norm"] = float(self.opt.grad_norm.item())
         return out
 
@@ -433,8 +463,10 @@ class B200Arm:
 
     def gate(self):
         """One eager micro-step (untimed) with the loss kernel's per-pair statistics: how many clamp gates were open."""
+        if self.kind == "dreambooth" or self.args.separate_forwards:
+            return None
         self.bucket.zero_()
-        _, stats = self.micro(self.d, return_stats=True) if not self.args.separate_forwards else (None, None)
+        _, stats = self.micro(self.d, return_stats=True)
         self.bucket.zero_()
         if stats is None:
             return None
@@ -626,14 +658,19 @@ def gpu_eager_baseline(args, name, dev, host, reps=4):
         torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
         m.lora_A.to(torch.bfloat16); m.lora_B.to(torch.bfloat16)
     unet.train()
-    sched = make_scheduler(kind, dev)
+    sched = make_scheduler(kind, dev) if kind != "dreambooth" else None
     d = {k: v.to(dev) for k, v in host.items()}
+    accum = 4 if kind == "dreambooth" else ACCUM
 
     def one():
         for m in wrapped:
             m.lora_A["default"].weight.grad = None
             m.lora_B["default"].weight.grad = None
-        return micro_step.oracle_micro_step(olora, olosses, unet, d, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM, kind=kind)
+        if kind == "dreambooth":
+            return micro_step.oracle_dreambooth_micro_step(olora, olosses, unet, d, loss_type="pso", beta_pso=5.0, neg_defactor=0.1,
+                                                           prior_loss_weight=0.5, loss_scale=1.0 / accum)[0].detach()
+        return micro_step.oracle_micro_step(olora, olosses, unet, d, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM,
+                                            kind=kind).detach()  # no autograd graph kept alive between steps
 
     def timed(fn, n):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
@@ -644,30 +681,33 @@ def gpu_eager_baseline(args, name, dev, host, reps=4):
             evs[i + 1].record()
         torch.cuda.synchronize()
         return statistics.mean(evs[i].elapsed_time(evs[i + 1]) for i in range(n))
-    for _ in range(2):
-        loss = one()
-    ms_eager = timed(one, reps)
     B = args.pairs
-    out = {"kind": "torch-eager on this GPU: stock nn.Linear + peft-style LoRA module (3 cuBLAS GEMMs + scale + add), 4 forwards, "
-                   "~340-launch loss chain, autograd; bf16, activations resident",
-           "value": round(B / (ms_eager * 1e-3), 3), "unit": UNIT, "ms_per_step": round(ms_eager, 2), "steps": reps,
-           "loss": round(float(loss.item()) * ACCUM, 6)}
-    try:  # the same step replayed from a CUDA graph (no host launch latency): only where the flow has no host sync (DMD2)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
-            one()
-        torch.cuda.synchronize()
-        with torch.cuda.graph(graph, stream=side):
-            one()
-        graph.replay()
-        ms_graph = timed(graph.replay, reps)
-        out["graph_replayed"] = {"value": round(B / (ms_graph * 1e-3), 3), "ms_per_step": round(ms_graph, 2)}
-        del graph
-    except Exception as e:
-        torch.cuda.synchronize()
-        out["graph_replayed"] = {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
+    side = torch.cuda.Stream()  # everything on ONE non-default stream: the AccumulateGrad nodes are created under it
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            loss = one()
+        ms_eager = timed(one, reps)
+        out = {"kind": "torch-eager on this GPU: stock nn.Linear + peft-style LoRA module (3 cuBLAS GEMMs + scale + add), 4 "
+                       "forwards, ~340-launch loss chain, autograd; bf16, activations resident",
+               "value": round(B / (ms_eager * 1e-3), 3), "unit": UNIT, "ms_per_step": round(ms_eager, 2), "steps": reps,
+               "loss": round(float(loss.item()) * accum, 6)}
+        if kind != "turbo":  # the same step replayed from a CUDA graph (no host launch latency); the Turbo flow syncs (.item(), TS:63)
+            try:
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(graph, stream=side):
+                    one()
+                graph.replay()
+                ms_graph = timed(graph.replay, reps)
+                out["graph_replayed"] = {"value": round(B / (ms_graph * 1e-3), 3), "ms_per_step": round(ms_graph, 2)}
+                del graph
+            except Exception as e:
+                out["graph_replayed"] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+        else:
+            out["graph_replayed"] = {"unavailable": "the Euler-ancestral step of the reference syncs with the host once per sample "
+                                                    "(turbo_inference_with_logprob.py:63): not capturable"}
+    torch.cuda.synchronize()
     del unet, wrapped
     import gc
     gc.collect()
@@ -704,7 +744,7 @@ def run_b200(args):
     extra = {}
     if world > 1:
         extra["exchange_check"] = arm.exchange_check()
-    run_details = {"parallelism": f"dp{world} (pairs sharded; one exchange of the flat LoRA gradient per {ACCUM} steps)",
+    run_details = {"parallelism": f"dp{world} (pairs sharded; one exchange of the flat LoRA gradient per {arm.accum} steps)",
                    "gradient_exchange": arm.exchange_kind,
                    "activations": ("recomputed in the backward (gradient checkpointing, as the reference)" if args.grad_checkpointing
                                    else "resident in HBM (no gradient checkpointing: same gradients, no recompute forward)"),
@@ -720,33 +760,48 @@ def run_b200(args):
     arm.close()
     del arm
 
+    def guarded(key, fn):
+        """Optional blocks never cost the headline line: a failure is recorded under the block's key."""
+        try:
+            extra[key] = fn()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            extra[key] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+            torch.cuda.synchronize()
+
     if rank == 0 and not args.no_kernel_figures:
-        extra["loss_kernel_roofline"] = loss_kernel_roofline(pso, dev, peaks)
-        extra["sampler_kernel_roofline"] = sampler_kernel_roofline(dev, peaks)
-        extra["lora_gemm_large"] = lora_gemm_large(dev, peaks)
+        guarded("loss_kernel_roofline", lambda: loss_kernel_roofline(pso, dev, peaks))
+        guarded("sampler_kernel_roofline", lambda: sampler_kernel_roofline(dev, peaks))
+        guarded("lora_gemm_large", lambda: lora_gemm_large(dev, peaks))
         if args.config == "dmd128" and not args.tiny:
-            extra["lora_projection_vs_cublas"] = lora_projection_vs_cublas(
-                dev, [(8192, 1280, 1280), (32768, 640, 640), (616, 2048, 1280)], CONFIGS[args.config]["rank"])
-    if rank == 0 and world == 1 and not args.no_eager_baseline:
-        eager = gpu_eager_baseline(args, args.config, dev, host_batch)
-        eager["ratio_ours_over_eager"] = round(t["value"] / eager["value"], 3)
-        if "value" in eager.get("graph_replayed", {}):
-            eager["ratio_ours_over_graph_replayed"] = round(t["value"] / eager["graph_replayed"]["value"], 3)
-        extra["gpu_eager_baseline"] = eager
+            guarded("lora_projection_vs_cublas", lambda: lora_projection_vs_cublas(
+                dev, [(8192, 1280, 1280), (32768, 640, 640), (616, 2048, 1280)], CONFIGS[args.config]["rank"]))
     if world == 1 and args.config == "dmd128" and not args.no_turbo64 and not args.tiny:
         # configs[1], short: the latency-bound regime (M = 2048 launches), driver-visible next to the headline configuration
-        arm2 = B200Arm(args, "turbo64", dev, rank, world, L)
-        if not args.no_graph:
-            arm2.capture()
-        t2 = arm2.timed(6, 3)
-        r2, s2 = arm2.instrumented(t2["ms_per_step"], peaks)
-        for blk in (r2, s2):
-            blk.pop("how", None); blk.pop("by_launch", None)
-        extra["turbo64"] = {"config": config_block(args, "turbo64"), "value": round(t2["value"], 3), "unit": UNIT, "steps": 6,
-                            "warmup": 3, "ms_per_step": round(t2["ms_per_step"], 3), "gpu_launches": t2["launches"],
-                            "loss": round(t2["loss"], 6), "roofline": r2, "lora_skinny_launches": s2}
-        arm2.close()
-        del arm2
+        def turbo64_block():
+            arm2 = B200Arm(args, "turbo64", dev, rank, world, L)
+            try:
+                if not args.no_graph:
+                    arm2.capture()
+                t2 = arm2.timed(6, 3)
+                r2, s2 = arm2.instrumented(t2["ms_per_step"], peaks)
+                for blk in (r2, s2):
+                    blk.pop("how", None); blk.pop("by_launch", None)
+                return {"config": config_block(args, "turbo64"), "value": round(t2["value"], 3), "unit": UNIT, "steps": 6,
+                        "warmup": 3, "ms_per_step": round(t2["ms_per_step"], 3), "gpu_launches": t2["launches"],
+                        "loss": round(t2["loss"], 6), "roofline": r2, "lora_skinny_launches": s2}
+            finally:
+                arm2.close()
+        guarded("turbo64", turbo64_block)
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        def eager_block():
+            eager = gpu_eager_baseline(args, args.config, dev, host_batch)
+            eager["ratio_ours_over_eager"] = round(t["value"] / eager["value"], 3)
+            if "value" in eager.get("graph_replayed", {}):
+                eager["ratio_ours_over_graph_replayed"] = round(t["value"] / eager["graph_replayed"]["value"], 3)
+            return eager
+        guarded("gpu_eager_baseline", eager_block)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(args, reps=1, warmup=0)
@@ -806,18 +861,28 @@ def _make_cpu_step(args, pairs):
         torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
     unet.train()
     unet.enable_gradient_checkpointing()
-    sched = schedules.turbo_scheduler(4) if KIND == "turbo" else schedules.dmd_scheduler()
     pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
-    batch = micro_step.synth_batch(pairs, LATENT_HW, cfg.cross_attention_dim, pooled, 100, getattr(sched, "sigmas", None),
-                                   kind=KIND)
+    if KIND == "dreambooth":
+        sched = schedules.dreambooth_scheduler()
+        batch = micro_step.synth_dreambooth_batch(pairs, LATENT_HW, cfg.cross_attention_dim, pooled, 100, sched)
+    else:
+        sched = schedules.turbo_scheduler(4) if KIND == "turbo" else schedules.dmd_scheduler()
+        batch = micro_step.synth_batch(pairs, LATENT_HW, cfg.cross_attention_dim, pooled, 100, getattr(sched, "sigmas", None),
+                                       kind=KIND)
 
     def one():
-        loss = micro_step.oracle_micro_step(olora, olosses, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM,
-                                            kind=KIND)
+        if KIND == "dreambooth":
+            loss, _ = micro_step.oracle_dreambooth_micro_step(olora, olosses, unet, batch, loss_type="pso", beta_pso=5.0,
+                                                              neg_defactor=0.1, prior_loss_weight=0.5, loss_scale=0.25)
+            scale = 4
+        else:
+            loss = micro_step.oracle_micro_step(olora, olosses, unet, batch, sched, beta=50.0, eps=0.1, loss_scale=1.0 / ACCUM,
+                                                kind=KIND)
+            scale = ACCUM
         for m in wrapped:
             m.lora_A["default"].weight.grad = None
             m.lora_B["default"].weight.grad = None
-        return float(loss.detach()) * ACCUM
+        return float(loss.detach()) * scale
     return one, threads
 
 

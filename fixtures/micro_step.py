@@ -134,3 +134,93 @@ def oracle_micro_step(olora, olosses, unet, batch, sched, *, beta=50.0, eps=0.1,
                                         step_ratio=DMD_STEP_RATIO if kind == "dmd" else None)
     (loss * loss_scale).backward()
     return loss * loss_scale
+
+
+# ----------------------------------------------------------------------------------------------- DreamBooth-style PSO (config 4)
+DB_LEVELS = 4  # args.distill_train_timesteps: the 4-level schedule 249 / 499 / 749 / 999 (dreambooth trainer :1769-1779)
+
+
+def synth_dreambooth_batch(b, latent_hw, cross_dim, pooled_dim, seed, sched, dtype=torch.float32, device="cpu"):
+    """Inputs of one DreamBooth-PSO step as the trainer builds them (train_pso_sdxl_turbo_dreambooth.py:1727-1804): 2b rows
+    -- b win latents (instance images) then b lose latents (negatives sampled from the base model) --, ONE noise draw shared by
+    win and lose (:1763), one of 4 timestep levels per pair (:1769-1781), sigma looked up by timestep equality (:1675-1685),
+    ``noisy = x0 + sigma noise`` (EulerDiscrete.add_noise, :1787), UNet input ``noisy / sqrt(sigma^2 + 1)`` (:1796), the
+    instance prompt's embeddings repeated for both halves (:1813-1817).  ``sched`` = oracle.schedules.dreambooth_scheduler()
+    or any object with ``.timesteps`` / ``.sigmas``."""
+    g = torch.Generator().manual_seed(seed)
+    shape = (4, latent_hw, latent_hw)
+    x0 = torch.randn(2 * b, *shape, generator=g) * 0.8                                   # VAE latents * scaling_factor
+    noise = torch.randn(2 * b, *shape, generator=g).chunk(2)[0].repeat(2, 1, 1, 1)       # :1763
+    raw = torch.randint(0, 1000, (b,), generator=g)
+    stride = 1000 // DB_LEVELS
+    idx = (stride * (raw % DB_LEVELS) + stride - 1).long().repeat(2)                     # :1769-1779
+    timesteps = sched.timesteps[idx]                                                     # :1781
+    sig = torch.stack([sched.sigmas[(sched.timesteps == t).nonzero().item()] for t in timesteps]).reshape(-1, 1, 1, 1)
+    noisy = x0 + sig * noise
+    inp = noisy / ((sig ** 2 + 1) ** 0.5)
+    px = 8.0 * latent_hw
+    out = {"model_input": x0, "noisy_model_input": noisy, "inp_noisy_latents": inp, "sigmas": sig.float(),
+           "timesteps": timesteps.float(),
+           "prompt_embeds": torch.randn(b, 77, cross_dim, generator=g).repeat(2, 1, 1),
+           "text_embeds": torch.randn(b, pooled_dim, generator=g).repeat(2, 1),
+           "time_ids": torch.tensor([[px, px, 0.0, 0.0, px, px]]).repeat(2 * b, 1)}
+    keep32 = ("sigmas", "timesteps", "time_ids")
+    return {k: (v.to(device=device, dtype=dtype) if k not in keep32 else v.to(device)) for k, v in out.items()}
+
+
+def _db_unet(unet, batch):
+    x = batch["inp_noisy_latents"]
+    return unet(x, batch["timesteps"], batch["prompt_embeds"],
+                added_cond_kwargs={"text_embeds": batch["text_embeds"], "time_ids": batch["time_ids"].to(x.dtype)},
+                return_dict=False)[0]
+
+
+def product_dreambooth_micro_step(pso, lora, unet, batch, *, loss_type="pso", beta_pso=5.0, neg_defactor=0.1,
+                                  prior_loss_weight=0.5, loss_scale=1.0, ref_stream=None, return_stats=False):
+    """Product path of train_pso_sdxl_turbo_dreambooth.py:1812-1953: ONE policy forward of 2b rows with grad, for
+    ``loss_type="pso"`` one adapter-disabled forward without (:1894-1905), then the fused DreamBooth-PSO kernel (EDM output
+    preconditioning :1855, sigma^-2 weighting :1865, win / lose split, reference branch, hinge / log-sigmoid, prior term :1932)
+    and the backward.  With ``ref_stream`` the frozen-reference forward runs on a second stream like the online step."""
+    ref = None
+    cur = torch.cuda.current_stream()
+    if loss_type == "pso" and ref_stream is not None:
+        ref_stream.wait_stream(cur)
+        lora.disable_adapters(unet)
+        with torch.cuda.stream(ref_stream), torch.no_grad():
+            ref = _db_unet(unet, batch)
+        lora.enable_adapters(unet)
+    pred = _db_unet(unet, batch)
+    if loss_type == "pso":
+        if ref_stream is not None:
+            cur.wait_stream(ref_stream)
+            ref.record_stream(cur)
+        else:
+            lora.disable_adapters(unet)
+            with torch.no_grad():
+                ref = _db_unet(unet, batch)
+            lora.enable_adapters(unet)
+    loss, lw, ll, logits = pso.pso_db_loss(pred, ref, batch["noisy_model_input"], batch["model_input"], batch["sigmas"],
+                                           loss_type=loss_type, beta_pso=beta_pso, neg_defactor=neg_defactor,
+                                           prior_loss_weight=prior_loss_weight, loss_scale=loss_scale)
+    loss.backward()
+    return (loss, (lw, ll, logits)) if return_stats else loss
+
+
+def oracle_dreambooth_micro_step(olora, olosses, unet, batch, *, loss_type="pso", beta_pso=5.0, neg_defactor=0.1,
+                                 prior_loss_weight=0.5, loss_scale=1.0, loss_fn=None):
+    """The trainer's flow restated with the oracle pieces (:1812-1953): policy forward, the reference forward with the
+    adapters disabled, the loss lines (``oracle.losses.dreambooth_pso_loss``, or ``loss_fn`` = the trainer's own lines from
+    ``reference_loader.trainer_dreambooth_block()``), autograd backward."""
+    pred = _db_unet(unet, batch)
+    ref = None
+    if loss_type == "pso":
+        olora.oracle_set_adapters(unet, False)
+        with torch.no_grad():
+            ref = _db_unet(unet, batch)
+        olora.oracle_set_adapters(unet, True)
+    fn = loss_fn or olosses.dreambooth_pso_loss
+    loss, lw, ll, logits = fn(pred.float(), None if ref is None else ref.float(), batch["noisy_model_input"].float(),
+                              batch["model_input"].float(), batch["sigmas"].float(), loss_type, beta_pso, neg_defactor,
+                              prior_loss_weight)
+    (loss * loss_scale).backward()
+    return loss * loss_scale, (lw, ll, logits)

@@ -496,11 +496,50 @@ typedef struct psob200_geglu_args {
 PSOB200_API int psob200_geglu_forward(const psob200_geglu_args* args, void* stream);
 PSOB200_API int psob200_geglu_backward(const psob200_geglu_args* args, void* stream);
 
+/*
+ * Reward-side image preprocessing on the device.  Replaces, in one launch, the round trip the
+ * trainers make before every reward call (train_online_pso_sdxl_turbo.py:632-640, pso_pytorch/pickscore_utils.py:24-33):
+ *     ((images + 1) * 127.5).clamp(0, 255).to(uint8).permute(0,2,3,1).cpu().numpy() -> PIL.Image.fromarray -> CLIPImageProcessor
+ *     (resize shortest edge to `size` with PIL BICUBIC, centre crop, * 1/255, (x - mean) / std, channels first) -> .to(device)
+ * bit-exactly: the resize is Pillow's two-pass fixed-point convolution (libImaging/Resample.c, 8 bits per channel: bicubic
+ * a = -0.5 with the support stretched by the down-scale factor, coefficients rounded to 22 fractional bits, horizontal pass
+ * rounded to uint8 before the vertical pass); rescale + normalise are a 3 x 256 entry table built with numpy's rounding.
+ *
+ * psob200_resample_taps / psob200_resample_plan (HOST only, no CUDA call): the coefficient table of one axis.  For output
+ * index j (0 <= j < out_size): bounds[2j] = first input index, bounds[2j+1] = tap count, coeffs[j*taps .. ] = fixed-point
+ * weights (the rest zero); `taps` = psob200_resample_taps(in_size, out_size).  The caller uploads both tables.
+ * psob200_clip_norm_table (HOST only): table[c*256 + v] = float32((float32(v * rescale) - mean[c]) / std[c]).
+ *
+ * psob200_clip_preprocess: src is uint8 NHWC [B, in_h, in_w, 3] (src_dtype = PSOB200_U8) or the decoded image itself,
+ * float NCHW [B, 3, in_h, in_w] in [-1, 1] (src_dtype F32 / BF16 / F16; quantised like the trainer's expression above, in
+ * the tensor's own arithmetic type).  The image is resized to [rs_h, rs_w] (the tables' out sizes) and the window
+ * [crop_top, crop_top + out_h) x [crop_left, crop_left + out_w) is written as dst [B, 3, out_h, out_w] (F32 / BF16 / F16).
+ */
+#define PSOB200_U8 3
+PSOB200_API int psob200_resample_taps(int64_t in_size, int64_t out_size);
+PSOB200_API int psob200_resample_plan(int64_t in_size, int64_t out_size, int32_t* bounds, int32_t* coeffs);
+PSOB200_API int psob200_clip_norm_table(double rescale, const float* mean3, const float* std3, float* table768);
+
+typedef struct psob200_clip_preprocess_args {
+  const void* src;
+  void* dst;
+  const int32_t* bounds_h; /* device: horizontal (x) axis tables, out size rs_w */
+  const int32_t* coeffs_h;
+  const int32_t* bounds_v; /* device: vertical (y) axis tables, out size rs_h */
+  const int32_t* coeffs_v;
+  const float* norm_table; /* device: 768 floats */
+  int64_t B, in_h, in_w, rs_h, rs_w, out_h, out_w, crop_top, crop_left;
+  int32_t taps_h, taps_v;
+  int32_t src_dtype, dst_dtype;
+} psob200_clip_preprocess_args;
+
+PSOB200_API int psob200_clip_preprocess(const psob200_clip_preprocess_args* args, void* stream);
+
 /* sizeof() of the argument structs as compiled into the library, for FFI bindings to
  * verify their mirror of this header: which = 0 schedule, 1 online_pso_args,
  * 2 dreambooth_args, 3 step_args, 4 step_bwd_args, 5 gemm_args,
  * 6 lora_linear_args, 7 flat_adamw_args, 8 geglu_args,
- * 9 flat_allreduce_args.  Returns 0 for unknown ids. */
+ * 9 flat_allreduce_args, 10 clip_preprocess_args.  Returns 0 for unknown ids. */
 PSOB200_API size_t psob200_struct_size(int which);
 
 #ifdef __cplusplus

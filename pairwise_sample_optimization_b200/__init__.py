@@ -7,13 +7,14 @@ Only what the path needs:
 * ``losses``                      fused online-PSO and DreamBooth-PSO loss + gradient
 * ``lora`` / ``gemm``              LoRA-wrapped attention projections (peft / diffusers surface) on the tcgen05 GEMM kernels
 * ``feed_forward``                fused gated GELU (GEGLU) of the transformer feed-forward, forward + backward
-* ``checkpoint``                  LoRA adapters in the reference's safetensors wire format
+* ``checkpoint``                  LoRA adapters in the reference's safetensors wire format (+ optimizer state)
+* ``reward_preprocess``           decoded images -> CLIP / PickScore ``pixel_values`` on the device (Pillow-exact resize)
 * ``runtime``                     device-resident schedule tables, workspace, status word
 
 There is no CPU or PyTorch fallback: every op raises if the CUDA library is missing.
 """
-from . import _lib, checkpoint, feed_forward, gemm, lora, runtime
-from .losses import compare, pso_db_loss, pso_pair_loss, sample_compare
+from . import _lib, checkpoint, feed_forward, gemm, lora, reward_preprocess, runtime
+from .losses import compare, edm_sigmas, pso_db_loss, pso_pair_loss, sample_compare
 from .pso_pytorch.diffusers_patch import (
     _get_x0_from_noise,
     distilled_step_with_logprob,
@@ -21,6 +22,7 @@ from .pso_pytorch.diffusers_patch import (
     sdxl_turbo_pipeline_with_logprob,
     turbo_step_with_logprob,
 )
+from .reward_preprocess import DeviceCLIPImageProcessor, clip_image_preprocess
 from .runtime import check_status
 
 __all__ = [
@@ -31,7 +33,10 @@ __all__ = [
     "sdxl_dmd_pipeline_with_logprob",
     "pso_pair_loss",
     "pso_db_loss",
+    "edm_sigmas",
     "sample_compare",
     "compare",
     "check_status",
+    "clip_image_preprocess",
+    "DeviceCLIPImageProcessor",
 ]

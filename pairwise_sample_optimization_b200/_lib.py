@@ -13,7 +13,7 @@ import torch
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libpsob200.so")
 
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, U8 = 0, 1, 2, 3
 TS_I64, TS_F32, TS_I32 = 0, 1, 2
 SCHED_TURBO, SCHED_DMD, SCHED_AFFINE = 0, 1, 2
 DB_PSO, DB_PSO_DB = 0, 1
@@ -109,8 +109,16 @@ class GegluArgs(C.Structure):
                 ("dtype", C.c_int32)]
 
 
+class ClipPreprocessArgs(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("bounds_h", _vp), ("coeffs_h", _vp), ("bounds_v", _vp), ("coeffs_v", _vp),
+                ("norm_table", _fp), ("B", C.c_int64), ("in_h", C.c_int64), ("in_w", C.c_int64), ("rs_h", C.c_int64),
+                ("rs_w", C.c_int64), ("out_h", C.c_int64), ("out_w", C.c_int64), ("crop_top", C.c_int64),
+                ("crop_left", C.c_int64), ("taps_h", C.c_int32), ("taps_v", C.c_int32), ("src_dtype", C.c_int32),
+                ("dst_dtype", C.c_int32)]
+
+
 _STRUCTS = {0: Schedule, 1: OnlinePsoArgs, 2: DreamboothArgs, 3: StepArgs, 4: StepBwdArgs, 5: GemmArgs,
-            6: LoraLinearArgs, 7: FlatAdamwArgs, 8: GegluArgs, 9: FlatAllreduceArgs}
+            6: LoraLinearArgs, 7: FlatAdamwArgs, 8: GegluArgs, 9: FlatAllreduceArgs, 10: ClipPreprocessArgs}
 
 # name -> (restype, argtypes): every symbol include/psob200.h declares
 SIGNATURES = {
@@ -134,6 +142,10 @@ SIGNATURES = {
     "psob200_flat_allreduce_sumsq": (C.c_int, [C.POINTER(FlatAllreduceArgs), _vp]),
     "psob200_geglu_forward": (C.c_int, [C.POINTER(GegluArgs), _vp]),
     "psob200_geglu_backward": (C.c_int, [C.POINTER(GegluArgs), _vp]),
+    "psob200_resample_taps": (C.c_int, [C.c_int64, C.c_int64]),
+    "psob200_resample_plan": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "psob200_clip_norm_table": (C.c_int, [C.c_double, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "psob200_clip_preprocess": (C.c_int, [C.POINTER(ClipPreprocessArgs), _vp]),
     "psob200_scale": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, C.c_int32, C.c_int32, _vp]),
     "psob200_scale_inplace_by_device_scalar": (C.c_int, [_vp, C.c_int64, C.c_int32, _fp, _vp]),
 }

@@ -164,6 +164,21 @@ def pso_pair_loss(noise_pred_0, noise_pred_1, noise_ref_pred_0, noise_ref_pred_1
 
 
 # ----------------------------------------------------------------------------- DreamBooth PSO
+def edm_sigmas(noise_scheduler, timesteps: torch.Tensor, n_dim: int = 4, dtype=torch.float32) -> torch.Tensor:
+    """``get_sigmas`` of the DreamBooth trainer (train_pso_sdxl_turbo_dreambooth.py:1675-1685): ``sigmas[i]`` for the schedule
+    position ``i`` whose ``scheduler.timesteps[i] == t``, shaped ``[B, 1, 1, 1]``.  The reference finds ``i`` with one
+    ``.nonzero().item()`` host sync per sample; here the lookup is one comparison matrix + argmax on the device, no sync
+    (a timestep that is not in the schedule selects position 0 instead of raising)."""
+    dev = timesteps.device
+    sched_ts = noise_scheduler.timesteps.to(dev)
+    sig = noise_scheduler.sigmas.to(device=dev, dtype=dtype)
+    idx = (sched_ts[None, :] == timesteps.to(sched_ts.dtype)[:, None]).to(torch.uint8).argmax(dim=1)
+    out = sig[idx].flatten()
+    while out.dim() < n_dim:
+        out = out.unsqueeze(-1)
+    return out
+
+
 class _DreamboothPsoLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model_pred, ref_pred, noisy, target, sigmas, loss_type, beta_pso, neg_defactor,
