@@ -306,6 +306,8 @@ class B200Arm:
         for m in wrapped:  # the reference starts from B = 0; use a small non-zero B so every adapter GEMM does real work
             torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
         unet.set_attn_processor(lora.PSOAttnProcessor2_0())
+        if args.fuse_projections:  # q / k / v (k / v) of every attention stacked into one launch per direction
+            lora.fuse_attention_projections(unet)
         if args.fused_geglu:  # the feed-forward's gated GELU on one fused kernel each way (outside SURVEY section 8's rows)
             from pairwise_sample_optimization_b200 import feed_forward
             feed_forward.install_fused_geglu(unet)
@@ -749,6 +751,8 @@ def run_b200(args):
                    "activations": ("recomputed in the backward (gradient checkpointing, as the reference)" if args.grad_checkpointing
                                    else "resident in HBM (no gradient checkpointing: same gradients, no recompute forward)"),
                    "weight_gradients": "dA / dB launches on a side stream" if args.wgrad_stream else "in stream order",
+                   "projections": ("q / k / v (k / v) stacked: one launch per group and direction, t / u as tiles of the main "
+                                   "launch" if args.fuse_projections else "one launch sequence per projection"),
                    "feed_forward": "fused GEGLU kernels" if args.fused_geglu else "stock torch GEGLU",
                    "l2_policy": "working set larger than L2 (5.1 GB of bf16 weights streamed every forward)",
                    "forwards": "4 separate (as the reference)" if args.separate_forwards else
@@ -967,6 +971,8 @@ def main():
     ap.add_argument("--no-fused-geglu", dest="fused_geglu", action="store_false", default=True,
                     help="leave the feed-forward's GEGLU on the stock torch kernels")
     ap.add_argument("--tiny", action="store_true", help="debug: the 32/64-channel fixture instead of the SDXL architecture")
+    ap.add_argument("--no-fuse-projections", dest="fuse_projections", action="store_false", default=True,
+                    help="one launch sequence per projection instead of stacked q / k / v (k / v) groups")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager-on-this-GPU baseline")
     ap.add_argument("--no-turbo64", action="store_true", help="skip the short configs[1] block after the main timing")
     args = ap.parse_args()

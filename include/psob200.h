@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PSOB200_ABI_VERSION 1
+#define PSOB200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PSOB200_API __attribute__((visibility("default")))
@@ -407,10 +407,62 @@ typedef struct psob200_lora_linear_args {
   int32_t adapters_enabled;
   int32_t backward_phases;
   int32_t forward_phases;
+  /* Optional zeroed int32 workspace (>= ceil(M / 128) + 1 entries, left zeroed): when given, and all phases of a direction
+   * are requested, t (u) becomes a problem of the SAME launch as y (dx) -- its tiles release a flag per row block and the
+   * adapter segment of the main problem waits for it -- so the forward is ONE launch and the backward two (input
+   * gradients; weight gradients).  One workspace per stream. */
+  int32_t* flags;
+  int64_t flags_len;
 } psob200_lora_linear_args;
 
 PSOB200_API int psob200_lora_linear_forward(const psob200_lora_linear_args* args, void* stream);
 PSOB200_API int psob200_lora_linear_backward(const psob200_lora_linear_args* args, void* stream);
+
+/*
+ * G LoRA-wrapped projections that share their input, STACKED (attention to_q / to_k / to_v, cross-attention to_k / to_v;
+ * G = 1 is psob200_lora_linear_*): the frozen weights are one matrix w [G N, K], the adapters lora_a [G r, K] and
+ * lora_b [G N, r] (projection g owns rows [g r, (g+1) r) resp. [g N, (g+1) N)), the output is y [M, G N] whose column
+ * group g is projection g (the reference runs G separate peft lora.Linear modules: attn.to_q / to_k / to_v in diffusers
+ * AttnProcessor2_0, wrapped at T:338-345).  Launches on `stream`:
+ *
+ *   forward  (1 launch with `flags`, else 2)   t = scaling * x lora_a^T  [M, G r]  (+ tt = t^T);   y = x w^T + t_g B_g^T
+ *   backward (2 launches with `flags`)         u_g = scaling * dy_g B_g  (+ ut);   dx = sum_g dy_g W_g + u lora_a
+ *                                              dA += u^T x  [G r, K];   dB_g += dy_g^T t_g  [N, r]   (fp32, accumulated)
+ *
+ * dy[g] are G separate [M, N] gradients (their own row pitches lddy[g]); dx may be NULL (cross-attention k / v: the prompt
+ * embeddings need no gradient).  G > 1 needs r % 8 == 0.  bias only for G = 1.  Phases and scratch as psob200_lora_linear_args.
+ */
+#define PSOB200_MAX_GROUP 3
+typedef struct psob200_lora_group_args {
+  const void* x;
+  const void* w;
+  const void* bias;
+  const void* lora_a;
+  const void* lora_b;
+  void* y;
+  void* t;
+  void* tt;
+  const void* dy[PSOB200_MAX_GROUP];
+  void* dx;
+  void* u;
+  void* ut;
+  float* d_lora_a;
+  float* d_lora_b;
+  int32_t* flags;
+  int64_t flags_len;
+  int64_t ldx, ldw, lda, ldb, ldy, ldt, ldtt, lddy[PSOB200_MAX_GROUP], lddx, ldu, ldut, ld_da, ld_db;
+  int64_t M, K, N, r;
+  int32_t G;
+  float scaling;
+  int32_t dtype;
+  int32_t bias_dtype;
+  int32_t adapters_enabled;
+  int32_t forward_phases;
+  int32_t backward_phases;
+} psob200_lora_group_args;
+
+PSOB200_API int psob200_lora_group_forward(const psob200_lora_group_args* args, void* stream);
+PSOB200_API int psob200_lora_group_backward(const psob200_lora_group_args* args, void* stream);
 
 /*
  * Optimizer boundary over the FLAT LoRA buffers (one fp32 buffer each for parameters, gradients and the two Adam
@@ -539,7 +591,7 @@ PSOB200_API int psob200_clip_preprocess(const psob200_clip_preprocess_args* args
  * verify their mirror of this header: which = 0 schedule, 1 online_pso_args,
  * 2 dreambooth_args, 3 step_args, 4 step_bwd_args, 5 gemm_args,
  * 6 lora_linear_args, 7 flat_adamw_args, 8 geglu_args,
- * 9 flat_allreduce_args, 10 clip_preprocess_args.  Returns 0 for unknown ids. */
+ * 9 flat_allreduce_args, 10 clip_preprocess_args, 11 lora_group_args.  Returns 0 for unknown ids. */
 PSOB200_API size_t psob200_struct_size(int which);
 
 #ifdef __cplusplus

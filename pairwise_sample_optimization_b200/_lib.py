@@ -87,7 +87,18 @@ class LoraLinearArgs(C.Structure):
                 ("ldu", C.c_int64), ("ldut", C.c_int64), ("ld_da", C.c_int64), ("ld_db", C.c_int64),
                 ("M", C.c_int64), ("K", C.c_int64), ("N", C.c_int64), ("r", C.c_int64), ("scaling", C.c_float),
                 ("dtype", C.c_int32), ("bias_dtype", C.c_int32), ("adapters_enabled", C.c_int32),
-                ("backward_phases", C.c_int32), ("forward_phases", C.c_int32)]
+                ("backward_phases", C.c_int32), ("forward_phases", C.c_int32), ("flags", _vp), ("flags_len", C.c_int64)]
+
+
+class LoraGroupArgs(C.Structure):
+    _fields_ = [("x", _vp), ("w", _vp), ("bias", _vp), ("lora_a", _vp), ("lora_b", _vp), ("y", _vp), ("t", _vp), ("tt", _vp),
+                ("dy", _vp * 3), ("dx", _vp), ("u", _vp), ("ut", _vp), ("d_lora_a", _fp), ("d_lora_b", _fp), ("flags", _vp),
+                ("flags_len", C.c_int64), ("ldx", C.c_int64), ("ldw", C.c_int64), ("lda", C.c_int64), ("ldb", C.c_int64),
+                ("ldy", C.c_int64), ("ldt", C.c_int64), ("ldtt", C.c_int64), ("lddy", C.c_int64 * 3), ("lddx", C.c_int64),
+                ("ldu", C.c_int64), ("ldut", C.c_int64), ("ld_da", C.c_int64), ("ld_db", C.c_int64), ("M", C.c_int64),
+                ("K", C.c_int64), ("N", C.c_int64), ("r", C.c_int64), ("G", C.c_int32), ("scaling", C.c_float),
+                ("dtype", C.c_int32), ("bias_dtype", C.c_int32), ("adapters_enabled", C.c_int32),
+                ("forward_phases", C.c_int32), ("backward_phases", C.c_int32)]
 
 
 class FlatAdamwArgs(C.Structure):
@@ -118,7 +129,7 @@ class ClipPreprocessArgs(C.Structure):
 
 
 _STRUCTS = {0: Schedule, 1: OnlinePsoArgs, 2: DreamboothArgs, 3: StepArgs, 4: StepBwdArgs, 5: GemmArgs,
-            6: LoraLinearArgs, 7: FlatAdamwArgs, 8: GegluArgs, 9: FlatAllreduceArgs, 10: ClipPreprocessArgs}
+            6: LoraLinearArgs, 7: FlatAdamwArgs, 8: GegluArgs, 9: FlatAllreduceArgs, 10: ClipPreprocessArgs, 11: LoraGroupArgs}
 
 # name -> (restype, argtypes): every symbol include/psob200.h declares
 SIGNATURES = {
@@ -138,6 +149,8 @@ SIGNATURES = {
     "psob200_lora_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "psob200_lora_linear_forward": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
     "psob200_lora_linear_backward": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
+    "psob200_lora_group_forward": (C.c_int, [C.POINTER(LoraGroupArgs), _vp]),
+    "psob200_lora_group_backward": (C.c_int, [C.POINTER(LoraGroupArgs), _vp]),
     "psob200_flat_adamw_step": (C.c_int, [C.POINTER(FlatAdamwArgs), _vp]),
     "psob200_flat_allreduce_sumsq": (C.c_int, [C.POINTER(FlatAllreduceArgs), _vp]),
     "psob200_geglu_forward": (C.c_int, [C.POINTER(GegluArgs), _vp]),

@@ -55,6 +55,7 @@ extern "C" size_t psob200_struct_size(int which) {
     case 8: return sizeof(psob200_geglu_args);
     case 9: return sizeof(psob200_flat_allreduce_args);
     case 10: return sizeof(psob200_clip_preprocess_args);
+    case 11: return sizeof(psob200_lora_group_args);
     default: return 0;
   }
 }

@@ -1,18 +1,24 @@
 // LoRA projection GEMMs on the 5th-generation tensor cores (sm_100a): TMA-fed tcgen05.mma with the
 // accumulators in tensor memory.
 //
-// One persistent, warp-specialised kernel computes
+// One persistent, warp-specialised kernel runs a short LIST OF PROBLEMS per launch; each problem is
 //
-//     D[M,N] = alpha * ( A1[M,K1] * B1[N,K1]^T  +  A2[M,K2] * B2[N,K2]^T ) + bias[N]
+//     D[M,N] = alpha * sum_s  A_s[M,K_s] * B_s[N,K_s]^T  + bias[N]              (up to 4 reduction segments)
 //
-// The second K segment is what makes the LoRA-wrapped projection ONE tensor-core pass over the frozen
-// weight instead of the reference stack's three GEMMs + scale + add (peft lora.Linear.forward, reached from
-// train_online_pso_sdxl_turbo.py:338-345):   y = x W^T + b + (s x A^T) B^T   is   [x | T] [W | B]^T  with
-// T = s x A^T  a skinny first pass of the same kernel.  The backward uses the same two shapes
-// (dX = dY W + U A with U = s dY B) plus a split-M reduction with MN-major A operand for dA / dB.
+// * Two segments make the LoRA-wrapped projection ONE tensor-core pass over the frozen weight instead of the reference
+//   stack's three GEMMs + scale + add (peft lora.Linear.forward, reached from train_online_pso_sdxl_turbo.py:338-345):
+//   y = x W^T + b + (s x A^T) B^T  is  [x | T] [W | B]^T  with  T = s x A^T.
+// * Several problems in one launch + a flag per row block make T a tile of the SAME launch: the tiles of the skinny
+//   problem T = s x A^T come first in the tile list and release flags[m_blk] when their rows are stored; a tile of the
+//   main problem waits for its flag only before the first TMA load of the adapter segment.  All CTAs of the persistent
+//   grid are co-resident, so the wait cannot deadlock.  The backward uses the same scheme (U = s dY B, then
+//   dX = dY W + U A); the weight gradients dA = U^T X and dB = dY^T T run as independent problems of one launch.
+// * Projections that share their input (attention to_q / to_k / to_v, cross-attention to_k / to_v) are STACKED: one
+//   problem over the concatenated weight [G N, K] whose adapter segment reads column group g of the stacked T, and in
+//   the backward one dX problem whose segments walk the G gradients.
 //
 // Warp roles (256 threads, 1 CTA per SM, grid = min(tiles, SMs), static round-robin tile schedule):
-//   warp 0      TMA producer: 128B-swizzled [128 x 64] A and [bn x 64] B boxes into a 4-stage ring (192 KB)
+//   warp 0      TMA producer: 128B-swizzled [128 x 64] A and [bn x 64] B boxes into a ring of stages
 //   warp 1      MMA issuer: one thread, 4 x tcgen05.mma (128 x bn x 16) per stage, tcgen05.commit frees the stage
 //   warp 2      tensor-memory allocator (512 columns = two accumulator buffers of <= 256 columns)
 //   warps 4-7   epilogue: tcgen05.ld 32x32b -> alpha, bias, convert -> global (also a transposed copy, or
@@ -36,19 +42,83 @@ constexpr int kStageBBytes = kBNMax * kBK * 2;   // 32 KB
 constexpr int kGemmSmemBytes = kStages * (kStageABytes + kStageBBytes) + 1024;  // + slack for 1024 B alignment
 constexpr int kTmemCols = 512;
 
-struct GemmKernelParams {
-  long long M, N;         // output extent
-  int nk1, nk2;           // 64-wide k-blocks of the two segments
-  int bn;                 // tile width, multiple of 16, <= 256
-  int m_tiles, n_tiles, splits, kb_per_split;
-  void* d; long long ldd;     // row-major output (may be null)
-  void* dt; long long lddt;   // transposed output [N, M] (may be null)
-  const void* bias;
-  float alpha;
-  int d_dtype, bias_dtype, ab_format, a_mn, b_mn, atomic, diag;
-  int stages;             // even; stage = 16 KB of A + bn*128 B of B
-  int pdl;                // programmatic dependent launch role bits (psob200_gemm_args.pdl)
+constexpr int kMaxSeg = 4;    // reduction segments per problem
+constexpr int kMaxProb = 4;   // problems per launch
+constexpr int kMaxMaps = 8;   // tensor maps per launch
+
+struct GemmMaps {
+  CUtensorMap m[kMaxMaps];
 };
+
+// One GEMM of the launch.  Tiles [tile0, tile0 + m_tiles * n_tiles * splits) of the launch's tile list belong to it,
+// n fastest, then m, then the split of the reduction.
+struct GemmProblem {
+  long long M, N;           // output extent
+  void* d;                  // row-major output [M, N] (may be null)
+  void* dt;                 // transposed output [N, M] (may be null)
+  const void* bias;
+  long long ldd, lddt;
+  long long group_n;        // stacked projections: output columns per group (>= N: one group); a tile never straddles groups
+  int tile0, m_tiles, n_tiles, tiles_per_group, splits, kb_per_split;
+  int bn;                   // tile width, multiple of 16, <= 256
+  int n_seg, nk_total;
+  int nk[kMaxSeg];          // 64-wide k-blocks per segment
+  int map_a[kMaxSeg], map_b[kMaxSeg];
+  int a_koff[kMaxSeg];      // A box: constant element offset along k (a column slice of a stacked buffer) ...
+  int a_gkoff[kMaxSeg];     // ... plus this per column group of the tile (group g of the stacked T / U)
+  int b_off[kMaxSeg];       // B box: constant offset along its row axis (the n coordinate; the k coordinate if B is reduction-major)
+  float alpha;
+  int bias_dtype;
+  int signal;               // != 0: every tile releases flags[m_blk] once its rows are stored
+  int wait_seg, wait_count; // wait_seg >= 0: the first load of that segment waits until wait_count tiles released flags[m_blk]
+};
+
+struct GemmLaunch {
+  GemmProblem prob[kMaxProb];
+  int n_prob;
+  int total_tiles;
+  int ab_format, a_mn, b_mn, atomic, diag;
+  int stages;               // even; stage = 16 KB of A + stage_b_bytes of B
+  int stage_b_bytes;        // of the widest problem
+  int pdl;                  // programmatic dependent launch role bits (psob200_gemm_args.pdl)
+  int* flags;               // n_flags row-block counters + 1 exit ticket, zero on entry, zeroed again by the last CTA
+  int n_flags;
+};
+
+struct TileInfo {
+  int p, m_blk, group, kb0, kb1;
+  long long n0, n_end;
+};
+
+__device__ __forceinline__ void decode_tile(const GemmLaunch& L, int t, TileInfo& ti) {
+  int p = 0;
+  while (p + 1 < L.n_prob && t >= L.prob[p + 1].tile0) ++p;
+  const GemmProblem& P = L.prob[p];
+  int loc = t - P.tile0;
+  const int n_blk = loc % P.n_tiles;
+  loc /= P.n_tiles;
+  ti.p = p;
+  ti.m_blk = loc % P.m_tiles;
+  const int split = loc / P.m_tiles;
+  ti.kb0 = split * P.kb_per_split;
+  ti.kb1 = ti.kb0 + P.kb_per_split < P.nk_total ? ti.kb0 + P.kb_per_split : P.nk_total;
+  ti.group = n_blk / P.tiles_per_group;
+  ti.n0 = (long long)ti.group * P.group_n + (long long)(n_blk - ti.group * P.tiles_per_group) * P.bn;
+  long long e = ti.n0 + P.bn;                         // a tile stops at the end of its column group and at N
+  const long long ge = (long long)(ti.group + 1) * P.group_n;
+  if (e > ge) e = ge;
+  if (e > P.N) e = P.N;
+  ti.n_end = e;
+}
+
+// Spin until `count` releases have reached *flag (acquire), then order the TMA (async proxy) reads behind it.
+__device__ __forceinline__ void wait_flag(const int* flag, int count) {
+  int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+  } while (v < count);
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
 
 template <typename T>
 __device__ __forceinline__ T cvt_out(float v);
@@ -82,14 +152,15 @@ __device__ __forceinline__ void load_bias32(const void* bias, long long n0, long
 }
 
 // Epilogue mode (compile time): bits 0-1 = outputs (1: row-major d only, 2: transposed dt only, 3: whichever pointers are
-// set, checked at run time), bit 2 = a bias may be present.  The hot launches of the training step get exact modes so that
-// their instruction footprint stays small (see lora_gemm_kernel); mode 7 is the general case.
+// set, checked at run time), bit 2 = a bias may be present, bit 3 = it has the output's element type.  The hot launches of
+// the training step get exact modes so that their instruction footprint stays small; mode 7 is the general case.
 constexpr int kEpiD = 1, kEpiDt = 2, kEpiAnyOut = 3, kEpiBias = 4, kEpiGeneral = 7;
 constexpr int kEpiBiasSameType = 8 | kEpiBias;  // the bias has the output's element type (nn.Linear in one dtype)
+constexpr int kEpiFused = kEpiAnyOut | kEpiBiasSameType;  // problem lists: outputs and bias differ per problem
 
 // One 32-column chunk of one accumulator row: v[j] belongs to (row, n0 + j).
 template <typename TD, bool kAtomic, int kMode>
-__device__ __forceinline__ void store_chunk(const GemmKernelParams& p, const float (&v)[32], long long row, long long n0,
+__device__ __forceinline__ void store_chunk(const GemmProblem& p, const float (&v)[32], long long row, long long n0,
                                             long long n_end) {
   if (row >= p.M) return;
   const long long nleft = n_end - n0;  // columns of this chunk that belong to this tile and exist
@@ -143,10 +214,9 @@ __device__ __forceinline__ void store_chunk(const GemmKernelParams& p, const flo
 // Drain one accumulator tile: TMEM -> registers (the load of chunk c+1 is in flight while chunk c is converted and
 // stored) -> alpha, bias -> global.
 template <typename TD, bool kAtomic, int kMode>
-__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_t taddr, long long row, long long n_tile0,
-                                              bool add_bias) {
+__device__ __forceinline__ void epilogue_tile(const GemmProblem& p, int diag, uint32_t taddr, long long row, long long n_tile0,
+                                              long long n_end, bool add_bias) {
   const int chunks = (p.bn + 31) / 32;
-  const long long n_end = n_tile0 + p.bn < p.N ? n_tile0 + p.bn : p.N;  // a chunk must not spill into the next tile
   uint32_t raw[2][32];
   ptx::tmem_ld_32x32(taddr, raw[0]);
 #pragma unroll 1
@@ -155,7 +225,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_
     for (int h = 0; h < 2; ++h) {
       const int cc = c + h;
       const long long n0 = n_tile0 + (long long)cc * 32;
-      if (cc < chunks && n0 < p.N) {  // uniform over the warp
+      if (cc < chunks && n0 < n_end) {  // uniform over the warp
         ptx::tmem_ld_wait();
         if (cc + 1 < chunks) ptx::tmem_ld_32x32(taddr + (uint32_t)(cc + 1) * 32, raw[h ^ 1]);
         float v[32];
@@ -171,7 +241,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(raw[h][j]);
         }
-        if (!(p.diag & 2)) store_chunk<TD, kAtomic, kMode>(p, v, row, n0, n_end);
+        if (!(diag & 2)) store_chunk<TD, kAtomic, kMode>(p, v, row, n0, n_end);
       }
     }
   }
@@ -184,9 +254,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_
 // kernels in between, only 18.4 us with the OPERANDS evicted instead).
 template <typename TD, bool kAtomic, int kMode>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
-                 const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
-                 const GemmKernelParams p) {
+lora_gemm_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmLaunch L) {
   extern __shared__ unsigned char gemm_smem_raw[];
   // one "full" barrier per stage, one "empty" barrier per PAIR of stages: tcgen05.commit costs several hundred
   // cycles of tensor-pipe command time, so the MMA warp commits every second k-block only
@@ -195,21 +263,19 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
 
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_a = smem;
-  const int n_stages = p.stages;
-  const int stage_b_bytes = p.bn * kBK * 2;
+  const int n_stages = L.stages;
+  const int stage_b_bytes = L.stage_b_bytes;
   unsigned char* smem_b = smem + n_stages * kStageABytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nk = p.nk1 + p.nk2;
-  const long long total_tiles = (long long)p.m_tiles * p.n_tiles * p.splits;
+  const int total_tiles = L.total_tiles;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&map_a1);
-    ptx::prefetch_tensormap(&map_b1);
-    if (p.nk2 > 0) {
-      ptx::prefetch_tensormap(&map_a2);
-      ptx::prefetch_tensormap(&map_b2);
-    }
+    for (int p = 0; p < L.n_prob; ++p)
+      for (int s = 0; s < L.prob[p].n_seg; ++s) {
+        ptx::prefetch_tensormap(&maps.m[L.prob[p].map_a[s]]);
+        ptx::prefetch_tensormap(&maps.m[L.prob[p].map_b[s]]);
+      }
   }
   if (warp == 1 && lane == 0) {
 #pragma unroll
@@ -225,21 +291,12 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
   }
   // primary of a programmatic dependent launch: the dependent grid (the main GEMM that needs this launch's output only
   // for its last k-blocks) may start filling the SMs this small grid leaves idle
-  if (p.pdl & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (L.pdl & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 2) ptx::tmem_alloc<kTmemCols>(&tmem_base_slot);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
-
-  auto tile_coords = [&](long long t, int& m_blk, int& n_blk, int& kb0, int& kb1) {
-    n_blk = (int)(t % p.n_tiles);
-    t /= p.n_tiles;
-    m_blk = (int)(t % p.m_tiles);
-    const int split = (int)(t / p.m_tiles);
-    kb0 = split * p.kb_per_split;
-    kb1 = kb0 + p.kb_per_split < nk ? kb0 + p.kb_per_split : nk;
-  };
 
   // The producer and MMA loops run WARP-UNIFORMLY (all 32 lanes keep the loop state) and only the issuing
   // instructions are predicated on elect.sync: UTMALDG / UTCHMMA take uniform-register operands, and a loop that
@@ -247,88 +304,99 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
   // ~450 cycles per k-block, more than the MMAs themselves).
   if (warp == 0) {
     // ================================================================= TMA producer
-    const uint32_t tx = ((p.diag & 8) ? 0u : (uint32_t)kStageABytes) + ((p.diag & 4) ? 0u : (uint32_t)p.bn * kBK * 2u);
     int stage = 0;
     uint32_t phase = 0;
-    bool dep_pending = (p.pdl & 2) != 0;  // launched ahead of the grid that produces a2 (or, bit 2, any operand)
-    if (dep_pending && (p.pdl & 4)) {
+    bool dep_pending = (L.pdl & 2) != 0;  // launched ahead of the grid that produces segment 1's A (or, bit 2, any operand)
+    if (dep_pending && (L.pdl & 4)) {
       asm volatile("griddepcontrol.wait;" ::: "memory");
       asm volatile("fence.proxy.async;" ::: "memory");
       dep_pending = false;
     }
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      int m_blk, n_blk, kb0, kb1;
-      tile_coords(t, m_blk, n_blk, kb0, kb1);
-      const int m0 = m_blk * kBM, n0 = n_blk * p.bn;
-      for (int kb = kb0; kb < kb1; ++kb) {
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      TileInfo ti;
+      decode_tile(L, t, ti);
+      const GemmProblem& P = L.prob[ti.p];
+      const uint32_t tx = ((L.diag & 8) ? 0u : (uint32_t)kStageABytes) + ((L.diag & 4) ? 0u : (uint32_t)P.bn * kBK * 2u);
+      const int m0 = ti.m_blk * kBM, n0 = (int)ti.n0;
+      // segment of the tile's first k-block
+      int seg = 0, kbs = ti.kb0;
+      while (kbs >= P.nk[seg]) { kbs -= P.nk[seg]; ++seg; }
+      bool need_wait = P.wait_seg >= 0;
+      for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
         if ((stage & 1) == 0) ptx::mbar_wait(&empty_bar[stage >> 1], phase ^ 1u);  // the pair (stage, stage+1) is free
-        const bool seg2 = kb >= p.nk1;
-        if (seg2 && dep_pending) {  // first read of the previous launch's output: wait for that grid, then fence the
+        if (seg >= 1 && dep_pending) {  // first read of the previous launch's output: wait for that grid, then fence the
           asm volatile("griddepcontrol.wait;" ::: "memory");  // generic-proxy writes against the TMA (async proxy) reads
           asm volatile("fence.proxy.async;" ::: "memory");
           dep_pending = false;
         }
-        const CUtensorMap* ma = seg2 ? &map_a2 : &map_a1;
-        const CUtensorMap* mb = seg2 ? &map_b2 : &map_b1;
-        const int kk = (seg2 ? kb - p.nk1 : kb) * kBK;
+        if (need_wait && seg >= P.wait_seg) {  // the operand of this segment is produced by other tiles of THIS launch
+          wait_flag(L.flags + ti.m_blk, P.wait_count * 4);
+          need_wait = false;
+        }
+        const CUtensorMap* ma = &maps.m[P.map_a[seg]];
+        const CUtensorMap* mb = &maps.m[P.map_b[seg]];
+        const int ka = kbs * kBK + P.a_koff[seg] + ti.group * P.a_gkoff[seg];
+        const int kk = kbs * kBK;
+        const int boff = P.b_off[seg];
         unsigned char* sa = smem_a + stage * kStageABytes;
         unsigned char* sb = smem_b + stage * stage_b_bytes;
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full_bar[stage], tx);
-          if (p.diag & 8) {
-          } else if (p.a_mn) {  // A given reduction-major: two [64 k x 64 m] boxes, m contiguous
-            ptx::tma_load_2d(sa, ma, m0, kk, &full_bar[stage]);
-            ptx::tma_load_2d(sa + kStageABytes / 2, ma, m0 + 64, kk, &full_bar[stage]);
+          if (L.diag & 8) {
+          } else if (L.a_mn) {  // A given reduction-major: two [64 k x 64 m] boxes, m contiguous
+            ptx::tma_load_2d(sa, ma, m0, ka, &full_bar[stage]);
+            ptx::tma_load_2d(sa + kStageABytes / 2, ma, m0 + 64, ka, &full_bar[stage]);
           } else {
-            ptx::tma_load_2d(sa, ma, kk, m0, &full_bar[stage]);
+            ptx::tma_load_2d(sa, ma, ka, m0, &full_bar[stage]);
           }
-          if (p.diag & 4) {
-          } else if (p.b_mn) {  // B given reduction-major: bn/64 boxes of [64 k x 64 n], n contiguous
-            for (int j = 0; j < p.bn / 64; ++j)
-              ptx::tma_load_2d(sb + j * (kBK * 128), mb, n0 + 64 * j, kk, &full_bar[stage]);
+          if (L.diag & 4) {
+          } else if (L.b_mn) {  // B given reduction-major: bn/64 boxes of [64 k x 64 n], n contiguous
+            for (int j = 0; j < P.bn / 64; ++j)
+              ptx::tma_load_2d(sb + j * (kBK * 128), mb, n0 + 64 * j, kk + boff, &full_bar[stage]);
           } else {
-            ptx::tma_load_2d(sb, mb, kk, n0, &full_bar[stage]);
+            ptx::tma_load_2d(sb, mb, kk, n0 + boff, &full_bar[stage]);
           }
         }
         __syncwarp();
         if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        if (++kbs == P.nk[seg]) { kbs = 0; ++seg; }
       }
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
-    const uint32_t idesc = ptx::umma_idesc_f16((uint32_t)p.ab_format, (uint32_t)p.a_mn, (uint32_t)p.b_mn, (uint32_t)p.bn);
     // per-k-step advance of the descriptor start address (>> 4) and the constant upper halves:
     //   K-major, 128B swizzle: 8-row atoms 1024 B apart (SBO); a 16-element k step is 32 B inside the swizzle span.
     //   reduction-major ("MN-major"): 64(mn) x 8(k) atoms, 1024 B between k atoms (SBO), 64 k-rows * 128 B between
     //   mn atoms (LBO); a 16-row k step is 2048 B.
-    const uint64_t a_hi = ptx::smem_desc_sw128(0, p.a_mn ? kBK * 128 : 0, 1024);
-    const uint64_t b_hi = ptx::smem_desc_sw128(0, p.b_mn ? kBK * 128 : 0, 1024);
-    const uint32_t a_step = p.a_mn ? 2048u >> 4 : 32u >> 4, b_step = p.b_mn ? 2048u >> 4 : 32u >> 4;
+    const uint64_t a_hi = ptx::smem_desc_sw128(0, L.a_mn ? kBK * 128 : 0, 1024);
+    const uint64_t b_hi = ptx::smem_desc_sw128(0, L.b_mn ? kBK * 128 : 0, 1024);
+    const uint32_t a_step = L.a_mn ? 2048u >> 4 : 32u >> 4, b_step = L.b_mn ? 2048u >> 4 : 32u >> 4;
     int stage = 0;
     uint32_t phase = 0;
-    long long iter = 0;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
-      int m_blk, n_blk, kb0, kb1;
-      tile_coords(t, m_blk, n_blk, kb0, kb1);
-      const int acc = (int)(iter & 1);
+    int iter = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+      TileInfo ti;
+      decode_tile(L, t, ti);
+      const uint32_t idesc = ptx::umma_idesc_f16((uint32_t)L.ab_format, (uint32_t)L.a_mn, (uint32_t)L.b_mn, (uint32_t)L.prob[ti.p].bn);
+      const int acc = iter & 1;
       const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * kBNMax;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after_sync();
         const uint64_t a_desc = a_hi | (uint64_t)((ptx::smem_addr(smem_a + stage * kStageABytes) >> 4) & 0x3FFFu);
         const uint64_t b_desc = b_hi | (uint64_t)((ptx::smem_addr(smem_b + stage * stage_b_bytes) >> 4) & 0x3FFFu);
         if (ptx::elect_one()) {
-          if (!(p.diag & 1)) {
+          if (!(L.diag & 1)) {
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
               ptx::umma_f16(d_tmem, a_desc + (uint64_t)(k * a_step), b_desc + (uint64_t)(k * b_step), idesc,
-                            (kb > kb0 || k > 0) ? 1u : 0u);
+                            (kb > ti.kb0 || k > 0) ? 1u : 0u);
           }
-          if (stage & 1) ptx::umma_commit(&empty_bar[stage >> 1]);   // the pair is reusable once these MMAs retire
-          if (kb == kb1 - 1) ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+          if (stage & 1) ptx::umma_commit(&empty_bar[stage >> 1]);      // the pair is reusable once these MMAs retire
+          if (kb == ti.kb1 - 1) ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete
         }
         __syncwarp();
         if (++stage == n_stages) { stage = 0; phase ^= 1u; }
@@ -337,22 +405,27 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
   } else if (warp >= 4) {
     // ================================================================= epilogue (TMEM lanes 32*(warp%4) ..)
     const int ew = warp - 4;
-    long long iter = 0;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
-      int m_blk, n_blk, kb0, kb1;
-      tile_coords(t, m_blk, n_blk, kb0, kb1);
-      const int acc = (int)(iter & 1);
+    int iter = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+      TileInfo ti;
+      decode_tile(L, t, ti);
+      const GemmProblem& P = L.prob[ti.p];
+      const int acc = iter & 1;
       const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
-      const long long row = (long long)m_blk * kBM + ew * 32 + lane;
-      const long long n_tile0 = (long long)n_blk * p.bn;
-      const bool add_bias = p.bias != nullptr && kb0 == 0;
+      const long long row = (long long)ti.m_blk * kBM + ew * 32 + lane;
+      const bool add_bias = P.bias != nullptr && ti.kb0 == 0;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kBNMax;
-      epilogue_tile<TD, kAtomic, kMode>(p, taddr, row, n_tile0, add_bias);
+      epilogue_tile<TD, kAtomic, kMode>(P, L.diag, taddr, row, ti.n0, ti.n_end, add_bias);
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      if (P.signal) {  // these rows are an operand of other tiles of this launch: publish them (4 warps = one tile)
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(L.flags + ti.m_blk, 1);
+      }
     }
   }
 
@@ -362,9 +435,17 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<kTmemCols>(tmem_base);
   }
+  if (L.flags != nullptr && threadIdx.x == 0) {  // the last CTA to leave zeroes the flags for the next launch
+    __threadfence();
+    const int done = atomicAdd(L.flags + L.n_flags, 1);
+    if (done == (int)gridDim.x - 1) {
+      for (int i = 0; i <= L.n_flags; ++i) L.flags[i] = 0;
+      __threadfence();
+    }
+  }
   // an independent dependent launch (bit 3): it never reads the previous grid's output, but it must not be seen as
   // complete before that grid is, so that later launches on the stream stay ordered after both
-  if ((p.pdl & 8) && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if ((L.pdl & 8) && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 }  // namespace psob200
@@ -442,20 +523,300 @@ static int choose_bn(long long N, bool b_mn) {
 // is (number of waves) x (time of one tile) and a tile costs ~ its width plus a fixed part (pipeline fill, drain of the last
 // accumulator): pick the width that minimises waves x (bn + fixed) instead of always 256.  E.g. M = 8192, N = 1280 on 74
 // pairs: 256 -> 160 tiles = 3 waves, 224 -> 192 tiles = 3 narrower waves (measured 29.0 -> 26.4 us).  Widths that are not
-// multiples of 32 are excluded (bn = 144 measured 30 % slower than the model predicts).
-static int choose_bn2(long long M, long long N, bool b_mn, int pairs) {
+// multiples of 32 are excluded (bn = 144 measured 30 % slower than the model predicts).  `groups` column groups of `N` columns
+// each are tiled separately (a tile never straddles two stacked projections); `other_tiles` = tiles of the launch's other problems.
+static int choose_bn2(long long M, long long N, int groups, bool b_mn, int pairs, long long other_tiles) {
   const int unit = b_mn ? 128 : 32;
-  if (N < 256) return (int)(((N + (b_mn ? 127 : 31)) / (b_mn ? 128 : 32)) * (b_mn ? 128 : 32));
+  if (N < 256) return (int)(((N + unit - 1) / unit) * unit);
   const long long m_tiles = (M + 255) / 256;
   int best = 256;
   long long best_cost = -1;
   for (int bn = 256; bn >= 128; bn -= unit) {
-    const long long tiles = m_tiles * ((N + bn - 1) / bn);
+    const long long tiles = m_tiles * groups * ((N + bn - 1) / bn) + other_tiles;
     const long long waves = (tiles + pairs - 1) / pairs;
     const long long cost = waves * (bn + kTileFixedCols);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
+}
+
+// ---- host description of a launch: what the C-ABI entry points assemble ---------------------------------------------
+struct HostSeg {
+  const void* a; long long lda, a_rows, a_cols;   // the matrix the A map describes ([M, cols] K-major, or [K, M] reduction-major)
+  const void* b; long long ldb, b_rows, b_cols;   // the matrix the B map describes ([N.., K] K-major, or [K.., N] reduction-major)
+  long long K;                                    // reduction length of the segment
+  int a_koff, a_gkoff, b_off;
+};
+struct HostProblem {
+  long long M, N;
+  int n_seg;
+  HostSeg seg[kMaxSeg];
+  void* d; long long ldd; void* dt; long long lddt;
+  const void* bias; int bias_dtype;
+  float alpha;
+  long long group_n;  // 0: one column group
+  int signal, wait_seg, wait_count;
+  int tune_bn;
+};
+struct HostLaunch {
+  HostProblem prob[kMaxProb];
+  int n_prob;
+  int ab_dtype, d_dtype, a_mn, b_mn, accumulate, split_k, pdl, diag;
+  int* flags; long long flags_len;
+};
+
+struct MapKey { const void* p; long long rows, cols, ld; int box; };
+
+static int launch_problems(const HostLaunch& H, cudaStream_t stream) {
+  if (H.n_prob < 1 || H.n_prob > kMaxProb) return PSOB200_ERR_INVALID_ARG;
+  const int sms = gemm_sm_count();
+  bool any_dep = false, any_dt = false, any_bias = false, bias_other = false, all_d = true;
+  for (int i = 0; i < H.n_prob; ++i) {
+    const HostProblem& hp = H.prob[i];
+    if (hp.M <= 0 || hp.N <= 0 || hp.n_seg < 1 || hp.n_seg > kMaxSeg || (!hp.d && !hp.dt)) return PSOB200_ERR_INVALID_ARG;
+    if ((hp.d && hp.ldd < hp.N) || (hp.dt && hp.lddt < hp.M)) return PSOB200_ERR_SHAPE;
+    if (hp.M > 0x7fffffffLL - 256 || hp.N > 0x7fffffffLL - 256) return PSOB200_ERR_SHAPE;
+    if (H.a_mn && hp.n_seg != 1) return PSOB200_ERR_INVALID_ARG;
+    for (int s = 0; s < hp.n_seg; ++s) {
+      const HostSeg& sg = hp.seg[s];
+      if (!sg.a || !sg.b || sg.K <= 0 || sg.K > 0x7fffffffLL - 256) return PSOB200_ERR_INVALID_ARG;
+      if (!aligned16(sg.a) || !aligned16(sg.b)) return PSOB200_ERR_ALIGNMENT;
+      if (sg.lda <= 0 || (sg.lda % 8) != 0 || sg.ldb <= 0 || (sg.ldb % 8) != 0) return PSOB200_ERR_SHAPE;  // TMA: 16-byte row pitch
+    }
+    any_dep |= hp.signal != 0 || hp.wait_seg >= 0;
+    any_dt |= hp.dt != nullptr;
+    all_d &= hp.d != nullptr && hp.dt == nullptr;
+    any_bias |= hp.bias != nullptr;
+    bias_other |= hp.bias != nullptr && hp.bias_dtype != H.d_dtype;
+    if (hp.bias && !valid_dtype(hp.bias_dtype)) return PSOB200_ERR_DTYPE;
+  }
+  if (H.ab_dtype != PSOB200_BF16 && H.ab_dtype != PSOB200_F16) return PSOB200_ERR_DTYPE;
+  if (!valid_dtype(H.d_dtype)) return PSOB200_ERR_DTYPE;
+  if (H.accumulate && H.d_dtype != PSOB200_F32) return PSOB200_ERR_DTYPE;
+  if (H.split_k < 0 || (H.split_k > 1 && !H.accumulate)) return PSOB200_ERR_INVALID_ARG;
+  if (any_dep && (H.accumulate || H.split_k > 1 || H.flags == nullptr)) return PSOB200_ERR_INVALID_ARG;
+
+  // ---- kernel: CTA pairs (cta_group::2) when the launch has at least half a wave of 256-row pair tiles
+  const HostProblem& big = H.prob[H.n_prob - 1];  // the main problem is listed last
+  const int big_groups = big.group_n > 0 ? (int)((big.N + big.group_n - 1) / big.group_n) : 1;
+  const long long big_gn = big.group_n > 0 ? big.group_n : big.N;
+  bool pair = false;
+  int big_bn2 = 0;
+  {
+    const int unit = H.b_mn ? 128 : 16;
+    const bool eligible = !H.a_mn && !H.accumulate && H.split_k <= 1 &&
+                          (big.tune_bn == 0 || (big.tune_bn % unit == 0 && big.tune_bn >= 32));
+    long long other = 0;
+    for (int i = 0; i + 1 < H.n_prob; ++i) other += (H.prob[i].M + 255) / 256;  // the skinny problems: one tile per row block
+    big_bn2 = big.tune_bn > 0 ? big.tune_bn : choose_bn2(big.M, big_gn, big_groups, H.b_mn != 0, sms / 2, other);
+    const long long pair_tiles = ((big.M + 255) / 256) * big_groups * ((big_gn + big_bn2 - 1) / big_bn2);
+    const bool want = (H.diag & 0x10000) || (pair_tiles >= sms / 2 && big_gn >= 128 && !(H.diag & 0x20000));
+    pair = eligible && want && big_bn2 <= kBNMax;
+  }
+  const int tile_m = pair ? 256 : kBM;
+
+  GemmLaunch L = {};
+  GemmMaps maps = {};
+  MapKey keys[kMaxMaps];
+  int n_maps = 0;
+  auto get_map = [&](const void* p, long long rows, long long cols, long long ld, int box) -> int {
+    for (int i = 0; i < n_maps; ++i)
+      if (keys[i].p == p && keys[i].rows == rows && keys[i].cols == cols && keys[i].ld == ld && keys[i].box == box) return i;
+    if (n_maps == kMaxMaps) return -1;
+    if (make_map(&maps.m[n_maps], p, rows, cols, ld, box, H.ab_dtype) != PSOB200_OK) return -2;
+    keys[n_maps] = {p, rows, cols, ld, box};
+    return n_maps++;
+  };
+
+  L.n_prob = H.n_prob;
+  int tile0 = 0, max_bn = 0, max_m_tiles = 0;
+  long long base_tiles = 0;
+  for (int i = 0; i < H.n_prob; ++i) {
+    const HostProblem& hp = H.prob[i];
+    const int groups = hp.group_n > 0 ? (int)((hp.N + hp.group_n - 1) / hp.group_n) : 1;
+    const long long gn = hp.group_n > 0 ? hp.group_n : hp.N;
+    int bn;
+    if (pair) {
+      bn = (i == H.n_prob - 1) ? big_bn2 : (hp.tune_bn > 0 ? hp.tune_bn : choose_bn2(hp.M, gn, groups, H.b_mn != 0, sms / 2, 0));
+      if (bn < 32 || bn > kBNMax || (bn % (H.b_mn ? 128 : 16)) != 0) return PSOB200_ERR_INVALID_ARG;
+    } else {
+      bn = hp.tune_bn > 0 ? hp.tune_bn : choose_bn(gn, H.b_mn != 0);
+      if (bn < 16 || bn > kBNMax || (bn % (H.b_mn ? 64 : 16)) != 0) return PSOB200_ERR_INVALID_ARG;
+    }
+    GemmProblem& P = L.prob[i];
+    P.M = hp.M; P.N = hp.N;
+    P.d = hp.d; P.ldd = hp.ldd; P.dt = hp.dt; P.lddt = hp.lddt;
+    P.bias = hp.bias; P.bias_dtype = hp.bias_dtype; P.alpha = hp.alpha;
+    P.group_n = gn;
+    P.bn = bn;
+    P.m_tiles = (int)((hp.M + tile_m - 1) / tile_m);
+    P.tiles_per_group = (int)((gn + bn - 1) / bn);
+    P.n_tiles = groups * P.tiles_per_group;
+    P.n_seg = hp.n_seg;
+    P.nk_total = 0;
+    for (int s = 0; s < hp.n_seg; ++s) {
+      const HostSeg& sg = hp.seg[s];
+      P.nk[s] = (int)((sg.K + kBK - 1) / kBK);
+      P.nk_total += P.nk[s];
+      P.a_koff[s] = sg.a_koff; P.a_gkoff[s] = sg.a_gkoff; P.b_off[s] = sg.b_off;
+      const int ma = H.a_mn ? get_map(sg.a, sg.a_rows, sg.a_cols, sg.lda, kBK) : get_map(sg.a, sg.a_rows, sg.a_cols, sg.lda, kBM);
+      const int mb = H.b_mn ? get_map(sg.b, sg.b_rows, sg.b_cols, sg.ldb, kBK)
+                            : get_map(sg.b, sg.b_rows, sg.b_cols, sg.ldb, pair ? bn / 2 : bn);
+      if (ma == -2 || mb == -2) return PSOB200_ERR_DRIVER;
+      if (ma < 0 || mb < 0) return PSOB200_ERR_INVALID_ARG;
+      P.map_a[s] = ma; P.map_b[s] = mb;
+    }
+    P.signal = hp.signal; P.wait_seg = hp.wait_seg; P.wait_count = hp.wait_count;
+    P.splits = 1; P.kb_per_split = P.nk_total;
+    base_tiles += (long long)P.m_tiles * P.n_tiles;
+    if (bn > max_bn) max_bn = bn;
+    if (P.m_tiles > max_m_tiles) max_m_tiles = P.m_tiles;
+  }
+  // split the reduction only for accumulating launches that cannot fill the GPU: the largest split count whose tiles all fit
+  // on the SMs at once (rounding UP gave e.g. 150 tiles on 148 SMs: two CTAs ran two tiles each and the launch took twice as
+  // long; measured 12.2 -> 10.1 us for dA at M = 8192)
+  int splits = H.split_k;
+  if (splits == 0) {
+    splits = 1;
+    if (H.accumulate) {
+      splits = (int)(sms / base_tiles);
+      if (splits < 1) splits = 1;
+    }
+  }
+  for (int i = 0; i < H.n_prob; ++i) {
+    GemmProblem& P = L.prob[i];
+    int sp = splits > P.nk_total ? P.nk_total : splits;
+    P.kb_per_split = (P.nk_total + sp - 1) / sp;
+    P.splits = (P.nk_total + P.kb_per_split - 1) / P.kb_per_split;
+    P.tile0 = tile0;
+    const long long nt = (long long)P.m_tiles * P.n_tiles * P.splits;
+    if (nt + tile0 > 0x7fffffffLL) return PSOB200_ERR_SHAPE;
+    tile0 += (int)nt;
+  }
+  L.total_tiles = tile0;
+  {  // a waiting problem waits for EVERY tile of the signalling problems in its row block
+    int released = 0;
+    for (int i = 0; i < H.n_prob; ++i)
+      if (L.prob[i].signal) released += L.prob[i].n_tiles;
+    for (int i = 0; i < H.n_prob; ++i)
+      if (L.prob[i].wait_seg >= 0) {
+        if (released == 0 || L.prob[i].wait_seg >= L.prob[i].n_seg) return PSOB200_ERR_INVALID_ARG;
+        L.prob[i].wait_count = released;
+      }
+  }
+  L.ab_format = H.ab_dtype == PSOB200_BF16 ? 1 : 0;
+  L.a_mn = H.a_mn ? 1 : 0;
+  L.b_mn = H.b_mn ? 1 : 0;
+  L.atomic = H.accumulate ? 1 : 0;
+  L.diag = H.diag;
+  L.pdl = H.pdl;
+  if (any_dep) {
+    if (H.flags_len < max_m_tiles + 1) return PSOB200_ERR_WORKSPACE;
+    L.flags = H.flags;
+    L.n_flags = max_m_tiles;
+  }
+
+  typedef void (*KernelFn)(GemmMaps, GemmLaunch);
+  const bool multi = H.n_prob > 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (H.pdl & (2 | 8)) {  // may begin while the previous kernel on the stream is still running (it waits on the device)
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  if (pair) {
+    L.stages = kStages2;
+    L.stage_b_bytes = (max_bn / 2) * kBK * 2;
+    // 0-2: general per output type (any bias type); then per 16-bit type: bias of the same type, no bias, problem lists
+    int variant;
+    if (H.d_dtype == PSOB200_F32) variant = 0;
+    else {
+      const int t16 = H.d_dtype == PSOB200_BF16 ? 0 : 1;
+      if (bias_other) variant = 1 + t16;
+      else if (any_dt || (multi && any_bias)) variant = 7 + t16;
+      else variant = 3 + 2 * t16 + (any_bias ? 0 : 1);
+    }
+    static const KernelFn kernels2[9] = {
+        lora_gemm2_kernel<float, kEpiGeneral>, lora_gemm2_kernel<__nv_bfloat16, kEpiGeneral>, lora_gemm2_kernel<__half, kEpiGeneral>,
+        lora_gemm2_kernel<__nv_bfloat16, kEpiD | kEpiBiasSameType>, lora_gemm2_kernel<__nv_bfloat16, kEpiD>,
+        lora_gemm2_kernel<__half, kEpiD | kEpiBiasSameType>, lora_gemm2_kernel<__half, kEpiD>,
+        lora_gemm2_kernel<__nv_bfloat16, kEpiFused>, lora_gemm2_kernel<__half, kEpiFused>};
+    static PerDevice<int> max_clusters[9];  // 0: not configured on this device yet
+    std::atomic<int>& cap = max_clusters[variant].here();
+    int clusters = cap.load(std::memory_order_acquire);
+    if (clusters == 0) {
+      const cudaError_t e = cudaFuncSetAttribute(kernels2[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm2SmemBytes);
+      if (e != cudaSuccess) return consume_launch_error("configure lora_gemm2_kernel", e);
+      // pairs that can be co-resident: a launch with in-kernel dependencies must never have more (its tiles spin-wait)
+      cudaLaunchConfig_t oc = {};
+      oc.gridDim = dim3((unsigned)(sms / 2 * 2));
+      oc.blockDim = dim3(kGemmThreads);
+      oc.dynamicSmemBytes = kGemm2SmemBytes;
+      cudaLaunchAttribute oa[1];
+      oa[0].id = cudaLaunchAttributeClusterDimension;
+      oa[0].val.clusterDim.x = 2; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
+      oc.attrs = oa; oc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kernels2[variant], &oc) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = sms / 2;
+      }
+      if (n > sms / 2) n = sms / 2;
+      clusters = n;
+      cap.store(n, std::memory_order_release);
+    }
+    const long long want = L.total_tiles < clusters ? L.total_tiles : clusters;
+    cfg.gridDim = dim3(2u * (unsigned)want);
+    cfg.dynamicSmemBytes = kGemm2SmemBytes;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernels2[variant], maps, L);
+    return consume_launch_error("launch lora_gemm2_kernel", e);
+  }
+
+  L.stages = (kStages * (kStageABytes + kStageBBytes)) / (kStageABytes + max_bn * kBK * 2);
+  if (L.stages > kMaxStages) L.stages = kMaxStages;
+  L.stages &= ~1;
+  if ((H.diag >> 8) & 15) L.stages = (H.diag >> 8) & 14;
+  L.stage_b_bytes = max_bn * kBK * 2;
+  // exact epilogue modes for the single-problem launches of the training step, the fused mode for problem lists, the
+  // general kernel for everything else
+  int variant;
+  if (L.atomic) {
+    bool only_d = true, only_dt = true;
+    for (int i = 0; i < H.n_prob; ++i) { only_d &= H.prob[i].d && !H.prob[i].dt; only_dt &= H.prob[i].dt && !H.prob[i].d; }
+    variant = any_bias ? 0 : (only_d ? 1 : (only_dt ? 2 : 0));
+  } else if (H.d_dtype == PSOB200_F32) variant = 3;
+  else {
+    const int base = H.d_dtype == PSOB200_BF16 ? 4 : 9;
+    if (bias_other) variant = base;
+    else if (multi) variant = (all_d && !any_bias) ? base + 2 : base + 4;
+    else variant = base + (any_bias ? (all_d ? 1 : 0) : (all_d ? 2 : 3));
+  }
+  static const KernelFn kernels[14] = {
+      lora_gemm_kernel<float, true, kEpiGeneral>, lora_gemm_kernel<float, true, kEpiD>, lora_gemm_kernel<float, true, kEpiDt>,
+      lora_gemm_kernel<float, false, kEpiGeneral>,
+      lora_gemm_kernel<__nv_bfloat16, false, kEpiGeneral>, lora_gemm_kernel<__nv_bfloat16, false, kEpiD | kEpiBiasSameType>,
+      lora_gemm_kernel<__nv_bfloat16, false, kEpiD>, lora_gemm_kernel<__nv_bfloat16, false, kEpiAnyOut>,
+      lora_gemm_kernel<__nv_bfloat16, false, kEpiFused>,
+      lora_gemm_kernel<__half, false, kEpiGeneral>, lora_gemm_kernel<__half, false, kEpiD | kEpiBiasSameType>,
+      lora_gemm_kernel<__half, false, kEpiD>, lora_gemm_kernel<__half, false, kEpiAnyOut>,
+      lora_gemm_kernel<__half, false, kEpiFused>};
+  static PerDevice<int> max_ctas[14];
+  std::atomic<int>& cap = max_ctas[variant].here();
+  int ctas = cap.load(std::memory_order_acquire);
+  if (ctas == 0) {
+    const cudaError_t e = cudaFuncSetAttribute(kernels[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    if (e != cudaSuccess) return consume_launch_error("configure lora_gemm_kernel", e);
+    ctas = sms;  // one CTA per SM by design (~193 KB of shared memory each): every CTA of the grid is co-resident
+    cap.store(ctas, std::memory_order_release);
+  }
+  cfg.gridDim = dim3((unsigned)(L.total_tiles < ctas ? L.total_tiles : ctas));
+  cfg.dynamicSmemBytes = kGemmSmemBytes;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[variant], maps, L);
+  return consume_launch_error("launch lora_gemm_kernel", e);
 }
 
 }  // namespace psob200
@@ -467,273 +828,244 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
   const psob200_gemm_args& g = *args;
   if (g.M <= 0 || g.N <= 0 || g.K1 <= 0 || g.K2 < 0 || !g.a1 || !g.b1 || (!g.d && !g.dt)) return PSOB200_ERR_INVALID_ARG;
   if (g.K2 > 0 && (!g.a2 || !g.b2)) return PSOB200_ERR_INVALID_ARG;
-  if (g.ab_dtype != PSOB200_BF16 && g.ab_dtype != PSOB200_F16) return PSOB200_ERR_DTYPE;
-  if (!valid_dtype(g.d_dtype) || (g.bias && !valid_dtype(g.bias_dtype))) return PSOB200_ERR_DTYPE;
-  if (g.accumulate && g.d_dtype != PSOB200_F32) return PSOB200_ERR_DTYPE;
   if (g.a_reduction_major && g.K2 > 0) return PSOB200_ERR_INVALID_ARG;
-  if (g.split_k < 0 || (g.split_k > 1 && !g.accumulate)) return PSOB200_ERR_INVALID_ARG;
-  const void* ptrs[4] = {g.a1, g.b1, g.a2, g.b2};
-  const long long lds[4] = {g.lda1, g.ldb1, g.lda2, g.ldb2};
-  for (int i = 0; i < (g.K2 > 0 ? 4 : 2); ++i) {
-    if (!aligned16(ptrs[i])) return PSOB200_ERR_ALIGNMENT;
-    if (lds[i] <= 0 || (lds[i] % 8) != 0) return PSOB200_ERR_SHAPE;  // TMA: row pitch is a multiple of 16 bytes
+  if (g.bias && !valid_dtype(g.bias_dtype)) return PSOB200_ERR_DTYPE;
+  HostLaunch H = {};
+  H.n_prob = 1;
+  H.ab_dtype = g.ab_dtype; H.d_dtype = g.d_dtype;
+  H.a_mn = g.a_reduction_major; H.b_mn = g.b_reduction_major; H.accumulate = g.accumulate; H.split_k = g.split_k;
+  H.pdl = g.pdl; H.diag = g.diag;
+  HostProblem& P = H.prob[0];
+  P.M = g.M; P.N = g.N;
+  P.d = g.d; P.ldd = g.ldd; P.dt = g.dt; P.lddt = g.lddt;
+  P.bias = g.bias; P.bias_dtype = g.bias_dtype; P.alpha = g.alpha;
+  P.wait_seg = -1; P.tune_bn = g.tune_bn;
+  P.n_seg = g.K2 > 0 ? 2 : 1;
+  const void* as[2] = {g.a1, g.a2};
+  const void* bs[2] = {g.b1, g.b2};
+  const long long ldas[2] = {g.lda1, g.lda2}, ldbs[2] = {g.ldb1, g.ldb2}, ks[2] = {g.K1, g.K2};
+  for (int s = 0; s < P.n_seg; ++s) {
+    HostSeg& sg = P.seg[s];
+    sg.a = as[s]; sg.lda = ldas[s]; sg.b = bs[s]; sg.ldb = ldbs[s]; sg.K = ks[s];
+    if (g.a_reduction_major) { sg.a_rows = ks[s]; sg.a_cols = g.M; } else { sg.a_rows = g.M; sg.a_cols = ks[s]; }
+    if (g.b_reduction_major) { sg.b_rows = ks[s]; sg.b_cols = g.N; } else { sg.b_rows = g.N; sg.b_cols = ks[s]; }
   }
-  if ((g.d && g.ldd < g.N) || (g.dt && g.lddt < g.M)) return PSOB200_ERR_SHAPE;
-  if (g.M > 0x7fffffffLL - 256 || g.N > 0x7fffffffLL - 256 || g.K1 > 0x7fffffffLL - 256 || g.K2 > 0x7fffffffLL - 256)
-    return PSOB200_ERR_SHAPE;
-
-  // ---- CTA-pair kernel (cta_group::2) for the large K-major problems: at least one full wave of 256-row pair tiles
-  {
-    const int sms = gemm_sm_count();
-    const int bn_unit = g.b_reduction_major ? 128 : 16;  // each CTA loads half the tile: whole 64-column boxes / 8-row atoms
-    const bool eligible = !g.a_reduction_major && !g.accumulate && g.dt == nullptr && g.split_k <= 1 &&
-                          (g.tune_bn == 0 || (g.tune_bn % bn_unit == 0 && g.tune_bn >= 32));
-    const int bn2 = g.tune_bn > 0 ? g.tune_bn : choose_bn2(g.M, g.N, g.b_reduction_major != 0, sms / 2);
-    const long long pair_tiles = ((g.M + 255) / 256) * ((g.N + bn2 - 1) / bn2);
-    const bool want = (g.diag & 0x10000) || (pair_tiles >= sms / 2 && g.N >= 128 && !(g.diag & 0x20000));
-    if (eligible && want && bn2 <= kBNMax) {
-      GemmKernelParams p = {};
-      p.M = g.M; p.N = g.N;
-      p.nk1 = (int)((g.K1 + kBK - 1) / kBK);
-      p.nk2 = (int)((g.K2 + kBK - 1) / kBK);
-      p.bn = bn2;
-      p.m_tiles = (int)((g.M + 255) / 256);
-      p.n_tiles = (int)((g.N + bn2 - 1) / bn2);
-      p.splits = 1; p.kb_per_split = p.nk1 + p.nk2;
-      p.d = g.d; p.ldd = g.ldd; p.bias = g.bias;
-      p.alpha = g.alpha; p.d_dtype = g.d_dtype; p.bias_dtype = g.bias_dtype;
-      p.ab_format = g.ab_dtype == PSOB200_BF16 ? 1 : 0;
-      p.b_mn = g.b_reduction_major ? 1 : 0;
-      p.diag = g.diag; p.pdl = g.pdl; p.stages = kStages2;
-      CUtensorMap ma1, mb1, ma2, mb2;
-      int rc;
-      if ((rc = make_map(&ma1, g.a1, g.M, g.K1, g.lda1, kBM, g.ab_dtype)) != PSOB200_OK) return rc;
-      if (p.b_mn) rc = make_map(&mb1, g.b1, g.K1, g.N, g.ldb1, kBK, g.ab_dtype);
-      else rc = make_map(&mb1, g.b1, g.N, g.K1, g.ldb1, bn2 / 2, g.ab_dtype);
-      if (rc != PSOB200_OK) return rc;
-      if (g.K2 > 0) {
-        if ((rc = make_map(&ma2, g.a2, g.M, g.K2, g.lda2, kBM, g.ab_dtype)) != PSOB200_OK) return rc;
-        if (p.b_mn) rc = make_map(&mb2, g.b2, g.K2, g.N, g.ldb2, kBK, g.ab_dtype);
-        else rc = make_map(&mb2, g.b2, g.N, g.K2, g.ldb2, bn2 / 2, g.ab_dtype);
-        if (rc != PSOB200_OK) return rc;
-      } else {
-        ma2 = ma1;
-        mb2 = mb1;
-      }
-      typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmKernelParams);
-      // 0: general (fp32 output, or a bias of another type); then per 16-bit type: bias of the same type, no bias
-      const bool bias_other = p.bias != nullptr && p.bias_dtype != p.d_dtype;
-      const int variant = (p.d_dtype == PSOB200_F32 || bias_other) ? (p.d_dtype == PSOB200_F32 ? 0 : (p.d_dtype == PSOB200_BF16 ? 1 : 2))
-                                                                   : ((p.d_dtype == PSOB200_BF16 ? 3 : 5) + (p.bias != nullptr ? 0 : 1));
-      static const KernelFn kernels2[7] = {
-          lora_gemm2_kernel<float, kEpiD | kEpiBias>, lora_gemm2_kernel<__nv_bfloat16, kEpiD | kEpiBias>,
-          lora_gemm2_kernel<__half, kEpiD | kEpiBias>,
-          lora_gemm2_kernel<__nv_bfloat16, kEpiD | kEpiBiasSameType>, lora_gemm2_kernel<__nv_bfloat16, kEpiD>,
-          lora_gemm2_kernel<__half, kEpiD | kEpiBiasSameType>, lora_gemm2_kernel<__half, kEpiD>};
-      static PerDevice<bool> configured2_dev[7];
-      std::atomic<bool>& conf2 = configured2_dev[variant].here();
-      if (!conf2.load(std::memory_order_acquire)) {
-        const cudaError_t e = cudaFuncSetAttribute(kernels2[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm2SmemBytes);
-        if (e != cudaSuccess) return consume_launch_error("configure lora_gemm2_kernel", e);
-        conf2.store(true, std::memory_order_release);
-      }
-      const long long max_pairs = sms / 2;
-      const unsigned grid = 2u * (unsigned)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(kGemmThreads);
-      cfg.dynamicSmemBytes = kGemm2SmemBytes;
-      cfg.stream = reinterpret_cast<cudaStream_t>(stream);
-      cudaLaunchAttribute attr[1];
-      if (g.pdl & (2 | 8)) {
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-      }
-      const cudaError_t e = cudaLaunchKernelEx(&cfg, kernels2[variant], ma1, mb1, ma2, mb2, p);
-      return consume_launch_error("launch lora_gemm2_kernel", e);
-    }
-  }
-
-  GemmKernelParams p = {};
-  p.M = g.M; p.N = g.N;
-  p.nk1 = (int)((g.K1 + kBK - 1) / kBK);
-  p.nk2 = (int)((g.K2 + kBK - 1) / kBK);
-  p.bn = g.tune_bn > 0 ? g.tune_bn : choose_bn(g.N, g.b_reduction_major != 0);
-  if (p.bn < 16 || p.bn > kBNMax || (p.bn % (g.b_reduction_major ? 64 : 16)) != 0) return PSOB200_ERR_INVALID_ARG;
-  p.m_tiles = (int)((g.M + kBM - 1) / kBM);
-  p.n_tiles = (int)((g.N + p.bn - 1) / p.bn);
-  const int nk = p.nk1 + p.nk2;
-  const int sms = gemm_sm_count();
-  int splits = g.split_k;
-  if (splits == 0) {  // heuristics: split the reduction only for accumulating launches that cannot fill the GPU
-    splits = 1;
-    if (g.accumulate) {
-      // one wave: the largest split count whose tiles all fit on the SMs at once (rounding UP gave e.g. 150 tiles on 148
-      // SMs: two CTAs ran two tiles each and the launch took twice as long; measured 12.2 -> 10.1 us for dA at M = 8192)
-      const long long tiles = (long long)p.m_tiles * p.n_tiles;
-      splits = (int)(sms / tiles);
-      if (splits > nk) splits = nk;
-      if (splits < 1) splits = 1;
-    }
-  }
-  if (splits > nk) splits = nk;
-  p.kb_per_split = (nk + splits - 1) / splits;
-  p.splits = (nk + p.kb_per_split - 1) / p.kb_per_split;
-  p.d = g.d; p.ldd = g.ldd; p.dt = g.dt; p.lddt = g.lddt; p.bias = g.bias;
-  p.alpha = g.alpha; p.d_dtype = g.d_dtype; p.bias_dtype = g.bias_dtype;
-  p.ab_format = g.ab_dtype == PSOB200_BF16 ? 1 : 0;
-  p.a_mn = g.a_reduction_major ? 1 : 0;
-  p.b_mn = g.b_reduction_major ? 1 : 0;
-  p.atomic = g.accumulate ? 1 : 0;
-  p.diag = g.diag;
-  p.pdl = g.pdl;
-  p.stages = (kStages * (kStageABytes + kStageBBytes)) / (kStageABytes + p.bn * kBK * 2);
-  if (p.stages > kMaxStages) p.stages = kMaxStages;
-  p.stages &= ~1;
-  if ((g.diag >> 8) & 15) p.stages = (g.diag >> 8) & 14;
-
-  CUtensorMap ma1, mb1, ma2, mb2;
-  int rc;
-  if (p.a_mn) rc = make_map(&ma1, g.a1, g.K1, g.M, g.lda1, kBK, g.ab_dtype);  // [K, M] row-major: box 64(m) x 64(k)
-  else rc = make_map(&ma1, g.a1, g.M, g.K1, g.lda1, kBM, g.ab_dtype);
-  if (rc != PSOB200_OK) return rc;
-  if (p.b_mn) rc = make_map(&mb1, g.b1, g.K1, g.N, g.ldb1, kBK, g.ab_dtype);  // [K, N] row-major
-  else rc = make_map(&mb1, g.b1, g.N, g.K1, g.ldb1, p.bn, g.ab_dtype);
-  if (rc != PSOB200_OK) return rc;
-  if (g.K2 > 0) {
-    if ((rc = make_map(&ma2, g.a2, g.M, g.K2, g.lda2, kBM, g.ab_dtype)) != PSOB200_OK) return rc;
-    if (p.b_mn) rc = make_map(&mb2, g.b2, g.K2, g.N, g.ldb2, kBK, g.ab_dtype);
-    else rc = make_map(&mb2, g.b2, g.N, g.K2, g.ldb2, p.bn, g.ab_dtype);
-    if (rc != PSOB200_OK) return rc;
-  } else {
-    ma2 = ma1;
-    mb2 = mb1;
-  }
-
-  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmKernelParams);
-  // exact epilogue modes for the launches of the training step, the general kernel for everything else
-  const int outs = (p.d != nullptr ? kEpiD : 0) | (p.dt != nullptr ? kEpiDt : 0);
-  const bool has_bias = p.bias != nullptr;
-  int variant;
-  if (p.atomic) variant = has_bias ? 0 : (outs == kEpiD ? 1 : (outs == kEpiDt ? 2 : 0));
-  else if (p.d_dtype == PSOB200_F32) variant = 3;
-  else {
-    const int base = p.d_dtype == PSOB200_BF16 ? 4 : 8;
-    variant = base + (has_bias ? (outs == kEpiD && p.bias_dtype == p.d_dtype ? 1 : 0) : (outs == kEpiD ? 2 : 3));
-  }
-  static const KernelFn kernels[12] = {
-      lora_gemm_kernel<float, true, kEpiGeneral>, lora_gemm_kernel<float, true, kEpiD>, lora_gemm_kernel<float, true, kEpiDt>,
-      lora_gemm_kernel<float, false, kEpiGeneral>,
-      lora_gemm_kernel<__nv_bfloat16, false, kEpiGeneral>, lora_gemm_kernel<__nv_bfloat16, false, kEpiD | kEpiBiasSameType>,
-      lora_gemm_kernel<__nv_bfloat16, false, kEpiD>, lora_gemm_kernel<__nv_bfloat16, false, kEpiAnyOut>,
-      lora_gemm_kernel<__half, false, kEpiGeneral>, lora_gemm_kernel<__half, false, kEpiD | kEpiBiasSameType>,
-      lora_gemm_kernel<__half, false, kEpiD>, lora_gemm_kernel<__half, false, kEpiAnyOut>};
-  static PerDevice<bool> configured_dev[12];
-  std::atomic<bool>& conf1 = configured_dev[variant].here();
-  if (!conf1.load(std::memory_order_acquire)) {
-    const cudaError_t e = cudaFuncSetAttribute(kernels[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-    if (e != cudaSuccess) return consume_launch_error("configure lora_gemm_kernel", e);
-    conf1.store(true, std::memory_order_release);
-  }
-  const long long total = (long long)p.m_tiles * p.n_tiles * p.splits;
-  const unsigned grid = (unsigned)(total < sms ? total : sms);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = kGemmSmemBytes;
-  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
-  if (g.pdl & (2 | 8)) {  // may begin while the previous kernel on the stream is still running (it waits on the device)
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-  }
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[variant], ma1, mb1, ma2, mb2, p);
-  return consume_launch_error("launch lora_gemm_kernel", e);
+  return launch_problems(H, reinterpret_cast<cudaStream_t>(stream));
 }
 
-// ---------------------------------------------------------------------------------------------- LoRA-wrapped Linear
-static psob200_gemm_args gemm_defaults(int32_t dtype) {
-  psob200_gemm_args g = {};
-  g.alpha = 1.0f;
-  g.ab_dtype = dtype;
-  g.d_dtype = dtype;
+// ---------------------------------------------------------------------------------------------- stacked LoRA projections
+namespace psob200 {
+
+static HostSeg seg_kmajor(const void* a, long long lda, long long a_rows, long long a_cols, const void* b, long long ldb,
+                          long long b_rows, long long b_cols, long long K) {
+  HostSeg s = {};
+  s.a = a; s.lda = lda; s.a_rows = a_rows; s.a_cols = a_cols;
+  s.b = b; s.ldb = ldb; s.b_rows = b_rows; s.b_cols = b_cols;
+  s.K = K;
+  return s;
+}
+
+static HostLaunch launch_defaults(int32_t dtype) {
+  HostLaunch H = {};
+  H.ab_dtype = dtype;
+  H.d_dtype = dtype;
+  for (int i = 0; i < kMaxProb; ++i) { H.prob[i].alpha = 1.0f; H.prob[i].wait_seg = -1; }
+  return H;
+}
+
+static int group_check(const psob200_lora_group_args& a, bool backward) {
+  if (a.G < 1 || a.G > PSOB200_MAX_GROUP || a.M <= 0 || a.K <= 0 || a.N <= 0 || !a.w) return PSOB200_ERR_INVALID_ARG;
+  const bool lora = a.adapters_enabled != 0;
+  if (lora && (!a.lora_a || !a.lora_b || a.r <= 0 || a.r * a.G > 4 * kBNMax)) return PSOB200_ERR_INVALID_ARG;
+  if (lora && a.G > 1 && (a.r % 8) != 0) return PSOB200_ERR_SHAPE;  // column group g of the stacked t / u starts at g * r: 16-byte aligned
+  if (a.G > 1 && a.bias) return PSOB200_ERR_INVALID_ARG;
+  if (!backward && (!a.x || !a.y || (lora && !a.t))) return PSOB200_ERR_INVALID_ARG;
+  if (backward) {
+    for (int g = 0; g < a.G; ++g)
+      if (!a.dy[g]) return PSOB200_ERR_INVALID_ARG;
+    if (lora && !a.u) return PSOB200_ERR_INVALID_ARG;
+    if (lora && a.d_lora_a && (!a.ut || !a.x)) return PSOB200_ERR_INVALID_ARG;
+    if (lora && a.d_lora_b && !a.tt) return PSOB200_ERR_INVALID_ARG;
+  }
+  return PSOB200_OK;
+}
+
+}  // namespace psob200
+
+extern "C" int psob200_lora_group_forward(const psob200_lora_group_args* args, void* stream) {
+  if (args == nullptr) return PSOB200_ERR_INVALID_ARG;
+  const psob200_lora_group_args& a = *args;
+  int rc = group_check(a, false);
+  if (rc != PSOB200_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool lora = a.adapters_enabled != 0;
+  const long long GN = a.G * a.N, Gr = a.G * a.r;
+  const int fph = a.forward_phases == 0 ? (PSOB200_FWD_DOWN | PSOB200_FWD_MAIN) : a.forward_phases;
+  const bool fused = lora && fph == (PSOB200_FWD_DOWN | PSOB200_FWD_MAIN) && a.flags != nullptr;
+
+  // t = scaling * x [A_1; ...; A_G]^T  (+ its transpose, the K-major operand of the dB reductions)
+  HostProblem down = {};
+  if (lora) {
+    down.M = a.M; down.N = Gr; down.n_seg = 1;
+    down.seg[0] = seg_kmajor(a.x, a.ldx, a.M, a.K, a.lora_a, a.lda, Gr, a.K, a.K);
+    down.d = a.t; down.ldd = a.ldt; down.dt = a.tt; down.lddt = a.ldtt;
+    down.alpha = a.scaling; down.wait_seg = -1;
+  }
+  // y = x [W_1; ...; W_G]^T + bias + t_g B_g^T for column group g  (ONE pass over the frozen weights)
+  HostProblem main = {};
+  main.M = a.M; main.N = GN; main.alpha = 1.0f; main.wait_seg = -1;
+  main.group_n = a.G > 1 ? a.N : 0;
+  main.n_seg = lora ? 2 : 1;
+  main.seg[0] = seg_kmajor(a.x, a.ldx, a.M, a.K, a.w, a.ldw, GN, a.K, a.K);
+  if (lora) {
+    main.seg[1] = seg_kmajor(a.t, a.ldt, a.M, Gr, a.lora_b, a.ldb, GN, a.r, a.r);
+    main.seg[1].a_gkoff = a.G > 1 ? (int)a.r : 0;
+  }
+  main.bias = a.bias; main.bias_dtype = a.bias_dtype;
+  main.d = a.y; main.ldd = a.ldy;
+
+  if (fused) {  // one launch: the tiles of t come first and release a flag per row block; y's adapter segment waits for it
+    HostLaunch H = launch_defaults(a.dtype);
+    H.n_prob = 2;
+    H.prob[0] = down; H.prob[0].signal = 1;
+    H.prob[1] = main; H.prob[1].wait_seg = 1;
+    H.flags = a.flags; H.flags_len = a.flags_len;
+    return launch_problems(H, st);
+  }
+  if (lora && (fph & PSOB200_FWD_DOWN)) {
+    HostLaunch H = launch_defaults(a.dtype);
+    H.n_prob = 1; H.prob[0] = down;
+    H.pdl = (fph & PSOB200_FWD_MAIN) ? 1 : 0;  // the main pass reads t only in its last k-blocks: let it start early
+    if ((rc = launch_problems(H, st)) != PSOB200_OK) return rc;
+  }
+  if (fph & PSOB200_FWD_MAIN) {
+    HostLaunch H = launch_defaults(a.dtype);
+    H.n_prob = 1; H.prob[0] = main;
+    H.pdl = (lora && (fph & PSOB200_FWD_DOWN)) ? 2 : 0;
+    return launch_problems(H, st);
+  }
+  return PSOB200_OK;
+}
+
+extern "C" int psob200_lora_group_backward(const psob200_lora_group_args* args, void* stream) {
+  if (args == nullptr) return PSOB200_ERR_INVALID_ARG;
+  const psob200_lora_group_args& a = *args;
+  int rc = group_check(a, true);
+  if (rc != PSOB200_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool lora = a.adapters_enabled != 0;
+  const int G = a.G;
+  const long long GN = G * a.N, Gr = G * a.r;
+  const int ph = a.backward_phases == 0 ? (PSOB200_BWD_INPUT_GRAD | PSOB200_BWD_WEIGHT_GRAD) : a.backward_phases;
+  const bool need_u = lora && (ph & PSOB200_BWD_U) && (a.dx != nullptr || a.ut != nullptr || a.d_lora_a != nullptr);
+  const bool need_dx = a.dx != nullptr && (ph & PSOB200_BWD_DX);
+
+  // u_g = scaling * dy_g B_g   (B [N,r] consumed reduction-major out of the stacked [G N, r]: no transposed copy)
+  HostProblem up[PSOB200_MAX_GROUP] = {};
+  for (int g = 0; g < G && lora; ++g) {
+    HostProblem& p = up[g];
+    p.M = a.M; p.N = a.r; p.n_seg = 1; p.alpha = a.scaling; p.wait_seg = -1;
+    p.seg[0] = seg_kmajor(a.dy[g], a.lddy[g], a.M, a.N, a.lora_b, a.ldb, GN, a.r, a.N);
+    p.seg[0].b_off = (int)(g * a.N);
+    p.d = reinterpret_cast<unsigned char*>(a.u) + (size_t)g * a.r * 2; p.ldd = a.ldu;
+    if (a.ut) { p.dt = reinterpret_cast<unsigned char*>(a.ut) + (size_t)g * a.r * a.ldut * 2; p.lddt = a.ldut; }
+  }
+  // dx = sum_g dy_g W_g + [u_1 .. u_G] [A_1; ..; A_G]   (W [N,K], A [r,K] reduction-major)
+  HostProblem dxp = {};
+  if (need_dx) {
+    dxp.M = a.M; dxp.N = a.K; dxp.alpha = 1.0f; dxp.wait_seg = -1;
+    dxp.n_seg = G + (lora ? 1 : 0);
+    for (int g = 0; g < G; ++g) {
+      dxp.seg[g] = seg_kmajor(a.dy[g], a.lddy[g], a.M, a.N, a.w, a.ldw, GN, a.K, a.N);
+      dxp.seg[g].b_off = (int)(g * a.N);
+    }
+    if (lora) dxp.seg[G] = seg_kmajor(a.u, a.ldu, a.M, Gr, a.lora_a, a.lda, Gr, a.K, Gr);
+    dxp.d = a.dx; dxp.ldd = a.lddx;
+  }
+  const bool fuse_in = need_u && need_dx && a.flags != nullptr && G + 1 <= kMaxProb;
+  if (fuse_in) {  // one launch: the u tiles release a flag per row block, dx's adapter segment waits for all G of them
+    HostLaunch H = launch_defaults(a.dtype);
+    H.b_mn = 1;
+    H.n_prob = G + 1;
+    for (int g = 0; g < G; ++g) { H.prob[g] = up[g]; H.prob[g].signal = 1; }
+    H.prob[G] = dxp; H.prob[G].wait_seg = G;
+    H.flags = a.flags; H.flags_len = a.flags_len;
+    if ((rc = launch_problems(H, st)) != PSOB200_OK) return rc;
+  } else {
+    if (need_u) {
+      HostLaunch H = launch_defaults(a.dtype);
+      H.b_mn = 1; H.n_prob = G;
+      for (int g = 0; g < G; ++g) H.prob[g] = up[g];
+      H.pdl = need_dx ? 1 : 0;
+      if ((rc = launch_problems(H, st)) != PSOB200_OK) return rc;
+    }
+    if (need_dx) {
+      HostLaunch H = launch_defaults(a.dtype);
+      H.b_mn = 1; H.n_prob = 1; H.prob[0] = dxp;
+      H.pdl = (lora && need_u) ? 2 : 0;
+      if ((rc = launch_problems(H, st)) != PSOB200_OK) return rc;
+    }
+  }
+  if (!lora) return PSOB200_OK;
+  // dA[G r, K] += [u_1 .. u_G]^T x  (written transposed);  dB_g[N, r] += dy_g^T t_g : independent split reductions, one launch
+  const bool want_da = (ph & PSOB200_BWD_DA) && a.d_lora_a != nullptr, want_db = (ph & PSOB200_BWD_DB) && a.d_lora_b != nullptr;
+  if (!want_da && !want_db) return PSOB200_OK;
+  HostLaunch H = launch_defaults(a.dtype);
+  H.a_mn = 1; H.accumulate = 1; H.d_dtype = PSOB200_F32;
+  int n = 0;
+  if (want_da) {
+    HostProblem& p = H.prob[n++];
+    p.M = a.K; p.N = Gr; p.n_seg = 1;
+    p.seg[0] = seg_kmajor(a.x, a.ldx, a.M, a.K, a.ut, a.ldut, Gr, a.M, a.M);
+    p.dt = a.d_lora_a; p.lddt = a.ld_da;
+  }
+  if (want_db) {
+    if (n + G > kMaxProb) {  // dA on its own launch, then the G dB problems
+      H.n_prob = n;
+      H.pdl = 1;
+      if ((rc = launch_problems(H, st)) != PSOB200_OK) return rc;
+      H = launch_defaults(a.dtype);
+      H.a_mn = 1; H.accumulate = 1; H.d_dtype = PSOB200_F32; H.pdl = 8;
+      n = 0;
+    }
+    for (int g = 0; g < G; ++g) {
+      HostProblem& p = H.prob[n++];
+      p.M = a.N; p.N = a.r; p.n_seg = 1;
+      p.seg[0] = seg_kmajor(a.dy[g], a.lddy[g], a.M, a.N, a.tt, a.ldtt, Gr, a.M, a.M);
+      p.seg[0].b_off = (int)(g * a.r);
+      p.d = a.d_lora_b + (size_t)g * a.N * a.ld_db; p.ldd = a.ld_db;
+    }
+  }
+  H.n_prob = n;
+  return launch_problems(H, st);
+}
+
+// ---------------------------------------------------------------------------------------------- LoRA-wrapped Linear (G = 1)
+static psob200_lora_group_args group_of_linear(const psob200_lora_linear_args& a) {
+  psob200_lora_group_args g = {};
+  g.x = a.x; g.w = a.w; g.bias = a.bias; g.lora_a = a.lora_a; g.lora_b = a.lora_b;
+  g.y = a.y; g.t = a.t; g.tt = a.tt; g.dy[0] = a.dy; g.dx = a.dx; g.u = a.u; g.ut = a.ut;
+  g.d_lora_a = a.d_lora_a; g.d_lora_b = a.d_lora_b;
+  g.flags = a.flags; g.flags_len = a.flags_len;
+  g.ldx = a.ldx; g.ldw = a.ldw; g.lda = a.lda; g.ldb = a.ldb; g.ldy = a.ldy; g.ldt = a.ldt; g.ldtt = a.ldtt;
+  g.lddy[0] = a.lddy; g.lddx = a.lddx; g.ldu = a.ldu; g.ldut = a.ldut; g.ld_da = a.ld_da; g.ld_db = a.ld_db;
+  g.M = a.M; g.K = a.K; g.N = a.N; g.r = a.r; g.G = 1;
+  g.scaling = a.scaling; g.dtype = a.dtype; g.bias_dtype = a.bias_dtype; g.adapters_enabled = a.adapters_enabled;
+  g.forward_phases = a.forward_phases; g.backward_phases = a.backward_phases;
   return g;
 }
 
 extern "C" int psob200_lora_linear_forward(const psob200_lora_linear_args* args, void* stream) {
   if (args == nullptr) return PSOB200_ERR_INVALID_ARG;
-  const psob200_lora_linear_args& a = *args;
-  if (!a.x || !a.w || !a.y || a.M <= 0 || a.K <= 0 || a.N <= 0) return PSOB200_ERR_INVALID_ARG;
-  const bool lora = a.adapters_enabled != 0;
-  if (lora && (!a.lora_a || !a.lora_b || !a.t || a.r <= 0 || a.r > kBNMax)) return PSOB200_ERR_INVALID_ARG;
-  int rc;
-  const int fph = a.forward_phases == 0 ? (PSOB200_FWD_DOWN | PSOB200_FWD_MAIN) : a.forward_phases;
-  if (lora && (fph & PSOB200_FWD_DOWN)) {  // t = scaling * x A^T  (+ its transpose, the K-major operand of the dB reduction)
-    psob200_gemm_args g = gemm_defaults(a.dtype);
-    g.a1 = a.x; g.lda1 = a.ldx; g.b1 = a.lora_a; g.ldb1 = a.lda;
-    g.M = a.M; g.N = a.r; g.K1 = a.K;
-    g.alpha = a.scaling;
-    g.d = a.t; g.ldd = a.ldt; g.dt = a.tt; g.lddt = a.ldtt;
-    g.pdl = 1;  // the main pass below reads t only in its last k-blocks: let it start on the SMs this launch leaves idle
-    if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
-  }
-  if (!(fph & PSOB200_FWD_MAIN)) return PSOB200_OK;
-  psob200_gemm_args g = gemm_defaults(a.dtype);
-  g.a1 = a.x; g.lda1 = a.ldx; g.b1 = a.w; g.ldb1 = a.ldw;
-  g.M = a.M; g.N = a.N; g.K1 = a.K;
-  if (lora) { g.a2 = a.t; g.lda2 = a.ldt; g.b2 = a.lora_b; g.ldb2 = a.ldb; g.K2 = a.r; g.pdl = 2; }
-  g.bias = a.bias; g.bias_dtype = a.bias_dtype;
-  g.d = a.y; g.ldd = a.ldy;
-  return psob200_lora_gemm(&g, stream);
+  if (args->adapters_enabled && args->r > kBNMax) return PSOB200_ERR_INVALID_ARG;
+  const psob200_lora_group_args g = group_of_linear(*args);
+  return psob200_lora_group_forward(&g, stream);
 }
 
 extern "C" int psob200_lora_linear_backward(const psob200_lora_linear_args* args, void* stream) {
   if (args == nullptr) return PSOB200_ERR_INVALID_ARG;
-  const psob200_lora_linear_args& a = *args;
-  if (!a.dy || !a.w || a.M <= 0 || a.K <= 0 || a.N <= 0) return PSOB200_ERR_INVALID_ARG;
-  const bool lora = a.adapters_enabled != 0;
-  if (lora && (!a.lora_a || !a.lora_b || !a.u || a.r <= 0 || a.r > kBNMax)) return PSOB200_ERR_INVALID_ARG;
-  if (lora && a.d_lora_a && (!a.ut || !a.x)) return PSOB200_ERR_INVALID_ARG;
-  if (lora && a.d_lora_b && !a.tt) return PSOB200_ERR_INVALID_ARG;
-  int rc;
-  const int ph = a.backward_phases == 0 ? (PSOB200_BWD_INPUT_GRAD | PSOB200_BWD_WEIGHT_GRAD) : a.backward_phases;
-  const bool need_u = lora && (ph & PSOB200_BWD_U) && (a.dx != nullptr || a.ut != nullptr || a.d_lora_a != nullptr);
-  if (need_u) {  // u = scaling * dy B   (B [N,r] consumed reduction-major: no transposed copy)
-    psob200_gemm_args g = gemm_defaults(a.dtype);
-    g.a1 = a.dy; g.lda1 = a.lddy; g.b1 = a.lora_b; g.ldb1 = a.ldb; g.b_reduction_major = 1;
-    g.M = a.M; g.N = a.r; g.K1 = a.N;
-    g.alpha = a.scaling;
-    g.d = a.u; g.ldd = a.ldu; g.dt = a.ut; g.lddt = a.ldut;
-    g.pdl = a.dx != nullptr ? 1 : 0;
-    if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
-  }
-  if (a.dx != nullptr && (ph & PSOB200_BWD_DX)) {  // dx = dy W + u A   (W [N,K], A [r,K] reduction-major)
-    psob200_gemm_args g = gemm_defaults(a.dtype);
-    g.a1 = a.dy; g.lda1 = a.lddy; g.b1 = a.w; g.ldb1 = a.ldw; g.b_reduction_major = 1;
-    g.M = a.M; g.N = a.K; g.K1 = a.N;
-    if (lora) { g.a2 = a.u; g.lda2 = a.ldu; g.b2 = a.lora_a; g.ldb2 = a.lda; g.K2 = a.r; g.pdl = 2; }
-    g.d = a.dx; g.ldd = a.lddx;
-    if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
-  }
-  if (lora && (ph & PSOB200_BWD_DA) && a.d_lora_a != nullptr) {  // dA[r,K] += u^T x : D[K,r] = sum_m x[m,:]^T ut[:,m], written transposed
-    psob200_gemm_args g = gemm_defaults(a.dtype);
-    g.a1 = a.x; g.lda1 = a.ldx; g.a_reduction_major = 1; g.b1 = a.ut; g.ldb1 = a.ldut;
-    g.M = a.K; g.N = a.r; g.K1 = a.M;
-    g.dt = a.d_lora_a; g.lddt = a.ld_da; g.d_dtype = PSOB200_F32; g.accumulate = 1;
-    g.pdl = a.d_lora_b != nullptr ? 1 : 0;  // dB below is independent of this launch: let the two overlap
-    if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
-  }
-  if (lora && (ph & PSOB200_BWD_DB) && a.d_lora_b != nullptr) {  // dB[N,r] += dy^T t
-    psob200_gemm_args g = gemm_defaults(a.dtype);
-    g.a1 = a.dy; g.lda1 = a.lddy; g.a_reduction_major = 1; g.b1 = a.tt; g.ldb1 = a.ldtt;
-    g.M = a.N; g.N = a.r; g.K1 = a.M;
-    g.d = a.d_lora_b; g.ldd = a.ld_db; g.d_dtype = PSOB200_F32; g.accumulate = 1;
-    g.pdl = a.d_lora_a != nullptr ? 8 : 0;
-    if ((rc = psob200_lora_gemm(&g, stream)) != PSOB200_OK) return rc;
-  }
-  return PSOB200_OK;
+  if (!args->dy) return PSOB200_ERR_INVALID_ARG;
+  if (args->adapters_enabled && args->r > kBNMax) return PSOB200_ERR_INVALID_ARG;
+  const psob200_lora_group_args g = group_of_linear(*args);
+  return psob200_lora_group_backward(&g, stream);
 }

@@ -13,8 +13,8 @@
 //     accumulator full);
 //   * the peer's epilogue warps release the accumulator on the leader's barrier (remote mbarrier arrive);
 //   * tensor memory is allocated / freed with .cta_group::2 by the same warp of both CTAs.
-// Supports: two K segments, bias, alpha, K-major or reduction-major B, PDL waits.  Not: reduction-major A, atomics,
-// transposed output, split-K (the 1-SM kernel keeps those).
+// Supports: problem lists with in-launch dependencies, reduction segments, stacked column groups, bias, alpha, K-major or
+// reduction-major B, transposed output copy, PDL waits.  Not: reduction-major A, atomics, split-K (the 1-SM kernel keeps those).
 #pragma once
 
 namespace psob200 {
@@ -66,9 +66,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 
 template <typename TD, int kMode>  // one instantiation per output type / bias presence (code size: see lora_gemm_kernel)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-lora_gemm2_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
-                  const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
-                  const GemmKernelParams p) {
+lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmLaunch L) {
   extern __shared__ unsigned char gemm_smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages2], empty_bar[kStages2 / 2], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
@@ -80,21 +78,18 @@ lora_gemm2_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
-  const int nk = p.nk1 + p.nk2;
-  const int half_bn = p.bn / 2;
-  const int stage_b_bytes = half_bn * kBK * 2;
-  const long long total_tiles = (long long)p.m_tiles * p.n_tiles;  // m_tiles counts 256-row pair tiles here
-  const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int stage_b_bytes = L.stage_b_bytes;  // half of the widest problem's B tile
+  const int total_tiles = L.total_tiles;      // m_tiles count 256-row pair tiles here
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&map_a1);
-    ptx::prefetch_tensormap(&map_b1);
-    if (p.nk2 > 0) {
-      ptx::prefetch_tensormap(&map_a2);
-      ptx::prefetch_tensormap(&map_b2);
-    }
+    for (int p = 0; p < L.n_prob; ++p)
+      for (int s = 0; s < L.prob[p].n_seg; ++s) {
+        ptx::prefetch_tensormap(&maps.m[L.prob[p].map_a[s]]);
+        ptx::prefetch_tensormap(&maps.m[L.prob[p].map_b[s]]);
+      }
   }
-  if (p.pdl & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (L.pdl & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 1 && lane == 0) {
 #pragma unroll
     for (int s = 0; s < kStages2; ++s) ptx::mbar_init(&full_bar[s], 1);  // leader's arrive.expect_tx (both CTAs' bytes)
@@ -119,70 +114,78 @@ lora_gemm2_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
 
-  auto tile_coords = [&](long long t, int& m_blk, int& n_blk) {
-    n_blk = (int)(t % p.n_tiles);
-    m_blk = (int)(t / p.n_tiles);
-  };
-
   if (warp == 0) {
     // ================================================================= TMA producer (both CTAs: own A rows, own half of B)
-    const uint32_t tx_pair = 2u * ((uint32_t)kStageABytes + (uint32_t)stage_b_bytes);
     int stage = 0;
     uint32_t phase = 0;
-    bool dep_pending = (p.pdl & 2) != 0;
-    if (dep_pending && (p.pdl & 4)) {
+    bool dep_pending = (L.pdl & 2) != 0;
+    if (dep_pending && (L.pdl & 4)) {
       asm volatile("griddepcontrol.wait;" ::: "memory");
       asm volatile("fence.proxy.async;" ::: "memory");
       dep_pending = false;
     }
-    for (long long t = cluster_id; t < total_tiles; t += n_clusters) {
-      int m_blk, n_blk;
-      tile_coords(t, m_blk, n_blk);
-      const int m0 = m_blk * 256 + (int)rank * kBM, n0 = n_blk * p.bn + (int)rank * half_bn;
-      for (int kb = 0; kb < nk; ++kb) {
+    for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+      TileInfo ti;
+      decode_tile(L, t, ti);
+      const GemmProblem& P = L.prob[ti.p];
+      const int half_bn = P.bn / 2;
+      const uint32_t tx_pair = 2u * ((uint32_t)kStageABytes + (uint32_t)(half_bn * kBK * 2));
+      const int m0 = ti.m_blk * 256 + (int)rank * kBM, n0 = (int)ti.n0 + (int)rank * half_bn;
+      int seg = 0, kbs = ti.kb0;
+      while (kbs >= P.nk[seg]) { kbs -= P.nk[seg]; ++seg; }
+      bool need_wait = P.wait_seg >= 0;
+      for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
         if ((stage & 1) == 0) ptx::mbar_wait(&empty_bar[stage >> 1], phase ^ 1u);
-        const bool seg2 = kb >= p.nk1;
-        if (seg2 && dep_pending) {
+        if (seg >= 1 && dep_pending) {
           asm volatile("griddepcontrol.wait;" ::: "memory");
           asm volatile("fence.proxy.async;" ::: "memory");
           dep_pending = false;
         }
-        const CUtensorMap* ma = seg2 ? &map_a2 : &map_a1;
-        const CUtensorMap* mb = seg2 ? &map_b2 : &map_b1;
-        const int kk = (seg2 ? kb - p.nk1 : kb) * kBK;
+        if (need_wait && seg >= P.wait_seg) {  // rows produced by other tiles of this launch (8 epilogue warps per pair tile)
+          wait_flag(L.flags + ti.m_blk, P.wait_count * 8);
+          need_wait = false;
+        }
+        const CUtensorMap* ma = &maps.m[P.map_a[seg]];
+        const CUtensorMap* mb = &maps.m[P.map_b[seg]];
+        const int ka = kbs * kBK + P.a_koff[seg] + ti.group * P.a_gkoff[seg];
+        const int kk = kbs * kBK;
+        const int boff = P.b_off[seg];
         unsigned char* sa = smem_a + stage * kStageABytes;
         unsigned char* sb = smem_b + stage * stage_b_bytes;
         if (ptx::elect_one()) {
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_pair);
-          ptx::tma_load_2d_pair(sa, ma, kk, m0, &full_bar[stage]);
-          if (p.b_mn) {
+          ptx::tma_load_2d_pair(sa, ma, ka, m0, &full_bar[stage]);
+          if (L.b_mn) {
             for (int j = 0; j < half_bn / 64; ++j)
-              ptx::tma_load_2d_pair(sb + j * (kBK * 128), mb, n0 + 64 * j, kk, &full_bar[stage]);
+              ptx::tma_load_2d_pair(sb + j * (kBK * 128), mb, n0 + 64 * j, kk + boff, &full_bar[stage]);
           } else {
-            ptx::tma_load_2d_pair(sb, mb, kk, n0, &full_bar[stage]);
+            ptx::tma_load_2d_pair(sb, mb, kk, n0 + boff, &full_bar[stage]);
           }
         }
         __syncwarp();
         if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+        if (++kbs == P.nk[seg]) { kbs = 0; ++seg; }
       }
     }
   } else if (warp == 1 && leader) {
     // ================================================================= MMA issuer (leader CTA, M = 256 across the pair)
-    const uint32_t idesc = (1u << 4) | ((uint32_t)p.ab_format << 7) | ((uint32_t)p.ab_format << 10) |
-                           ((uint32_t)p.b_mn << 16) | (((uint32_t)p.bn >> 3) << 17) | ((256u >> 4) << 24);
     const uint64_t a_hi = ptx::smem_desc_sw128(0, 0, 1024);
-    const uint64_t b_hi = ptx::smem_desc_sw128(0, p.b_mn ? kBK * 128 : 0, 1024);
-    const uint32_t b_step = p.b_mn ? 2048u >> 4 : 32u >> 4;
+    const uint64_t b_hi = ptx::smem_desc_sw128(0, L.b_mn ? kBK * 128 : 0, 1024);
+    const uint32_t b_step = L.b_mn ? 2048u >> 4 : 32u >> 4;
     int stage = 0;
     uint32_t phase = 0;
-    long long iter = 0;
-    for (long long t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
-      const int acc = (int)(iter & 1);
+    int iter = 0;
+    for (int t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
+      TileInfo ti;
+      decode_tile(L, t, ti);
+      const uint32_t idesc = (1u << 4) | ((uint32_t)L.ab_format << 7) | ((uint32_t)L.ab_format << 10) |
+                             ((uint32_t)L.b_mn << 16) | (((uint32_t)L.prob[ti.p].bn >> 3) << 17) | ((256u >> 4) << 24);
+      const int acc = iter & 1;
       const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);  // both CTAs' epilogues have drained this accumulator
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * kBNMax;
-      for (int kb = 0; kb < nk; ++kb) {
+      for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after_sync();
         const uint64_t a_desc = a_hi | (uint64_t)((ptx::smem_addr(smem_a + stage * kStageABytes) >> 4) & 0x3FFFu);
@@ -191,9 +194,9 @@ lora_gemm2_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
             ptx::umma_f16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * b_step), idesc,
-                               (kb > 0 || k > 0) ? 1u : 0u);
+                               (kb > ti.kb0 || k > 0) ? 1u : 0u);
           if (stage & 1) ptx::umma_commit_pair(&empty_bar[stage >> 1]);
-          if (kb == nk - 1) ptx::umma_commit_pair(&tmem_full_bar[acc]);
+          if (kb == ti.kb1 - 1) ptx::umma_commit_pair(&tmem_full_bar[acc]);
         }
         __syncwarp();
         if (++stage == kStages2) { stage = 0; phase ^= 1u; }
@@ -202,22 +205,27 @@ lora_gemm2_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   } else if (warp >= 4) {
     // ================================================================= epilogue (each CTA: its 128 rows)
     const int ew = warp - 4;
-    long long iter = 0;
-    for (long long t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
-      int m_blk, n_blk;
-      tile_coords(t, m_blk, n_blk);
-      const int acc = (int)(iter & 1);
+    int iter = 0;
+    for (int t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
+      TileInfo ti;
+      decode_tile(L, t, ti);
+      const GemmProblem& P = L.prob[ti.p];
+      const int acc = iter & 1;
       const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
-      const long long row = (long long)m_blk * 256 + (long long)rank * kBM + ew * 32 + lane;
-      const long long n_tile0 = (long long)n_blk * p.bn;
-      const bool add_bias = p.bias != nullptr;
+      const long long row = (long long)ti.m_blk * 256 + (long long)rank * kBM + ew * 32 + lane;
+      const bool add_bias = P.bias != nullptr;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kBNMax;
-      epilogue_tile<TD, false, kMode>(p, taddr, row, n_tile0, add_bias);
+      epilogue_tile<TD, false, kMode>(P, L.diag, taddr, row, ti.n0, ti.n_end, add_bias);
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_leader(&tmem_empty_bar[acc]);
+      if (P.signal) {  // publish these rows to the tiles of this launch that read them (8 warps = one pair tile)
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(L.flags + ti.m_blk, 1);
+      }
     }
   }
 
@@ -226,6 +234,14 @@ lora_gemm2_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   if (warp == 2) {
     ptx::tc_fence_after_sync();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+  if (L.flags != nullptr && threadIdx.x == 0) {  // the last CTA to leave zeroes the flags for the next launch
+    __threadfence();
+    const int done = atomicAdd(L.flags + L.n_flags, 1);
+    if (done == (int)gridDim.x - 1) {
+      for (int i = 0; i <= L.n_flags; ++i) L.flags[i] = 0;
+      __threadfence();
+    }
   }
 }
 

@@ -435,7 +435,8 @@ extern "C" int psob200_dmd_x0_from_noise(const float* alphas_cumprod, int32_t n_
   if (ts_rows != 1 && ts_rows != B) return PSOB200_ERR_INVALID_ARG;
   if (B > 65535) return PSOB200_ERR_SHAPE;
   if (!valid_dtype(pred_dtype) || !valid_dtype(latent_dtype)) return PSOB200_ERR_DTYPE;
-  if (out_dtype != pred_dtype && out_dtype != latent_dtype) return PSOB200_ERR_DTYPE;
+  // the inputs' types, or fp32 (the reference's promotion with the fp32 alphas_cumprod gather, DS:36-42)
+  if (out_dtype != pred_dtype && out_dtype != latent_dtype && out_dtype != PSOB200_F32) return PSOB200_ERR_DTYPE;
   const bool vec_ok = (N % 8) == 0 && aligned16(model_output) && aligned16(sample) && aligned16(x0_out);
   const long long nchunk = vec_ok ? N / 8 : N;
   const dim3 grid(elementwise_blocks(nchunk, B), (unsigned)B);
@@ -453,7 +454,7 @@ extern "C" int psob200_dmd_x0_from_noise(const float* alphas_cumprod, int32_t n_
       x0_from_noise_kernel<TP, TL, TO, 1><<<grid, 256, 0, st>>>(alphas_cumprod, n_table, model_output, sample, ts,  \
                                                                 ts_dtype, ts_rows, x0_out, N, status);              \
   } while (0)
-    if (out_is_latent) PSOB200_X0(TL); else PSOB200_X0(TP);
+    if (out_is_latent) PSOB200_X0(TL); else if (out_dtype == pred_dtype) PSOB200_X0(TP); else PSOB200_X0(float);
 #undef PSOB200_X0
     return check_launch();
   });

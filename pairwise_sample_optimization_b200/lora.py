@@ -16,8 +16,10 @@ Mirrors the third-party surface the reference's trainers touch (SURVEY.md sectio
   weight-gradient kernels (so gradient accumulation costs nothing) and all-reduced with ONE NCCL call
   (the reference: DDP buckets behind accelerator.prepare, turbo :491, sync gate :858).
 
-The forward is two launches (skinny ``t = s x A^T``; then ``y = x W^T + b + t B^T`` in one pass over W) where the
-reference stack issues five; the backward is four.  There is no PyTorch fallback: a CPU tensor raises.
+The forward of a projection is ONE launch (the skinny ``t = s x A^T`` runs as tiles of the same launch as
+``y = x W^T + b + t B^T``, one pass over W) where the reference stack issues five; the backward is two (input gradient with
+``u = s dy B`` in-launch; both weight gradients).  ``fuse_attention_projections`` stacks q / k / v (k / v) into one such
+problem.  There is no PyTorch fallback: a CPU tensor raises.
 """
 from __future__ import annotations
 
@@ -179,24 +181,153 @@ class LoRALinear(nn.Module):
         self._operand("b", dtype)
 
     def forward(self, x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
-        n = self.active_adapter
-        # the adapter matrices are passed so that autograd knows the output depends on them (their gradients are
+        # the adapter matrices are passed to the autograd function so that the output depends on them (their gradients are
         # accumulated in place by the kernels; the Function returns None for them)
-        return _LoraLinearFn.apply(x, self, self.lora_A[n].weight, self.lora_B[n].weight, torch.is_grad_enabled())
+        g = self.__dict__.get("_solo_group")
+        if g is None:
+            g = self.__dict__["_solo_group"] = LoRAProjectionGroup([self])
+        return g(x)
 
 
-class _LoraLinearFn(torch.autograd.Function):
-    """psob200_lora_linear_forward / _backward.  Gradients of the adapter matrices are ACCUMULATED IN PLACE into
+_FLAGS: dict = {}
+
+
+def _flags_workspace(dev: torch.device) -> torch.Tensor:
+    """Zeroed int32 scratch for the in-launch dependencies of the fused projection launches (psob200_lora_group_args.flags):
+    one per (device, stream) -- launches on a stream are ordered and every launch leaves it zeroed."""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _FLAGS.get(key)
+    if ws is None:
+        ws = _FLAGS[key] = torch.zeros(8192, dtype=torch.int32, device=dev)
+    return ws
+
+
+class LoRAProjectionGroup:
+    """G LoRA-wrapped projections that read the SAME input, run as one stacked problem (psob200_lora_group_*): attention
+    to_q / to_k / to_v (G = 3), cross-attention to_k / to_v (G = 2), or a single ``LoRALinear`` (G = 1).
+
+    The frozen weights of the members become views of ONE [G N, K] matrix (their values are unchanged; ``layer.weight`` still
+    works).  The adapters are consumed stacked as well: when the members' 16-bit operand copies (and fp32 gradient targets) sit
+    next to each other in memory -- they do once ``LoRAGradBucket`` / ``FusedLoRAOptimizer`` laid the parameters out in
+    ``lora_parameters()`` order -- they are used in place; otherwise the group keeps private stacked copies."""
+
+    def __init__(self, layers):
+        layers = list(layers)
+        l0 = layers[0]
+        for l in layers[1:]:
+            if (l.in_features, l.out_features) != (l0.in_features, l0.out_features) or l.r != l0.r or l.scaling != l0.scaling \
+                    or l.base_layer.weight.dtype != l0.base_layer.weight.dtype or l.active_adapter != l0.active_adapter:
+                raise ValueError("stacked projections must have the same shape, rank, scaling and dtype")
+        if len(layers) > 1 and any(l.base_layer.bias is not None for l in layers):
+            raise ValueError("stacked projections must not have a bias (attention q / k / v have none)")
+        self.layers = layers
+        self.G = len(layers)
+        self.K, self.N = l0.in_features, l0.out_features
+        self._op = {}     # which -> [versions, stacked 16-bit buffer]
+        self._grad = {}   # which -> stacked fp32 gradient buffer (only without a flat bucket)
+        if self.G > 1:
+            w = torch.cat([l.base_layer.weight.detach() for l in layers], dim=0).contiguous()
+            for g, l in enumerate(layers):
+                l.base_layer.weight.data = w[g * self.N:(g + 1) * self.N]
+            self.weight = w
+        else:
+            self.weight = None
+
+    @property
+    def name(self):
+        return self.layers[0].active_adapter
+
+    def stacked_weight(self) -> torch.Tensor:
+        if self.G == 1:
+            return self.layers[0].base_layer.weight
+        w, l0 = self.weight, self.layers[0]
+        if l0.base_layer.weight.data_ptr() != w.data_ptr() or w.device != l0.base_layer.weight.device:  # model.to(...) moved the members
+            w = torch.cat([l.base_layer.weight.detach() for l in self.layers], dim=0).contiguous()
+            for g, l in enumerate(self.layers):
+                l.base_layer.weight.data = w[g * self.N:(g + 1) * self.N]
+            self.weight = w
+        return w
+
+    def _adjacent(self, tensors) -> bool:
+        t0 = tensors[0]
+        step = t0.numel() * t0.element_size()
+        return all(t.is_contiguous() and t.data_ptr() == t0.data_ptr() + g * step for g, t in enumerate(tensors))
+
+    def stacked_operand(self, which: str, dtype: torch.dtype) -> torch.Tensor:
+        """[G r, K] (which = "a") or [G N, r] ("b") 16-bit, row pitch a multiple of 8 elements."""
+        ops = [l._operand(which, dtype) for l in self.layers]
+        if self.G == 1:
+            return ops[0]
+        if self._adjacent(ops) and ops[0].stride(0) == ops[0].shape[1]:
+            return ops[0].as_strided((self.G * ops[0].shape[0], ops[0].shape[1]), (ops[0].shape[1], 1))
+        params = [(l.lora_A if which == "a" else l.lora_B)[l.active_adapter].weight for l in self.layers]
+        vers = tuple((p.data_ptr(), p._version) for p in params)
+        hit = self._op.get((which, dtype))
+        if hit is None or hit[1].device != ops[0].device:
+            hit = [None, torch.empty(self.G * ops[0].shape[0], ops[0].shape[1], dtype=dtype, device=ops[0].device)]
+            self._op[(which, dtype)] = hit
+        if hit[0] != vers:  # refreshed IN PLACE: stable address (CUDA-graph friendly)
+            rows = ops[0].shape[0]
+            for g, o in enumerate(ops):
+                hit[1][g * rows:(g + 1) * rows].copy_(o)
+            hit[0] = vers
+        return hit[1]
+
+    def refresh_operands(self) -> None:
+        dtype = self.layers[0].base_layer.weight.dtype
+        self.stacked_operand("a", dtype)
+        self.stacked_operand("b", dtype)
+
+    def stacked_grad(self, which: str) -> torch.Tensor:
+        """fp32 accumulation target [G r, K] / [G N, r]: the members' slices of the flat bucket when they are adjacent, else
+        a private stacked buffer the members' ``.grad`` become views of."""
+        params = [(l.lora_A if which == "a" else l.lora_B)[l.active_adapter].weight for l in self.layers]
+        if any(p.dtype != torch.float32 for p in params):
+            raise _lib.Psob200Error("stacked projections train fp32 adapter parameters (the shipped mixed-precision recipes)")
+        if self.G == 1:
+            return _grad_buffer(params[0])
+        views = [getattr(p, "_psob200_grad_view", None) for p in params]
+        if all(v is not None for v in views):
+            if not self._adjacent(views):
+                raise _lib.Psob200Error("the gradient slices of stacked projections are not adjacent in the flat bucket: build "
+                                        "LoRAGradBucket / FusedLoRAOptimizer from lora.lora_parameters(model) AFTER "
+                                        "lora.fuse_attention_projections(model)")
+            for p in params:
+                _grad_buffer(p)  # re-attach p.grad / refuse foreign tensors
+            v0 = views[0]
+            return v0.as_strided((self.G * v0.shape[0], v0.shape[1]), (v0.shape[1], 1))
+        buf = torch.zeros(self.G * params[0].shape[0], params[0].shape[1], dtype=torch.float32, device=params[0].device)
+        rows = params[0].shape[0]
+        for g, p in enumerate(params):
+            v = buf[g * rows:(g + 1) * rows]
+            if p.grad is not None:
+                v.copy_(p.grad)
+            p.grad = v
+            p._psob200_grad_view = v
+        self._grad[which] = buf
+        return buf
+
+    def __call__(self, x: torch.Tensor):
+        """Returns the G projections of ``x`` (views of one [.., G N] buffer)."""
+        params = []
+        for l in self.layers:
+            params += [l.lora_A[l.active_adapter].weight, l.lora_B[l.active_adapter].weight]
+        return _LoraGroupFn.apply(x, self, torch.is_grad_enabled(), *params)
+
+
+class _LoraGroupFn(torch.autograd.Function):
+    """psob200_lora_group_forward / _backward.  Gradients of the adapter matrices are ACCUMULATED IN PLACE into
     ``param.grad`` (fp32 views of the flat bucket when one is attached), so autograd receives only ``dx``."""
 
     @staticmethod
-    def forward(ctx, x: torch.Tensor, layer: LoRALinear, _pa, _pb, grad_mode: bool):
-        w = layer.base_layer.weight
+    def forward(ctx, x: torch.Tensor, group: LoRAProjectionGroup, grad_mode: bool, *params):
+        l0 = group.layers[0]
+        w = group.stacked_weight()
         dev = _lib.require_cuda(x, w)
         dtype = w.dtype
         if dtype not in (torch.bfloat16, torch.float16):
             raise _lib.Psob200Error(f"the tcgen05 LoRA path needs bf16/fp16 base weights, got {dtype}")
-        K, N = layer.in_features, layer.out_features
+        G, K, N = group.G, group.K, group.N
         if x.shape[-1] != K:
             raise _lib.Psob200Error(f"input feature size {x.shape[-1]} != in_features {K}")
         x2 = x.detach().reshape(-1, K)
@@ -207,114 +338,129 @@ class _LoraLinearFn(torch.autograd.Function):
         if K % 8 or w.stride(0) != K or w.data_ptr() % 16:
             raise _lib.Psob200Error("base weight must be contiguous with in_features a multiple of 8")
         M = x2.shape[0]
-        enabled = not layer._disable_adapters
-        name = layer.active_adapter
-        r = layer.r[name]
-        a = _lib.LoraLinearArgs()
-        y = torch.empty(M, N, dtype=dtype, device=dev)
-        a.x, a.ldx, a.w, a.ldw, a.y, a.ldy = x2.data_ptr(), K, w.data_ptr(), K, y.data_ptr(), N
-        bias = layer.base_layer.bias
+        enabled = not l0._disable_adapters
+        if any(l._disable_adapters != l0._disable_adapters for l in group.layers):
+            raise _lib.Psob200Error("stacked projections must be enabled / disabled together")
+        name = l0.active_adapter
+        r = l0.r[name]
+        if enabled and G > 1 and r % 8:
+            raise _lib.Psob200Error("stacked projections need a LoRA rank that is a multiple of 8")
+        a = _lib.LoraGroupArgs()
+        y = torch.empty(M, G * N, dtype=dtype, device=dev)
+        a.x, a.ldx, a.w, a.ldw, a.y, a.ldy = x2.data_ptr(), K, w.data_ptr(), K, y.data_ptr(), G * N
+        bias = l0.base_layer.bias if G == 1 else None
         if bias is not None:
             a.bias, a.bias_dtype = bias.data_ptr(), _lib.dtype_code(bias)
-        a.M, a.K, a.N, a.r = M, K, N, r
+        a.M, a.K, a.N, a.r, a.G = M, K, N, r, G
         a.dtype = _lib.dtype_code(x2)
         a.adapters_enabled = int(enabled)
-        want_wgrad = enabled and grad_mode and _pa.requires_grad  # False under no_grad (the frozen-reference pass)
+        want_wgrad = enabled and grad_mode and params[0].requires_grad  # False under no_grad (the frozen-reference pass)
         t = tt = None
+        fl_t = by_t = 0.0
         if enabled:
-            la, lb = layer._operand("a", dtype), layer._operand("b", dtype)
-            r8 = _ceil8(r)
-            t = torch.empty(M, r8, dtype=dtype, device=dev)
+            la, lb = group.stacked_operand("a", dtype), group.stacked_operand("b", dtype)
+            gr8 = _ceil8(G * r)
+            t = torch.empty(M, gr8, dtype=dtype, device=dev)
             a.lora_a, a.lda, a.lora_b, a.ldb = la.data_ptr(), la.stride(0), lb.data_ptr(), lb.stride(0)
-            a.t, a.ldt = t.data_ptr(), r8
-            a.scaling = float(layer.scaling[name])
+            a.t, a.ldt = t.data_ptr(), gr8
+            a.scaling = float(l0.scaling[name])
             if want_wgrad:
-                tt = torch.empty(r, _ceil8(M), dtype=dtype, device=dev)
+                tt = torch.empty(G * r, _ceil8(M), dtype=dtype, device=dev)
                 a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
+            ws = _flags_workspace(dev)  # t becomes tiles of the same launch as y
+            a.flags, a.flags_len = ws.data_ptr(), ws.numel()
+            fl_t = 2.0 * M * G * r * K
+            by_t = 2 * (G * r * K + M * G * r * (2 if tt is not None else 1))
         if _TIMING is None:
-            _lib.launch(dev, "psob200_lora_linear_forward", C.byref(a), _lib.current_stream(dev))
-        else:  # instrumented pass: the same launches one by one, each between its own pair of events
-            eb = 2  # bytes per 16-bit element
-            roles = [(1, "t = s x A^T", 2.0 * M * r * K, eb * (M * K + r * K + M * r * (2 if tt is not None else 1)))] if enabled else []
-            roles.append((2, "y = x W^T + t B^T" if enabled else "y = x W^T (frozen reference)",
-                          2.0 * M * N * (K + (r if enabled else 0)), eb * (M * K + N * K + M * N + ((M + N) * r if enabled else 0))))
-            for mask, role, fl, by in roles:
-                a.forward_phases = mask
-                _timed_launch(dev, lambda: _lib.lib().psob200_lora_linear_forward(C.byref(a), _lib.current_stream(dev)),
-                              "psob200_lora_linear_forward", role, fl, by, (M, K, N, r))
-        ctx.layer, ctx.enabled, ctx.x_shape, ctx.x_dtype, ctx.want_wgrad = layer, enabled, x.shape, x.dtype, want_wgrad
+            _lib.launch(dev, "psob200_lora_group_forward", C.byref(a), _lib.current_stream(dev))
+        else:  # instrumented pass: the same launch between its own pair of events
+            role = ("y = x W^T + t B^T (t = s x A^T as tiles of the same launch)" if enabled else "y = x W^T (frozen reference)")
+            _timed_launch(dev, lambda: _lib.lib().psob200_lora_group_forward(C.byref(a), _lib.current_stream(dev)),
+                          "psob200_lora_group_forward", role, 2.0 * M * G * N * (K + (r if enabled else 0)) + fl_t,
+                          2 * (M * K + G * N * K + M * G * N + (G * N * r if enabled else 0)) + by_t, (M, K, G * N, r if enabled else 0))
+        ctx.group, ctx.enabled, ctx.x_shape, ctx.x_dtype, ctx.want_wgrad = group, enabled, x.shape, x.dtype, want_wgrad
         ctx.save_for_backward(x2, tt)
-        return y.view(*x.shape[:-1], N)
+        y = y.view(*x.shape[:-1], G * N)
+        if G == 1:
+            return y
+        return tuple(y[..., g * N:(g + 1) * N] for g in range(G))
 
     @staticmethod
-    def backward(ctx, dy: torch.Tensor):
-        layer: LoRALinear = ctx.layer
+    def backward(ctx, *dys):
+        group: LoRAProjectionGroup = ctx.group
         x2, tt = ctx.saved_tensors
-        w = layer.base_layer.weight
+        l0 = group.layers[0]
+        w = group.stacked_weight()
         dev, dtype = w.device, w.dtype
-        K, N = layer.in_features, layer.out_features
+        G, K, N = group.G, group.K, group.N
         M = x2.shape[0]
-        dy2 = dy.reshape(-1, N)
-        if dy2.dtype != dtype:
-            dy2 = dy2.to(dtype)
-        if not dy2.is_contiguous() or dy2.data_ptr() % 16:
-            dy2 = dy2.contiguous()
-        name = layer.active_adapter
-        r = layer.r[name]
-        a = _lib.LoraLinearArgs()
-        a.dy, a.lddy, a.w, a.ldw, a.x, a.ldx = dy2.data_ptr(), N, w.data_ptr(), K, x2.data_ptr(), K
-        a.M, a.K, a.N, a.r = M, K, N, r
-        a.dtype = _lib.dtype_code(dy2)
+        name = l0.active_adapter
+        r = l0.r[name]
+        a = _lib.LoraGroupArgs()
+        dy2 = []
+        for g in range(G):
+            d = dys[g].reshape(-1, N)
+            if d.dtype != dtype:
+                d = d.to(dtype)
+            if d.stride(1) != 1 or d.stride(0) % 8 or d.data_ptr() % 16:
+                d = d.contiguous()
+            dy2.append(d)
+            a.dy[g], a.lddy[g] = d.data_ptr(), d.stride(0)
+        a.w, a.ldw, a.x, a.ldx = w.data_ptr(), K, x2.data_ptr(), K
+        a.M, a.K, a.N, a.r, a.G = M, K, N, r, G
+        a.dtype = _lib.dtype_code(dy2[0])
         a.adapters_enabled = int(ctx.enabled)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, dtype=dtype, device=dev)
             a.dx, a.lddx = dx.data_ptr(), K
         keep = []
+        wg = False
         if ctx.enabled:
-            pa, pb = layer.lora_A[name].weight, layer.lora_B[name].weight
-            la, lb = layer._operand("a", dtype), layer._operand("b", dtype)
+            la, lb = group.stacked_operand("a", dtype), group.stacked_operand("b", dtype)
             a.lora_a, a.lda, a.lora_b, a.ldb = la.data_ptr(), la.stride(0), lb.data_ptr(), lb.stride(0)
-            a.scaling = float(layer.scaling[name])
-            r8 = _ceil8(r)
-            u = torch.empty(M, r8, dtype=dtype, device=dev)
-            a.u, a.ldu = u.data_ptr(), r8
+            a.scaling = float(l0.scaling[name])
+            gr8 = _ceil8(G * r)
+            u = torch.empty(M, gr8, dtype=dtype, device=dev)
+            a.u, a.ldu = u.data_ptr(), gr8
             keep.append(u)
+            ws = _flags_workspace(dev)
+            a.flags, a.flags_len = ws.data_ptr(), ws.numel()
             if ctx.want_wgrad:
-                ga, gb = _grad_buffer(pa), _grad_buffer(pb)
-                ut = torch.empty(r, _ceil8(M), dtype=dtype, device=dev)
+                ga, gb = group.stacked_grad("a"), group.stacked_grad("b")
+                ut = torch.empty(G * r, _ceil8(M), dtype=dtype, device=dev)
                 a.ut, a.ldut = ut.data_ptr(), ut.stride(0)
                 a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
                 a.d_lora_a, a.ld_da = ga.data_ptr(), ga.stride(0)
                 a.d_lora_b, a.ld_db = gb.data_ptr(), gb.stride(0)
                 keep += [ut, ga, gb]
-        if dx is not None or (ctx.enabled and a.d_lora_a):
-            wg = bool(ctx.enabled and a.d_lora_a)
+                wg = True
+        if dx is not None or wg:
             side = _WGRAD_SIDE["enabled"] and wg and _TIMING is None
             if _TIMING is not None:  # instrumented pass: one launch at a time, each between its own pair of events
                 eb = 2
-                roles = []
-                if ctx.enabled and (dx is not None or wg):
-                    roles.append((1, "u = s dy B", 2.0 * M * N * r, eb * (M * N + N * r + M * r * (2 if wg else 1))))
-                if dx is not None:
-                    roles.append((2, "dx = dy W + u A", 2.0 * M * K * (N + (r if ctx.enabled else 0)),
-                                  eb * (M * N + N * K + M * K + ((M + K) * r if ctx.enabled else 0))))
+                if dx is not None or wg:
+                    fl = (2.0 * M * K * G * N if dx is not None else 0.0) + (2.0 * M * G * r * (N + (K if dx is not None else 0)) if ctx.enabled else 0.0)
+                    by = eb * (M * G * N + (G * N * K + M * K if dx is not None else 0) + ((G * N * r + G * r * K + M * G * r * (2 if wg else 1)) if ctx.enabled else 0))
+                    role = ("dx = dy W + u A (u = s dy B as tiles of the same launch)" if dx is not None else "u = s dy B")
+                    a.backward_phases = 3
+                    _timed_launch(dev, lambda: _lib.lib().psob200_lora_group_backward(C.byref(a), _lib.current_stream(dev)),
+                                  "psob200_lora_group_backward", role, fl, by, (M, K, G * N, r if ctx.enabled else 0))
                 if wg:
-                    roles.append((4, "dA += u^T x", 2.0 * M * r * K, eb * (M * K + M * r) + 4 * r * K))
-                    roles.append((8, "dB += dy^T t", 2.0 * M * N * r, eb * (M * N + M * r) + 4 * N * r))
-                for mask, role, fl, by in roles:
-                    a.backward_phases = mask
-                    _timed_launch(dev, lambda: _lib.lib().psob200_lora_linear_backward(C.byref(a), _lib.current_stream(dev)),
-                                  "psob200_lora_linear_backward", role, fl, by, (M, K, N, r))
+                    a.backward_phases = 12
+                    _timed_launch(dev, lambda: _lib.lib().psob200_lora_group_backward(C.byref(a), _lib.current_stream(dev)),
+                                  "psob200_lora_group_backward", "dA += u^T x ; dB += dy^T t (one launch)",
+                                  2.0 * M * G * r * (K + N), eb * (M * K + M * G * N + 2 * M * G * r) + 4 * G * r * (K + N),
+                                  (M, K, G * N, r))
             else:
                 if side:
                     a.backward_phases = 3  # PSOB200_BWD_INPUT_GRAD: u (+ ut), dx
-                _lib.launch(dev, "psob200_lora_linear_backward", C.byref(a), _lib.current_stream(dev))
+                _lib.launch(dev, "psob200_lora_group_backward", C.byref(a), _lib.current_stream(dev))
             if side:
                 st = _wgrad_side_stream(dev)
                 st.wait_stream(torch.cuda.current_stream(dev))
                 a.backward_phases = 12  # PSOB200_BWD_WEIGHT_GRAD: dA, dB
-                _lib.launch(dev, "psob200_lora_linear_backward", C.byref(a), st.cuda_stream)
+                _lib.launch(dev, "psob200_lora_group_backward", C.byref(a), st.cuda_stream)
                 _WGRAD_SIDE["pending"].setdefault(dev, []).append((x2, tt, dy2, keep))  # alive until the join
                 keep = []
                 _arm_wgrad_join(dev)
@@ -323,7 +469,7 @@ class _LoraLinearFn(torch.autograd.Function):
             dx = dx.view(ctx.x_shape)
             if dx.dtype != ctx.x_dtype:
                 dx = dx.to(ctx.x_dtype)
-        return dx, None, None, None, None
+        return (dx, None, None) + (None,) * (2 * G)
 
 
 def _grad_buffer(p: torch.nn.Parameter) -> torch.Tensor:
@@ -386,16 +532,59 @@ def enable_adapters(model: nn.Module) -> None:
         m.enable_adapters(True)
 
 
+def fuse_attention_projections(model: nn.Module) -> int:
+    """Stack the LoRA-wrapped projections that share their input: ``to_q / to_k / to_v`` of every self-attention module become
+    one ``LoRAProjectionGroup`` (G = 3), ``to_k / to_v`` of every cross-attention module one (G = 2).  ``PSOAttnProcessor2_0``
+    then issues one launch per group (forward), one for the input gradient and one for the weight gradients (backward) instead of
+    2 + 4 per projection.  Call it after ``add_adapter`` and BEFORE building ``LoRAGradBucket`` / ``FusedLoRAOptimizer`` (the flat
+    layout follows ``lora_parameters()``, which keeps a group's matrices adjacent).  Modules whose rank is not a multiple of 8,
+    or whose projections have biases or different shapes, keep the per-projection path.  Returns the number of groups."""
+    n = 0
+    for m in model.modules():
+        q, k, v = (getattr(m, a, None) for a in ("to_q", "to_k", "to_v"))
+        if not all(isinstance(t, LoRALinear) for t in (q, k, v)) or "_psob200_groups" in m.__dict__:
+            continue
+        if q.r[q.active_adapter] % 8 or any(t.base_layer.bias is not None for t in (q, k, v)):
+            continue
+        same = lambda a, b: (a.in_features, a.out_features, a.r, a.scaling) == (b.in_features, b.out_features, b.r, b.scaling)
+        if same(k, v) and same(q, k):
+            members, key = [q, k, v], "qkv"
+        elif same(k, v):
+            members, key = [k, v], "kv"
+        else:
+            continue
+        group = LoRAProjectionGroup(members)
+        for t in members:
+            t.__dict__["_psob200_group"] = group
+        m.__dict__["_psob200_groups"] = {key: group}
+        n += 1
+    return n
+
+
+def projection_groups(model: nn.Module) -> list:
+    return [g for m in model.modules() for g in m.__dict__.get("_psob200_groups", {}).values()]
+
+
 def refresh_operands(model: nn.Module) -> None:
     for m in lora_layers(model):
         m.refresh_operands()
+    for g in projection_groups(model):
+        g.refresh_operands()
 
 
 def lora_parameters(model: nn.Module):
-    out = []
+    """The trainable adapter matrices in FLAT-LAYOUT order: per projection ``A, B``; for a stacked group all ``A`` of its
+    members, then all ``B`` -- so that a group's matrices are adjacent in the flat buffers built from this list."""
+    out, seen = [], set()
     for m in lora_layers(model):
-        n = m.active_adapter
-        out += [m.lora_A[n].weight, m.lora_B[n].weight]
+        g = m.__dict__.get("_psob200_group")
+        if g is None:
+            n = m.active_adapter
+            out += [m.lora_A[n].weight, m.lora_B[n].weight]
+        elif id(g) not in seen:
+            seen.add(id(g))
+            out += [l.lora_A[l.active_adapter].weight for l in g.layers]
+            out += [l.lora_B[l.active_adapter].weight for l in g.layers]
     return out
 
 
@@ -660,13 +849,20 @@ class PSOAttnProcessor2_0:
         bsz = hidden_states.shape[0]
         if getattr(attn, "group_norm", None) is not None:
             hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
-        query = attn.to_q(hidden_states)
-        if encoder_hidden_states is None:
-            encoder_hidden_states = hidden_states
-        elif getattr(attn, "norm_cross", None):
-            encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
-        key = attn.to_k(encoder_hidden_states)
-        value = attn.to_v(encoder_hidden_states)
+        groups = attn.__dict__.get("_psob200_groups")  # lora.fuse_attention_projections: stacked q / k / v (or k / v) launches
+        if encoder_hidden_states is None and groups is not None and "qkv" in groups:
+            query, key, value = groups["qkv"](hidden_states)
+        else:
+            query = attn.to_q(hidden_states)
+            if encoder_hidden_states is None:
+                encoder_hidden_states = hidden_states
+            elif getattr(attn, "norm_cross", None):
+                encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
+            if groups is not None and "kv" in groups:
+                key, value = groups["kv"](encoder_hidden_states)
+            else:
+                key = attn.to_k(encoder_hidden_states)
+                value = attn.to_v(encoder_hidden_states)
         inner = key.shape[-1]
         hd = inner // attn.heads
         query = query.view(bsz, -1, attn.heads, hd).transpose(1, 2)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 def test_binding_loads_and_struct_sizes_match(built_lib):
     from pairwise_sample_optimization_b200 import _lib
     lib = _lib.lib()  # raises on any ABI mismatch (psob200_struct_size check)
-    assert lib.psob200_abi_version() == 1
+    assert lib.psob200_abi_version() == 2
     assert lib.psob200_strerror(0) == b"ok"
     assert b"workspace" in lib.psob200_strerror(-6)
     assert lib.psob200_pair_loss_workspace_bytes(0) == 16

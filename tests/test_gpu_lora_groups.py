@@ -1,0 +1,154 @@
+"""Stacked LoRA projections (psob200_lora_group_*; lora.LoRAProjectionGroup / fuse_attention_projections): G projections that
+share their input as ONE problem list per direction -- t / u as tiles of the same launch as y / dx (flags per row block),
+q / k / v stacked along N, dx as one reduction over the G gradients, dA + dB_g as one launch -- against the per-projection
+oracle (oracle.lora.lora_linear_rounded_flow: the peft flow with the 16-bit rounding points of a half-precision run) and
+against the per-projection product path."""
+import pytest
+import torch
+
+from oracle import lora as olora
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L(built_lib):
+    from pairwise_sample_optimization_b200 import lora
+    return lora
+
+
+def _mk(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype)
+
+
+def _layers(L, G, K, N, r, dtype, seed):
+    out = []
+    for g in range(G):
+        base = torch.nn.Linear(K, N, bias=False)
+        with torch.no_grad():
+            base.weight.copy_(_mk((N, K), seed + 10 * g, K ** -0.5, torch.float32))
+        lay = L.LoRALinear(base.to(device="cuda", dtype=dtype), r, 2 * r)
+        with torch.no_grad():
+            lay.lora_B["default"].weight.copy_(_mk((N, r), seed + 10 * g + 2, 0.05, torch.float32))
+        out.append(lay)
+    return out
+
+
+def _ulp_ok(got, want64, dtype, what, slack=None):
+    w = want64.float()
+    eps = 2.0 ** (-7 if dtype == torch.bfloat16 else -10)
+    ulp = w.abs() * eps + 1e-5 * w.abs().max()
+    if slack is not None:
+        ulp = ulp + eps * slack.float().reshape(w.shape)
+    bad = (got.float().cpu() - w).abs() > ulp
+    assert not bool(bad.any()), f"{what}: {int(bad.sum())} of {bad.numel()} elements off by more than 1 ulp"
+
+
+def _rel(got, want64):
+    return ((got.double().cpu() - want64).abs().max() / want64.abs().max()).item()
+
+
+@pytest.mark.parametrize("G,M_shape,K,N,r,need_dx", [(3, (2, 300), 640, 640, 8, True), (3, (4, 256), 1280, 1280, 64, True),
+                                                     (2, (4, 77), 2048, 640, 16, False), (2, (3, 77), 2048, 1280, 64, True),
+                                                     (3, (1, 130), 320, 320, 128, True), (3, (8, 1024), 1280, 1280, 64, True),
+                                                     (3, (2, 1024), 640, 640, 8, True)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_stacked_group_forward_backward_vs_oracle(L, G, M_shape, K, N, r, need_dx, dtype):
+    layers = _layers(L, G, K, N, r, dtype, 3)
+    group = L.LoRAProjectionGroup(layers)
+    x = _mk(M_shape + (K,), 5, 1.0, dtype).cuda().requires_grad_(need_dx)
+    dys = [_mk(M_shape + (N,), 7 + g, 1.0, dtype).cuda() for g in range(G)]
+    ys = group(x)
+    assert len(ys) == G and ys[0].shape == M_shape + (N,)
+    torch.autograd.backward(list(ys), dys)
+    torch.cuda.synchronize()
+    assert int(L._flags_workspace(torch.device("cuda", 0)).abs().sum()) == 0  # every launch leaves the dependency flags zeroed
+    dx_want = 0
+    slack_dx = 0
+    for g, lay in enumerate(layers):
+        A, Bm = lay.lora_A["default"].weight, lay.lora_B["default"].weight
+        o = olora.lora_linear_rounded_flow(x.detach().cpu(), lay.base_layer.weight.cpu(), None, A.detach().cpu(), Bm.detach().cpu(),
+                                           dys[g].cpu(), scaling=2.0, dtype=dtype)
+        # y: 1 ulp of the output type (+ what 1-ulp differences of the 16-bit t can do: |B| summed over r per unit of t's ulp)
+        slack_y = (o["T"].abs() @ Bm.detach().cpu().to(dtype).double().abs().t())
+        _ulp_ok(ys[g].detach().reshape(-1, N), o["y"].reshape(-1, N), dtype, f"y[{g}]", slack_y)
+        dx_want = dx_want + o["dX"]
+        slack_dx = slack_dx + (o["U"].abs() @ A.detach().cpu().to(dtype).double().abs())
+        assert _rel(A.grad, o["dA"]) <= 1e-3 and _rel(Bm.grad, o["dB"]) <= 1e-3, (g, _rel(A.grad, o["dA"]), _rel(Bm.grad, o["dB"]))
+    if need_dx:
+        _ulp_ok(x.grad.reshape(-1, K), dx_want.reshape(-1, K), dtype, "dx", slack_dx)
+    else:
+        assert x.grad is None
+
+
+def test_fused_launches_equal_the_separate_launch_sequence(L):
+    """The in-launch dependency (flags) changes WHEN t / u are computed, not how: results are bit-identical to the
+    launch-by-launch sequence (forward_phases / backward_phases one at a time, the instrumented path)."""
+    dtype = torch.bfloat16
+    outs = []
+    for timing in (False, True):
+        layers = _layers(L, 3, 1280, 1280, 64, dtype, 11)
+        group = L.LoRAProjectionGroup(layers)
+        x = _mk((2, 1024, 1280), 5, 1.0, dtype).cuda().requires_grad_(True)
+        dys = [_mk((2, 1024, 1280), 7 + g, 1.0, dtype).cuda() for g in range(3)]
+        sink = []
+        if timing:
+            L.set_timing_sink(sink)
+        try:
+            ys = group(x)
+            torch.autograd.backward(list(ys), dys)
+        finally:
+            L.set_timing_sink(None)
+        torch.cuda.synchronize()
+        if timing:
+            assert len(sink) == 3  # forward, input gradient, weight gradients: three launches for three projections
+        outs.append([y.detach().clone() for y in ys] + [x.grad.clone()] +
+                    [l.lora_A["default"].weight.grad.clone() for l in layers])
+    for a, b in zip(outs[0][:4], outs[1][:4]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs[0][4:], outs[1][4:]):  # split reductions accumulate with fp32 atomics: order-dependent in the last bits
+        assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item()
+
+
+def test_processor_with_fused_projections_matches_the_per_projection_path(L):
+    from tests.test_gpu_lora import _Attention
+    dtype = torch.bfloat16
+    res = []
+    for fuse in (False, True):
+        for cross in (None, 2048):
+            torch.manual_seed(3)
+            attn = _Attention(640, cross, 10, 64).to(device="cuda", dtype=dtype)
+            wrapped = L.add_adapter(attn, L.LoraConfig(r=8, lora_alpha=8))
+            g = torch.Generator().manual_seed(4)
+            for m in wrapped:
+                with torch.no_grad():
+                    m.lora_B["default"].weight.copy_(torch.randn(m.lora_B["default"].weight.shape, generator=g) * 0.05)
+            if fuse:
+                assert L.fuse_attention_projections(attn) == 1
+            attn.processor = L.PSOAttnProcessor2_0()
+            opt = L.FusedLoRAOptimizer(attn)
+            if fuse:  # the flat layout keeps a group's matrices adjacent: the stacked operands are views, not copies
+                grp = L.projection_groups(attn)[0]
+                assert grp.stacked_operand("a", dtype).data_ptr() == grp.layers[0]._operand("a", dtype).data_ptr()
+                assert grp.stacked_grad("b").data_ptr() == grp.layers[0].lora_B["default"].weight.grad.data_ptr()
+            x = _mk((2, 256, 640), 9, 1.0, dtype).cuda().requires_grad_(True)
+            enc = None if cross is None else _mk((2, 77, 2048), 10, 1.0, dtype).cuda()
+            y = attn(x, encoder_hidden_states=enc)
+            y.backward(_mk((2, 256, 640), 12, 1.0, dtype).cuda())
+            torch.cuda.synchronize()
+            grads = {n: p.grad.clone() for n, p in attn.named_parameters() if p.requires_grad}
+            res.append((y.detach().clone(), x.grad.clone(), grads))
+            L.disable_adapters(attn)
+            with torch.no_grad():
+                y0 = attn(x, encoder_hidden_states=enc)
+            L.enable_adapters(attn)
+            res[-1] = res[-1] + (y0.clone(),)
+    for k in (0, 1):  # self-attention, cross-attention
+        (y_a, dx_a, g_a, y0_a), (y_b, dx_b, g_b, y0_b) = res[k], res[2 + k]
+        assert torch.equal(y0_a, y0_b)  # the frozen-reference pass: same reduction order per element, any tile width
+        assert (y_a.float() - y_b.float()).abs().max().item() <= 2e-2 * y_a.float().abs().max().item()
+        assert (dx_a.float() - dx_b.float()).abs().max().item() <= 2e-2 * dx_a.float().abs().max().item()
+        assert set(g_a) == set(g_b)
+        for n in g_a:
+            assert (g_a[n] - g_b[n]).abs().max().item() <= 2e-2 * g_a[n].abs().max().item() + 1e-6, n
