@@ -312,6 +312,7 @@ class B200Arm:
             from pairwise_sample_optimization_b200 import feed_forward
             feed_forward.install_fused_geglu(unet)
         lora.set_wgrad_stream(args.wgrad_stream)
+        lora.set_in_launch_dependencies(not args.no_inlaunch_deps)
         unet.train()
         if args.grad_checkpointing:
             unet.enable_gradient_checkpointing()  # turbo trainer :358
@@ -973,6 +974,8 @@ def main():
     ap.add_argument("--tiny", action="store_true", help="debug: the 32/64-channel fixture instead of the SDXL architecture")
     ap.add_argument("--no-fuse-projections", dest="fuse_projections", action="store_false", default=True,
                     help="one launch sequence per projection instead of stacked q / k / v (k / v) groups")
+    ap.add_argument("--no-inlaunch-deps", action="store_true",
+                    help="A/B: t / u as launches of their own (PDL overlap) instead of tiles of the main launch")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager-on-this-GPU baseline")
     ap.add_argument("--no-turbo64", action="store_true", help="skip the short configs[1] block after the main timing")
     args = ap.parse_args()

@@ -190,6 +190,13 @@ class LoRALinear(nn.Module):
 
 
 _FLAGS: dict = {}
+_IN_LAUNCH_DEPS = {"enabled": True}
+
+
+def set_in_launch_dependencies(enabled: bool) -> None:
+    """A/B switch: False issues t / u as launches of their own (programmatic dependent launch overlaps them with the main
+    pass, as in round 1) instead of as tiles of the main launch.  Results are bit-identical."""
+    _IN_LAUNCH_DEPS["enabled"] = bool(enabled)
 
 
 def _flags_workspace(dev: torch.device) -> torch.Tensor:
@@ -251,7 +258,9 @@ class LoRAProjectionGroup:
     def _adjacent(self, tensors) -> bool:
         t0 = tensors[0]
         step = t0.numel() * t0.element_size()
-        return all(t.is_contiguous() and t.data_ptr() == t0.data_ptr() + g * step for g, t in enumerate(tensors))
+        base = t0.untyped_storage().data_ptr()  # slices of ONE buffer (the flat layout), not neighbours by allocator luck
+        return all(t.is_contiguous() and t.untyped_storage().data_ptr() == base and t.data_ptr() == t0.data_ptr() + g * step
+                   for g, t in enumerate(tensors))
 
     def stacked_operand(self, which: str, dtype: torch.dtype) -> torch.Tensor:
         """[G r, K] (which = "a") or [G N, r] ("b") 16-bit, row pitch a multiple of 8 elements."""
@@ -367,8 +376,9 @@ class _LoraGroupFn(torch.autograd.Function):
             if want_wgrad:
                 tt = torch.empty(G * r, _ceil8(M), dtype=dtype, device=dev)
                 a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
-            ws = _flags_workspace(dev)  # t becomes tiles of the same launch as y
-            a.flags, a.flags_len = ws.data_ptr(), ws.numel()
+            if _IN_LAUNCH_DEPS["enabled"]:
+                ws = _flags_workspace(dev)  # t becomes tiles of the same launch as y
+                a.flags, a.flags_len = ws.data_ptr(), ws.numel()
             fl_t = 2.0 * M * G * r * K
             by_t = 2 * (G * r * K + M * G * r * (2 if tt is not None else 1))
         if _TIMING is None:
@@ -424,8 +434,9 @@ class _LoraGroupFn(torch.autograd.Function):
             u = torch.empty(M, gr8, dtype=dtype, device=dev)
             a.u, a.ldu = u.data_ptr(), gr8
             keep.append(u)
-            ws = _flags_workspace(dev)
-            a.flags, a.flags_len = ws.data_ptr(), ws.numel()
+            if _IN_LAUNCH_DEPS["enabled"]:
+                ws = _flags_workspace(dev)
+                a.flags, a.flags_len = ws.data_ptr(), ws.numel()
             if ctx.want_wgrad:
                 ga, gb = group.stacked_grad("a"), group.stacked_grad("b")
                 ut = torch.empty(G * r, _ceil8(M), dtype=dtype, device=dev)

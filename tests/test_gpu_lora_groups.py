@@ -83,26 +83,27 @@ def test_stacked_group_forward_backward_vs_oracle(L, G, M_shape, K, N, r, need_d
 
 
 def test_fused_launches_equal_the_separate_launch_sequence(L):
-    """The in-launch dependency (flags) changes WHEN t / u are computed, not how: results are bit-identical to the
-    launch-by-launch sequence (forward_phases / backward_phases one at a time, the instrumented path)."""
+    """The in-launch dependency (flags) changes WHEN t / u are computed, not how: y and dx are bit-identical to the
+    launch-by-launch sequence (t, y / u, dx as launches of their own, ordered by the stream)."""
     dtype = torch.bfloat16
     outs = []
-    for timing in (False, True):
+    for deps in (True, False):
+        torch.manual_seed(21)  # LoRALinear draws A from the global generator
         layers = _layers(L, 3, 1280, 1280, 64, dtype, 11)
         group = L.LoRAProjectionGroup(layers)
         x = _mk((2, 1024, 1280), 5, 1.0, dtype).cuda().requires_grad_(True)
         dys = [_mk((2, 1024, 1280), 7 + g, 1.0, dtype).cuda() for g in range(3)]
         sink = []
-        if timing:
-            L.set_timing_sink(sink)
+        L.set_in_launch_dependencies(deps)
+        L.set_timing_sink(sink)
         try:
             ys = group(x)
             torch.autograd.backward(list(ys), dys)
         finally:
             L.set_timing_sink(None)
+            L.set_in_launch_dependencies(True)
         torch.cuda.synchronize()
-        if timing:
-            assert len(sink) == 3  # forward, input gradient, weight gradients: three launches for three projections
+        assert len(sink) == 3  # forward, input gradient, weight gradients: three host calls for three projections
         outs.append([y.detach().clone() for y in ys] + [x.grad.clone()] +
                     [l.lora_A["default"].weight.grad.clone() for l in layers])
     for a, b in zip(outs[0][:4], outs[1][:4]):
