@@ -10,7 +10,8 @@ stream + the fused GEGLU kernels, captured in ONE CUDA graph and replayed, with 
    weights: (1) the plain eager 4-forward ``product_micro_step`` with the stock GEGLU; (2a) the batched step with the fused
    GEGLU, eager, one stream -- statistical agreement with (1) (two bf16 runs: loss 1e-2, gradient cosine >= 0.995);
    (2b) the batched step as bench.py times it (second-stream reference forward, side-stream dA / dB, CUDA-graph replay) --
-   loss BIT-IDENTICAL to (2a), gradient equal up to the fp32 atomic order (cosine >= 0.999999, worst element 1e-3).
+   loss BIT-IDENTICAL to (2a), gradient as close to (2a) as a second run of (2a) itself is (the backward of the bf16 UNet is
+   not run-to-run deterministic: atomics in stock attention / convolution backward kernels and in the split reductions).
 """
 import copy
 
@@ -164,9 +165,20 @@ def test_full_sdxl_fixture_graph_replayed_batched_step_vs_eager_separate_forward
     # absolute; measured: loss 5e-3, gradient cosine 0.9989, norm ratio 0.995
     assert abs(loss_b - loss_ref) <= 1e-2 * abs(loss_ref), report
     assert cos_ab >= 0.995 and abs(report[3] - 1.0) <= 2e-2, report
+    # run-to-run floor: the SAME eager one-stream step again.  The forward is deterministic (bit-identical loss); the backward is
+    # not -- stock torch kernels in it (cuDNN attention backward, convolution weight / data gradients) and this library's split
+    # reductions accumulate with atomics, and 70 bf16 blocks amplify the last-bit differences (tools/diag_step_determinism.py:
+    # cosine 0.99990, worst element 1.5e-2 of max |g| between two identical runs, with or without any of the ingredients below)
+    opt.bucket.zero_()
+    loss_b2 = micro_step.product_micro_step_batched(pso, lora, unet, d, sched, **kw)
+    torch.cuda.synchronize()
+    flat_b2 = opt.bucket.flat.double().cpu().clone()
+    assert float(loss_b2.item()) == loss_b
+    floor_cos = (torch.dot(flat_b, flat_b2) / (flat_b.norm() * flat_b2.norm())).item()
+    floor_worst = ((flat_b - flat_b2).abs().max() / flat_b.abs().max()).item()
     # arm 2b: what bench.py times -- the SAME kernels on the SAME shapes, now with the reference forward on a second stream,
-    # dA / dB on the weight-gradient side stream, captured in a CUDA graph and replayed: the loss must be bit-identical and the
-    # gradient may differ only by the order of the fp32 atomic accumulation in dA / dB
+    # dA / dB on the weight-gradient side stream, captured in a CUDA graph and replayed: the loss must be BIT-IDENTICAL and the
+    # gradient must agree with the eager run as well as two eager runs agree with each other
     lora.set_wgrad_stream(True)
     try:
         graph, static_loss = _capture(pso, lora, unet, d, sched, torch.cuda.Stream(), **kw)
@@ -179,8 +191,8 @@ def test_full_sdxl_fixture_graph_replayed_batched_step_vs_eager_separate_forward
             flat_g = opt.bucket.flat.double().cpu()
             cos = (torch.dot(flat_b, flat_g) / (flat_b.norm() * flat_g.norm())).item()
             worst = ((flat_b - flat_g).abs().max() / flat_b.abs().max()).item()
-            report = (replay, loss_g, loss_b, cos, worst)
+            report = (replay, loss_g, loss_b, cos, worst, floor_cos, floor_worst)
             assert loss_g == loss_b, report
-            assert cos >= 0.999999 and worst <= 1e-3, report
+            assert 1.0 - cos <= 3.0 * (1.0 - floor_cos) + 1e-6 and worst <= 3.0 * floor_worst + 1e-3, report
     finally:
         lora.set_wgrad_stream(False)
