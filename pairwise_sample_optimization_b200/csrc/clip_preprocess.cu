@@ -9,8 +9,10 @@
 //   * per axis: scale = in / out, support = 2 * max(scale, 1), taps centred on (j + 0.5) * scale, bicubic a = -0.5, weights
 //     normalised to sum 1 in double, then rounded to 22 fractional bits  (host: psob200_resample_plan);
 //   * horizontal pass first, result rounded and clamped to uint8 ((acc + 2^21) >> 22), then the vertical pass on those bytes.
-// HBM-bound byte work: B * (3 H W read + 3 h w * sizeof(out) written); one CTA per (image, block of output rows) keeps the
-// horizontally resized rows it needs in shared memory, so the intermediate image never touches HBM.
+// Byte work: B * (3 H W read + 3 h w * sizeof(out) written) of HBM traffic; one CTA per (image, block of output rows) stages the
+// input rows it needs in shared memory as bytes (each read from HBM once per CTA, 128-bit loads), runs the horizontal pass
+// shared -> shared and the vertical pass shared -> global, so the intermediate image never touches HBM.  The arithmetic (11 + 11
+// integer taps per output at 512 -> 224) runs on the CUDA cores by design: this is not a GEMM.
 #include <cmath>
 #include <vector>
 
@@ -26,42 +28,8 @@ __device__ __forceinline__ int clip8(int v) {
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-// one source sample as the byte PIL would see: uint8 NHWC as is; float NCHW quantised like
-// ((x + 1.0) * 127.5).clamp(0, 255).to(torch.uint8) evaluated in the tensor's own type (truncation toward zero)
-template <typename TS>
-struct SrcPixel;
-template <>
-struct SrcPixel<uint8_t> {
-  static __device__ __forceinline__ int get(const uint8_t* img, long long, long long in_w, long long y, long long x, int c) {
-    return img[(y * in_w + x) * 3 + c];
-  }
-};
-template <>
-struct SrcPixel<float> {
-  static __device__ __forceinline__ int get(const float* img, long long in_h, long long in_w, long long y, long long x, int c) {
-    float v = __fmul_rn(__fadd_rn(img[((long long)c * in_h + y) * in_w + x], 1.0f), 127.5f);
-    v = fminf(fmaxf(v, 0.f), 255.f);
-    return (int)v;
-  }
-};
-template <>
-struct SrcPixel<__half> {
-  static __device__ __forceinline__ int get(const __half* img, long long in_h, long long in_w, long long y, long long x, int c) {
-    __half v = __hmul(__hadd(img[((long long)c * in_h + y) * in_w + x], __float2half(1.0f)), __float2half(127.5f));
-    float f = fminf(fmaxf(__half2float(v), 0.f), 255.f);
-    return (int)f;
-  }
-};
-template <>
-struct SrcPixel<__nv_bfloat16> {
-  static __device__ __forceinline__ int get(const __nv_bfloat16* img, long long in_h, long long in_w, long long y, long long x,
-                                            int c) {
-    __nv_bfloat16 v = __hmul(__hadd(img[((long long)c * in_h + y) * in_w + x], __float2bfloat16(1.0f)), __float2bfloat16(127.5f));
-    float f = fminf(fmaxf(__bfloat162float(v), 0.f), 255.f);
-    return (int)f;
-  }
-};
-
+// A source sample becomes the byte PIL would see: uint8 NHWC as is; float NCHW quantised like
+// ((x + 1.0) * 127.5).clamp(0, 255).to(torch.uint8) evaluated in the tensor's own type (truncation toward zero) -- quantize8.
 template <typename TD>
 __device__ __forceinline__ TD cvt_px(float v);
 template <> __device__ __forceinline__ float cvt_px<float>(float v) { return v; }
@@ -75,14 +43,59 @@ struct PreKernelArgs {
   const float* table;
   long long in_h, in_w, out_h, out_w, crop_top, crop_left;
   int taps_h, taps_v, rows_per_cta, max_in_rows;
+  int x_lo, x_w;  // input columns [x_lo, x_lo + x_w) are all the horizontal taps of the crop window touch (x_w a multiple of 8)
 };
 
-// grid = (ceil(out_h / rows_per_cta), B).  Shared memory: [max_in_rows][out_w][3] bytes of horizontally resized rows.
+// 8 consecutive samples of one input row as the bytes PIL would see (see SrcPixel), packed little-endian into two words.
+template <typename TS>
+__device__ __forceinline__ uint2 quantize8(const TS* p, long long valid) {
+  uint32_t w[2] = {0u, 0u};
+  if constexpr (sizeof(TS) == 2) {
+    if (valid >= 8 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+      const TS* e = reinterpret_cast<const TS*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const TS v = __hmul(__hadd(e[j], static_cast<TS>(1.0f)), static_cast<TS>(127.5f));
+        const float f = fminf(fmaxf(static_cast<float>(v), 0.f), 255.f);
+        w[j >> 2] |= (uint32_t)(int)f << (8 * (j & 3));
+      }
+      return make_uint2(w[0], w[1]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < valid) {
+      int q;
+      if constexpr (sizeof(TS) == 4) {
+        float v = __fmul_rn(__fadd_rn(p[j], 1.0f), 127.5f);
+        q = (int)fminf(fmaxf(v, 0.f), 255.f);
+      } else {
+        const TS v = __hmul(__hadd(p[j], static_cast<TS>(1.0f)), static_cast<TS>(127.5f));
+        q = (int)fminf(fmaxf(static_cast<float>(v), 0.f), 255.f);
+      }
+      w[j >> 2] |= (uint32_t)q << (8 * (j & 3));
+    }
+  }
+  return make_uint2(w[0], w[1]);
+}
+
+// grid = (ceil(out_h / rows_per_cta), B).  Shared memory (planar, so that every pass reads and writes consecutive bytes):
+//   src_s [3][max_in_rows][x_w]   the input rows this CTA needs, quantised to bytes, read from HBM exactly once per CTA
+//   hrow_s[3][max_in_rows][out_w] the same rows after the horizontal pass (rounded to bytes, as Pillow does)
+//   kh_s  [out_w][taps_h], bh_s[out_w][2]  horizontal coefficients of the crop window
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(kPreThreads) clip_preprocess_kernel(const PreKernelArgs a) {
-  extern __shared__ unsigned char hrows[];
+  extern __shared__ __align__(16) unsigned char pre_smem[];
   __shared__ float table[768];
+  const int out_w = (int)a.out_w, x_w = a.x_w, rows_cap = a.max_in_rows;
+  unsigned char* src_s = pre_smem;
+  unsigned char* hrow_s = src_s + (size_t)3 * rows_cap * x_w;
+  int32_t* kh_s = reinterpret_cast<int32_t*>(hrow_s + (((size_t)3 * rows_cap * out_w + 15) & ~(size_t)15));
+  int32_t* bh_s = kh_s + out_w * a.taps_h;
   for (int i = threadIdx.x; i < 768; i += kPreThreads) table[i] = a.table[i];
+  for (int i = threadIdx.x; i < out_w * a.taps_h; i += kPreThreads) kh_s[i] = a.coeffs_h[(long long)a.crop_left * a.taps_h + i];
+  for (int i = threadIdx.x; i < out_w * 2; i += kPreThreads) bh_s[i] = a.bounds_h[2 * a.crop_left + i];
   const long long b = blockIdx.y;
   const long long r0 = (long long)blockIdx.x * a.rows_per_cta;  // first output row (inside the crop window) of this CTA
   const long long r1 = r0 + a.rows_per_cta < a.out_h ? r0 + a.rows_per_cta : a.out_h;
@@ -90,33 +103,51 @@ __global__ void __launch_bounds__(kPreThreads) clip_preprocess_kernel(const PreK
   const long long y_first = a.bounds_v[2 * (a.crop_top + r0)];
   const long long y_last = a.bounds_v[2 * (a.crop_top + r1 - 1)] + a.bounds_v[2 * (a.crop_top + r1 - 1) + 1];  // exclusive
   const int n_in = (int)(y_last - y_first);
-  const TS* img = reinterpret_cast<const TS*>(a.src) + b * 3 * a.in_h * a.in_w;
-  const int row_elems = (int)a.out_w * 3;
-  // ---- horizontal pass: every needed input row -> out_w x 3 bytes
-  for (int i = threadIdx.x; i < n_in * row_elems; i += kPreThreads) {
-    const int yy = i / row_elems, rem = i - yy * row_elems;
-    const int xx = rem / 3, c = rem - xx * 3;
-    const int j = (int)a.crop_left + xx;
-    const int xmin = a.bounds_h[2 * j], n = a.bounds_h[2 * j + 1];
-    const int32_t* k = a.coeffs_h + (long long)j * a.taps_h;
-    int acc = 1 << (kPrecisionBits - 1);
-    for (int t = 0; t < n; ++t) acc += SrcPixel<TS>::get(img, a.in_h, a.in_w, y_first + yy, xmin + t, c) * k[t];
-    hrows[i] = (unsigned char)clip8(acc);
+  // ---- stage the needed input window as bytes
+  if constexpr (sizeof(TS) == 1) {  // uint8 NHWC
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(a.src) + b * 3 * a.in_h * a.in_w;
+    for (int i = threadIdx.x; i < n_in * x_w * 3; i += kPreThreads) {
+      const int yy = i / (x_w * 3), rem = i - yy * (x_w * 3);
+      const int x = rem / 3, c = rem - x * 3;
+      const long long gx = a.x_lo + x;
+      src_s[((size_t)c * rows_cap + yy) * x_w + x] = gx < a.in_w ? __ldg(img + ((y_first + yy) * a.in_w + gx) * 3 + c) : 0;
+    }
+  } else {  // float NCHW: 8 samples per thread per step, one 8-byte shared store
+    const TS* img = reinterpret_cast<const TS*>(a.src) + b * 3 * a.in_h * a.in_w;
+    const int vec_per_row = x_w / 8;
+    for (int i = threadIdx.x; i < 3 * n_in * vec_per_row; i += kPreThreads) {
+      const int c = i / (n_in * vec_per_row), rem = i - c * (n_in * vec_per_row);
+      const int yy = rem / vec_per_row, v = rem - yy * vec_per_row;
+      const long long gx = a.x_lo + 8 * v;
+      const uint2 q = quantize8<TS>(img + ((long long)c * a.in_h + y_first + yy) * a.in_w + gx, a.in_w - gx);
+      *reinterpret_cast<uint2*>(src_s + ((size_t)c * rows_cap + yy) * x_w + 8 * v) = q;
+    }
   }
   __syncthreads();
-  // ---- vertical pass + rescale / normalise table + channels-first store (consecutive threads: consecutive x)
+  // ---- horizontal pass: thread -> (plane, input row, output column), consecutive threads = consecutive columns
+  for (int i = threadIdx.x; i < 3 * n_in * out_w; i += kPreThreads) {
+    const int pr = i / out_w, xx = i - pr * out_w;  // pr = c * n_in + yy
+    const int c = pr / n_in, yy = pr - c * n_in;
+    const int xmin = bh_s[2 * xx] - a.x_lo, n = bh_s[2 * xx + 1];
+    const int32_t* k = kh_s + xx * a.taps_h;
+    const unsigned char* row = src_s + ((size_t)c * rows_cap + yy) * x_w + xmin;
+    int acc = 1 << (kPrecisionBits - 1);
+    for (int t = 0; t < n; ++t) acc += (int)row[t] * k[t];
+    hrow_s[((size_t)c * rows_cap + yy) * out_w + xx] = (unsigned char)clip8(acc);
+  }
+  __syncthreads();
+  // ---- vertical pass + rescale / normalise table + channels-first store
   TD* out = reinterpret_cast<TD*>(a.dst) + b * 3 * a.out_h * a.out_w;
-  const int n_out = (int)(r1 - r0) * row_elems;
-  for (int i = threadIdx.x; i < n_out; i += kPreThreads) {
-    const int c = i / ((int)(r1 - r0) * (int)a.out_w);
-    const int rem = i - c * (int)(r1 - r0) * (int)a.out_w;
-    const int rr = rem / (int)a.out_w, xx = rem - rr * (int)a.out_w;
+  const int n_rows = (int)(r1 - r0);
+  for (int i = threadIdx.x; i < 3 * n_rows * out_w; i += kPreThreads) {
+    const int pr = i / out_w, xx = i - pr * out_w;
+    const int c = pr / n_rows, rr = pr - c * n_rows;
     const long long j = a.crop_top + r0 + rr;
     const int ymin = a.bounds_v[2 * j], n = a.bounds_v[2 * j + 1];
     const int32_t* k = a.coeffs_v + j * a.taps_v;
-    const unsigned char* col = hrows + ((long long)(ymin - y_first) * a.out_w + xx) * 3 + c;
+    const unsigned char* col = hrow_s + ((size_t)c * rows_cap + (ymin - y_first)) * out_w + xx;
     int acc = 1 << (kPrecisionBits - 1);
-    for (int t = 0; t < n; ++t) acc += (int)col[(long long)t * row_elems] * k[t];
+    for (int t = 0; t < n; ++t) acc += (int)col[(size_t)t * out_w] * __ldg(k + t);
     out[((long long)c * a.out_h + (r0 + rr)) * a.out_w + xx] = cvt_px<TD>(table[c * 256 + clip8(acc)]);
   }
 }
@@ -198,23 +229,44 @@ extern "C" int psob200_clip_preprocess(const psob200_clip_preprocess_args* args,
   if (p.src_dtype != PSOB200_U8 && !valid_dtype(p.src_dtype)) return PSOB200_ERR_DTYPE;
   if (!valid_dtype(p.dst_dtype)) return PSOB200_ERR_DTYPE;
   if (p.B > 65535 || p.in_h > (1 << 20) || p.in_w > (1 << 20) || p.out_w > 4096) return PSOB200_ERR_SHAPE;
-  // rows per CTA: as many as keep the horizontally resized input rows within ~96 KB of shared memory (and >= 1)
+  // input columns the crop window's horizontal taps touch (host reads nothing from the device: recompute the two bounds)
+  auto h_bound = [&](long long j, int& xmin, int& n) {
+    const double scale = (double)p.in_w / (double)p.rs_w;
+    const double support = 2.0 * (scale < 1.0 ? 1.0 : scale);
+    const double center = (j + 0.5) * scale;
+    xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > (int)p.in_w) xmax = (int)p.in_w;
+    n = xmax - xmin;
+  };
+  int xa, na, xb, nb;
+  h_bound(p.crop_left, xa, na);
+  h_bound(p.crop_left + p.out_w - 1, xb, nb);
+  const int x_lo = xa & ~7;  // 8-sample vectors stay 16-byte aligned for 16-bit sources whose rows are
+  const int x_w = ((xb + nb - x_lo) + 7) & ~7;
+  // rows per CTA: as many as keep both shared-memory planes within 96 KB (two CTAs per SM), else within 200 KB
   const double vscale = (double)p.in_h / (double)p.rs_h;
-  const long long row_bytes = p.out_w * 3;
-  int rows = 16;
+  const size_t coef_bytes = (size_t)p.out_w * (p.taps_h + 2) * 4 + 16;
+  int rows = 0;
   long long max_in = 0;
-  for (; rows >= 1; rows >>= 1) {
-    max_in = (long long)std::ceil(rows * vscale) + p.taps_v + 2;
-    if (max_in * row_bytes <= 96 * 1024) break;
+  size_t smem = 0;
+  for (const size_t limit : {(size_t)96 * 1024, (size_t)200 * 1024}) {
+    for (rows = 16; rows >= 1; rows >>= 1) {
+      max_in = (long long)std::ceil(rows * vscale) + p.taps_v + 2;
+      smem = (size_t)3 * max_in * x_w + (((size_t)3 * max_in * p.out_w + 15) & ~(size_t)15) + coef_bytes;
+      if (smem <= limit) break;
+    }
+    if (rows >= 4 || (rows >= 1 && limit > 100 * 1024)) break;
   }
   if (rows < 1) return PSOB200_ERR_SHAPE;
-  const size_t smem = (size_t)(max_in * row_bytes);
   PreKernelArgs a;
   a.src = p.src; a.dst = p.dst;
   a.bounds_h = p.bounds_h; a.coeffs_h = p.coeffs_h; a.bounds_v = p.bounds_v; a.coeffs_v = p.coeffs_v;
   a.table = p.norm_table;
   a.in_h = p.in_h; a.in_w = p.in_w; a.out_h = p.out_h; a.out_w = p.out_w; a.crop_top = p.crop_top; a.crop_left = p.crop_left;
   a.taps_h = p.taps_h; a.taps_v = p.taps_v; a.rows_per_cta = rows; a.max_in_rows = (int)max_in;
+  a.x_lo = x_lo; a.x_w = x_w;
   const dim3 grid((unsigned)((p.out_h + rows - 1) / rows), (unsigned)p.B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static PerDevice<int> configured[12];
@@ -224,7 +276,7 @@ extern "C" int psob200_clip_preprocess(const psob200_clip_preprocess_args* args,
     auto kern = clip_preprocess_kernel<TS, TD>;                                                                       \
     std::atomic<int>& conf = configured[slot].here();                                                                 \
     if (smem > 48 * 1024 && !conf.load(std::memory_order_acquire)) {                                                  \
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);                        \
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);                        \
       if (e != cudaSuccess) return consume_launch_error("configure clip_preprocess_kernel", e);                       \
       conf.store(1, std::memory_order_release);                                                                       \
     }                                                                                                                 \
