@@ -84,7 +84,9 @@ __device__ __forceinline__ uint2 quantize8(const TS* p, long long valid) {
 //   src_s [3][max_in_rows][x_w]   the input rows this CTA needs, quantised to bytes, read from HBM exactly once per CTA
 //   hrow_s[3][max_in_rows][out_w] the same rows after the horizontal pass (rounded to bytes, as Pillow does)
 //   kh_s  [out_w][taps_h], bh_s[out_w][2]  horizontal coefficients of the crop window
-template <typename TS, typename TD>
+// kTH / kTV: compile-time tap counts (the trainers' 512 -> 224 resize has 11 + 11; the coefficient rows are zero-padded to the
+// tap count, so the unrolled loops always run all taps: a zero weight makes an unused sample harmless); 0 = run-time loops.
+template <typename TS, typename TD, int kTH, int kTV>
 __global__ void __launch_bounds__(kPreThreads) clip_preprocess_kernel(const PreKernelArgs a) {
   extern __shared__ __align__(16) unsigned char pre_smem[];
   __shared__ float table[768];
@@ -124,16 +126,37 @@ __global__ void __launch_bounds__(kPreThreads) clip_preprocess_kernel(const PreK
     }
   }
   __syncthreads();
-  // ---- horizontal pass: thread -> (plane, input row, output column), consecutive threads = consecutive columns
-  for (int i = threadIdx.x; i < 3 * n_in * out_w; i += kPreThreads) {
-    const int pr = i / out_w, xx = i - pr * out_w;  // pr = c * n_in + yy
-    const int c = pr / n_in, yy = pr - c * n_in;
-    const int xmin = bh_s[2 * xx] - a.x_lo, n = bh_s[2 * xx + 1];
-    const int32_t* k = kh_s + xx * a.taps_h;
-    const unsigned char* row = src_s + ((size_t)c * rows_cap + yy) * x_w + xmin;
-    int acc = 1 << (kPrecisionBits - 1);
-    for (int t = 0; t < n; ++t) acc += (int)row[t] * k[t];
-    hrow_s[((size_t)c * rows_cap + yy) * out_w + xx] = (unsigned char)clip8(acc);
+  // ---- horizontal pass: a thread owns (plane, output column) pairs and walks the input rows with its weights in registers;
+  // consecutive threads = consecutive columns (their taps overlap: the byte loads of a warp hit a few words, broadcast)
+  if constexpr (kTH > 0) {
+    for (int item = threadIdx.x; item < 3 * out_w; item += kPreThreads) {
+      const int c = item / out_w, xx = item - c * out_w;
+      const int xmin = bh_s[2 * xx] - a.x_lo;
+      int k[kTH];
+#pragma unroll
+      for (int t = 0; t < kTH; ++t) k[t] = kh_s[xx * kTH + t];
+      const unsigned char* row = src_s + (size_t)c * rows_cap * x_w + xmin;
+      unsigned char* dst = hrow_s + (size_t)c * rows_cap * out_w + xx;
+      for (int yy = 0; yy < n_in; ++yy) {
+        int acc = 1 << (kPrecisionBits - 1);
+#pragma unroll
+        for (int t = 0; t < kTH; ++t) acc += (int)row[t] * k[t];
+        *dst = (unsigned char)clip8(acc);
+        row += x_w;
+        dst += out_w;
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < 3 * n_in * out_w; i += kPreThreads) {
+      const int pr = i / out_w, xx = i - pr * out_w;  // pr = c * n_in + yy
+      const int c = pr / n_in, yy = pr - c * n_in;
+      const int xmin = bh_s[2 * xx] - a.x_lo, n = bh_s[2 * xx + 1];
+      const int32_t* k = kh_s + xx * a.taps_h;
+      const unsigned char* row = src_s + ((size_t)c * rows_cap + yy) * x_w + xmin;
+      int acc = 1 << (kPrecisionBits - 1);
+      for (int t = 0; t < n; ++t) acc += (int)row[t] * k[t];
+      hrow_s[((size_t)c * rows_cap + yy) * out_w + xx] = (unsigned char)clip8(acc);
+    }
   }
   __syncthreads();
   // ---- vertical pass + rescale / normalise table + channels-first store
@@ -143,11 +166,17 @@ __global__ void __launch_bounds__(kPreThreads) clip_preprocess_kernel(const PreK
     const int pr = i / out_w, xx = i - pr * out_w;
     const int c = pr / n_rows, rr = pr - c * n_rows;
     const long long j = a.crop_top + r0 + rr;
-    const int ymin = a.bounds_v[2 * j], n = a.bounds_v[2 * j + 1];
+    const int ymin = a.bounds_v[2 * j];
+    [[maybe_unused]] const int n = a.bounds_v[2 * j + 1];
     const int32_t* k = a.coeffs_v + j * a.taps_v;
     const unsigned char* col = hrow_s + ((size_t)c * rows_cap + (ymin - y_first)) * out_w + xx;
     int acc = 1 << (kPrecisionBits - 1);
-    for (int t = 0; t < n; ++t) acc += (int)col[(size_t)t * out_w] * __ldg(k + t);
+    if constexpr (kTV > 0) {
+#pragma unroll
+      for (int t = 0; t < kTV; ++t) acc += (int)col[(size_t)t * out_w] * __ldg(k + t);  // k is warp-uniform: one broadcast load
+    } else {
+      for (int t = 0; t < n; ++t) acc += (int)col[(size_t)t * out_w] * __ldg(k + t);
+    }
     out[((long long)c * a.out_h + (r0 + rr)) * a.out_w + xx] = cvt_px<TD>(table[c * 256 + clip8(acc)]);
   }
 }
@@ -244,7 +273,7 @@ extern "C" int psob200_clip_preprocess(const psob200_clip_preprocess_args* args,
   h_bound(p.crop_left, xa, na);
   h_bound(p.crop_left + p.out_w - 1, xb, nb);
   const int x_lo = xa & ~7;  // 8-sample vectors stay 16-byte aligned for 16-bit sources whose rows are
-  const int x_w = ((xb + nb - x_lo) + 7) & ~7;
+  const int x_w = ((xb + nb - x_lo) + p.taps_h + 7) & ~7;  // + one tap row of slack: the unrolled loops read all taps (zero weights)
   // rows per CTA: as many as keep both shared-memory planes within 96 KB (two CTAs per SM), else within 200 KB
   const double vscale = (double)p.in_h / (double)p.rs_h;
   const size_t coef_bytes = (size_t)p.out_w * (p.taps_h + 2) * 4 + 16;
@@ -269,12 +298,13 @@ extern "C" int psob200_clip_preprocess(const psob200_clip_preprocess_args* args,
   a.x_lo = x_lo; a.x_w = x_w;
   const dim3 grid((unsigned)((p.out_h + rows - 1) / rows), (unsigned)p.B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static PerDevice<int> configured[12];
+  static PerDevice<int> configured[24];
   cudaError_t e = cudaSuccess;
+  const bool taps11 = p.taps_h == 11 && p.taps_v == 11;  // 512 -> 224 (turbo :626-640); other sizes: run-time tap loops
 #define PSOB200_PRE_LAUNCH(TS, TD, slot)                                                                              \
   do {                                                                                                                \
-    auto kern = clip_preprocess_kernel<TS, TD>;                                                                       \
-    std::atomic<int>& conf = configured[slot].here();                                                                 \
+    auto kern = taps11 ? clip_preprocess_kernel<TS, TD, 11, 11> : clip_preprocess_kernel<TS, TD, 0, 0>;               \
+    std::atomic<int>& conf = configured[(slot) + (taps11 ? 12 : 0)].here();                                           \
     if (smem > 48 * 1024 && !conf.load(std::memory_order_acquire)) {                                                  \
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);                        \
       if (e != cudaSuccess) return consume_launch_error("configure clip_preprocess_kernel", e);                       \

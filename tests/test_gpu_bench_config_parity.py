@@ -173,7 +173,8 @@ def test_full_sdxl_fixture_graph_replayed_batched_step_vs_eager_separate_forward
     loss_b2 = micro_step.product_micro_step_batched(pso, lora, unet, d, sched, **kw)
     torch.cuda.synchronize()
     flat_b2 = opt.bucket.flat.double().cpu().clone()
-    assert float(loss_b2.item()) == loss_b
+    loss_b2 = float(loss_b2.item())  # (rebinding drops the autograd graph: a live graph from another stream breaks the capture below)
+    assert loss_b2 == loss_b
     floor_cos = (torch.dot(flat_b, flat_b2) / (flat_b.norm() * flat_b2.norm())).item()
     floor_worst = ((flat_b - flat_b2).abs().max() / flat_b.abs().max()).item()
     # arm 2b: what bench.py times -- the SAME kernels on the SAME shapes, now with the reference forward on a second stream,
