@@ -219,6 +219,11 @@ PSOB200_API int psob200_dreambooth_pso_loss_grad(const psob200_dreambooth_args* 
  * prev_out [B,N] `out_dtype` (model_output dtype for turbo TS:116, sample dtype for DMD
  * DS:137).  scaled_next_out (may be NULL) = prev_out_fp32 / sqrt(sigma_next^2+1), the
  * next UNet input of the turbo sampler (TP:120-121), `out_dtype`.
+ * Throughput mode (prev_sample == NULL, noise == NULL, use_philox != 0): the N(0,1) draws come from a counter-based
+ * generator inside the kernel (Philox4x32-10 + Box-Muller; four draws per counter (q, philox_offset), q = index of the
+ * 4-element group inside the [noise_rows, N] noise tensor, key = philox_seed; values rounded through `out_dtype` as
+ * randn(dtype=...) would), so no noise tensor is written or read.  torch's own generator stream is not reproduced: pass
+ * `noise` when the draws must be the caller's.  Advance philox_offset by 1 per call.
  */
 typedef struct psob200_step_args {
   const void* model_output; /* [B,N] pred_dtype   */
@@ -244,7 +249,9 @@ typedef struct psob200_step_args {
   int32_t out_dtype;
   int32_t tune_threads;
   int32_t tune_cluster;
-  int32_t reserved;
+  int32_t use_philox;
+  uint64_t philox_seed;
+  uint64_t philox_offset;
 } psob200_step_args;
 
 PSOB200_API int psob200_step_logprob(const psob200_schedule* sched, const psob200_step_args* args, void* stream);

@@ -58,7 +58,7 @@ class StepArgs(C.Structure):
                 ("ts_rows", C.c_int64), ("stride_model_output", C.c_int64), ("stride_sample", C.c_int64),
                 ("stride_prev_sample", C.c_int64), ("pred_dtype", C.c_int32), ("latent_dtype", C.c_int32),
                 ("out_dtype", C.c_int32), ("tune_threads", C.c_int32), ("tune_cluster", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("use_philox", C.c_int32), ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64)]
 
 
 class StepBwdArgs(C.Structure):

@@ -37,7 +37,45 @@ struct StepKernelArgs {
   long long B, N, noise_rows, ts_rows;
   long long stride_eps, stride_x, stride_xn;
   int chunks_per_cta;
+  int use_philox;  // sampling mode without a noise tensor: N(0,1) draws from the counter-based generator below
+  unsigned long long philox_seed, philox_offset;
 };
+
+// ---- Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11) + Box-Muller: the throughput mode of
+// the sampler (hard part 8).  Four N(0,1) draws per counter; counter = (q, offset) with q = index of the
+// 4-element group inside the noise tensor (per sample, or shared by the batch: DS:123-124), key = seed: the stream does not
+// depend on the launch geometry.  oracle/philox.py restates it; torch's own generator stream is NOT reproduced (parity mode
+// takes the noise as an input instead).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ void philox_normal4(unsigned long long q, unsigned long long seed, unsigned long long offset, float (&n)[4]) {
+  uint32_t x[4];
+  philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)offset, (uint32_t)(offset >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), x);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = ((float)(x[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-8f;      // (0, 1): 24 bits
+    const float u2 = ((float)(x[2 * h + 1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    n[2 * h] = rad * cs;
+    n[2 * h + 1] = rad * sn;
+  }
+}
+template <typename T>
+__device__ __forceinline__ float round_through(float v) {  // the reference draws the noise IN the tensor's dtype (TS:97)
+  if constexpr (sizeof(T) == 4) return v;
+  else return static_cast<float>(static_cast<T>(v));
+}
 
 template <typename TP, typename TL, int MODE, int W>
 __global__ void __launch_bounds__(kStepMaxThreads) step_logprob_kernel(const StepKernelArgs a) {
@@ -85,7 +123,7 @@ __global__ void __launch_bounds__(kStepMaxThreads) step_logprob_kernel(const Ste
         if (c < cend) {
           re[u] = Vec8<TP>::load_raw(eps + c * 8);
           rx[u] = Vec8<TL>::load_raw(x + c * 8);
-          rn[u] = Vec8<TN>::load_raw(third + c * 8);
+          if (MODE == kScore || !a.use_philox) rn[u] = Vec8<TN>::load_raw(third + c * 8);
         }
       }
 #pragma unroll
@@ -95,7 +133,16 @@ __global__ void __launch_bounds__(kStepMaxThreads) step_logprob_kernel(const Ste
           float ve[8], vx[8], vn[8], o[8], o2[8];
           Vec8<TP>::decode(re[u], ve);
           Vec8<TL>::decode(rx[u], vx);
-          Vec8<TN>::decode(rn[u], vn);
+          if (MODE != kScore && a.use_philox) {
+            const unsigned long long q = (unsigned long long)((a.noise_rows == 1 ? 0 : base) / 4 + 2 * c);  // N % 8 == 0 here
+            float lo[4], hi[4];
+            philox_normal4(q, a.philox_seed, a.philox_offset, lo);
+            philox_normal4(q + 1, a.philox_seed, a.philox_offset, hi);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { vn[i] = round_through<TO>(lo[i]); vn[4 + i] = round_through<TO>(hi[i]); }
+          } else {
+            Vec8<TN>::decode(rn[u], vn);
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float mu = fmaf(ca, ve[i], kx * vx[i]);
@@ -124,7 +171,16 @@ __global__ void __launch_bounds__(kStepMaxThreads) step_logprob_kernel(const Ste
       if constexpr (MODE == kScore) {
         r = Vec8<TL>::load1(xn + c) - mu;
       } else {
-        const float nx = fmaf(Vec8<TO>::load1(noise + c), sd, mu);
+        float nz;
+        if (a.use_philox) {
+          const unsigned long long e = (unsigned long long)((a.noise_rows == 1 ? 0 : base) + c);
+          float n4[4];
+          philox_normal4(e / 4, a.philox_seed, a.philox_offset, n4);
+          nz = round_through<TO>(n4[e & 3]);
+        } else {
+          nz = Vec8<TO>::load1(noise + c);
+        }
+        const float nx = fmaf(nz, sd, mu);
         r = nx - mu;
         Vec8<TO>::store1(prev_out + c, nx);
         if (scaled_out != nullptr) Vec8<TO>::store1(scaled_out + c, nx * nscale);
@@ -341,7 +397,9 @@ extern "C" int psob200_step_logprob(const psob200_schedule* sched, const psob200
   if (p.ts_rows != 1 && p.ts_rows != p.B) return PSOB200_ERR_INVALID_ARG;
   if (!valid_dtype(p.pred_dtype) || !valid_dtype(p.latent_dtype)) return PSOB200_ERR_DTYPE;
   const bool scoring = p.prev_sample != nullptr;
-  if (scoring == (p.noise != nullptr)) return PSOB200_ERR_INVALID_ARG;  // exactly one of the two (DS:115-119)
+  const bool philox = p.use_philox != 0;
+  if (scoring && (p.noise != nullptr || philox)) return PSOB200_ERR_INVALID_ARG;  // exactly one of the two (DS:115-119)
+  if (!scoring && ((p.noise != nullptr) == philox)) return PSOB200_ERR_INVALID_ARG;
   int mode = kScore;
   bool vec_ok = (p.N % 8) == 0 && aligned16(p.model_output) && aligned16(p.sample);
   if (scoring) {
@@ -352,7 +410,8 @@ extern "C" int psob200_step_logprob(const psob200_schedule* sched, const psob200
     if (p.out_dtype == p.pred_dtype) mode = kSampleOutPred;
     else if (p.out_dtype == p.latent_dtype) mode = kSampleOutLatent;
     else return PSOB200_ERR_DTYPE;
-    vec_ok = vec_ok && aligned16(p.noise) && aligned16(p.prev_out) && (!p.scaled_next_out || aligned16(p.scaled_next_out));
+    if (philox && p.noise_rows == p.B && (p.N % 4) != 0) return PSOB200_ERR_SHAPE;  // a 4-draw group never straddles two samples
+    vec_ok = vec_ok && (philox || aligned16(p.noise)) && aligned16(p.prev_out) && (!p.scaled_next_out || aligned16(p.scaled_next_out));
   }
   if (p.stride_model_output < 0 || p.stride_sample < 0 || p.stride_prev_sample < 0) return PSOB200_ERR_INVALID_ARG;
   const long long st_e = p.stride_model_output ? p.stride_model_output : p.N;
@@ -379,6 +438,7 @@ extern "C" int psob200_step_logprob(const psob200_schedule* sched, const psob200
   ka.B = p.B; ka.N = p.N; ka.noise_rows = p.noise_rows; ka.ts_rows = p.ts_rows;
   ka.stride_eps = st_e; ka.stride_x = st_x; ka.stride_xn = st_n;
   ka.chunks_per_cta = (int)((nchunk + cluster - 1) / cluster);
+  ka.use_philox = philox ? 1 : 0; ka.philox_seed = p.philox_seed; ka.philox_offset = p.philox_offset;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return dispatch2(p.pred_dtype, p.latent_dtype, [&](auto tp, auto tl) -> int {
     using TP = decltype(tp);

@@ -46,6 +46,10 @@ def distilled_step_with_logprob(self, model_output, timestep, prev_timestep, sam
     ts_prev = runtime.timesteps_on(prev_timestep, dev).to(ts.dtype)
     sched = runtime.dmd_schedule(self, dev, _lib.ts_dtype_code(ts))
     if prev_sample is None:
+        if runtime.sampler_noise_in_kernel(generator):  # one in-kernel draw shared by the batch (:123-124)
+            log_prob, prev_out, _ = step_ops.step_forward(sched, model_output.detach(), sample, ts, ts_prev,
+                                                          philox=step_ops.next_philox(), noise_rows=1, out_dtype=sample.dtype)
+            return prev_out, log_prob
         noise = torch.randn((1,) + tuple(model_output.shape[1:]), generator=generator, device=dev,
                             dtype=sample.dtype)  # :123-124
         log_prob, prev_out, _ = step_ops.step_forward(sched, model_output.detach(), sample, ts, ts_prev, noise=noise)

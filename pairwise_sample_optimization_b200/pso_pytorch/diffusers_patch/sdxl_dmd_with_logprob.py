@@ -78,9 +78,13 @@ def sdxl_dmd_pipeline_with_logprob(
             if i != n_steps - 1:                                                                               # :124
                 ts_prev = runtime.timesteps_on(timesteps[i + 1], dev).to(ts.dtype)
                 sched = runtime.dmd_schedule(noise_scheduler, dev, _lib.ts_dtype_code(ts))
-                noise = torch.randn((1,) + tuple(noise_pred.shape[1:]), generator=generator, device=dev,
-                                    dtype=latents.dtype)                                                       # DS:123-124
-                log_prob, latents, _ = step_ops.step_forward(sched, noise_pred, latents, ts, ts_prev, noise=noise)
+                if runtime.sampler_noise_in_kernel(generator):                                             # DS:123-124
+                    log_prob, latents, _ = step_ops.step_forward(sched, noise_pred, latents, ts, ts_prev, noise_rows=1,
+                                                                 philox=step_ops.next_philox(), out_dtype=latents.dtype)
+                else:
+                    noise = torch.randn((1,) + tuple(noise_pred.shape[1:]), generator=generator, device=dev,
+                                        dtype=latents.dtype)
+                    log_prob, latents, _ = step_ops.step_forward(sched, noise_pred, latents, ts, ts_prev, noise=noise)
                 all_latents.append(latents)
                 all_log_probs.append(log_prob)
             else:                                                                                              # :154-162

@@ -64,7 +64,11 @@ def sdxl_turbo_pipeline_with_logprob(
         num_channels_latents = accelerator.unwrap_model(unet).config.in_channels
         latents = prepare_latents(batch_size * num_images_per_prompt, num_channels_latents, height, width,
                                   prompt_embeds.dtype, dev, generator, latents)
-        latents = step_ops.scale(latents, float(noise_scheduler.init_noise_sigma))          # :99
+        init_sigma = noise_scheduler.init_noise_sigma                                        # :99
+        if torch.is_tensor(init_sigma) and init_sigma.is_cuda:  # a device scalar: scale without reading it back
+            latents = step_ops.scale_by_device_scalar(latents, init_sigma)
+        else:
+            latents = step_ops.scale(latents, float(init_sigma))
         noise_scheduler.set_timesteps(num_inference_steps, device=dev)                       # :102
         timesteps = noise_scheduler.timesteps
         sigmas = noise_scheduler.sigmas
@@ -73,8 +77,9 @@ def sdxl_turbo_pipeline_with_logprob(
         all_latents = [latents]
         all_model_input_latents = []
         all_log_probs = []
-        sigma0 = float(sigmas[0])
-        latent_model_input = step_ops.scale(latents, 1.0 / (sigma0 ** 2 + 1) ** 0.5)        # :120-121 (i = 0)
+        # :120-121 (i = 0): latents / sqrt(sigma_0^2 + 1) with sigma_0 read on the device (the reference's `sigmas[i]` indexing
+        # inside scale_model_input costs a host sync per step; here no step of the loop reads anything back)
+        latent_model_input = step_ops.scale_by_device_scalar(latents, torch.rsqrt(sigmas[0].to(dev, torch.float32) ** 2 + 1))
         for i, t in enumerate(timesteps):
             noise_scheduler.is_scale_input_called = True
             noise_pred = unet(
@@ -86,10 +91,15 @@ def sdxl_turbo_pipeline_with_logprob(
             )[0]
             ts = runtime.timesteps_on(t, dev)
             sched = runtime.turbo_schedule(noise_scheduler, dev, _lib.ts_dtype_code(ts))
-            noise = torch.randn(noise_pred.shape, dtype=noise_pred.dtype, device=dev, generator=generator)
             # fused: x_next = mu + sigma_up*noise, log_prob, and the NEXT step's scaled input     :136-142, :121
-            log_prob, latents_next, scaled_next = step_ops.step_forward(
-                sched, noise_pred, latents, ts, noise=noise, want_scaled_next=True)
+            if runtime.sampler_noise_in_kernel(generator):
+                log_prob, latents_next, scaled_next = step_ops.step_forward(
+                    sched, noise_pred, latents, ts, philox=step_ops.next_philox(), out_dtype=noise_pred.dtype,
+                    want_scaled_next=True)
+            else:
+                noise = torch.randn(noise_pred.shape, dtype=noise_pred.dtype, device=dev, generator=generator)
+                log_prob, latents_next, scaled_next = step_ops.step_forward(
+                    sched, noise_pred, latents, ts, noise=noise, want_scaled_next=True)
             if i != num_inference_steps - 1:                                                   # :146-149
                 all_model_input_latents.append(latent_model_input)
                 all_latents.append(latents_next)

@@ -34,6 +34,10 @@ def turbo_step_with_logprob(self, model_output, timestep, sample, generator=None
     ts = runtime.timesteps_on(timestep, dev)
     sched = runtime.turbo_schedule(self, dev, _lib.ts_dtype_code(ts))
     if prev_sample is None:
+        if runtime.sampler_noise_in_kernel(generator):  # no generator given: the draw of :97 happens inside the kernel
+            log_prob, prev_out, _ = step_ops.step_forward(sched, model_output.detach(), sample, ts, philox=step_ops.next_philox(),
+                                                          out_dtype=model_output.dtype)
+            return prev_out, log_prob
         noise = torch.randn(model_output.shape, dtype=model_output.dtype, device=dev, generator=generator)  # :97
         log_prob, prev_out, _ = step_ops.step_forward(sched, model_output.detach(), sample, ts, noise=noise)
         return prev_out, log_prob

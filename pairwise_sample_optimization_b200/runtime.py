@@ -15,6 +15,21 @@ import torch
 from . import _lib
 
 _tables: dict = {}
+_SAMPLER_NOISE = {"mode": "philox"}
+
+
+def set_sampler_noise(mode: str) -> None:
+    """Where the sampler's N(0,1) draws come from when the caller passes NO generator: "philox" (default) = generated inside the
+    step kernel (no noise tensor, no extra launch; keyed by torch's seed and a call counter), "torch" = ``torch.randn`` from the
+    global generator, as the reference does.  With an explicit ``generator`` the draw is always ``torch.randn(generator=...)``."""
+    if mode not in ("philox", "torch"):
+        raise ValueError(mode)
+    _SAMPLER_NOISE["mode"] = mode
+
+
+def sampler_noise_in_kernel(generator) -> bool:
+    return generator is None and _SAMPLER_NOISE["mode"] == "philox"
+
 _workspaces: dict = {}
 _status: dict = {}
 

@@ -33,10 +33,22 @@ def _fill_common(args, model_output, sample, ts, ts_prev, coef, n):
     return mo, sa
 
 
+_PHILOX = {"offset": 0}
+
+
+def next_philox(seed=None):
+    """(seed, offset) for one in-kernel draw: torch's global seed (or ``seed``) and a process-wide call counter -- no device
+    work, no sync.  Re-seeding torch (``torch.manual_seed``) re-keys the stream."""
+    _PHILOX["offset"] += 1
+    return (int(torch.initial_seed()) if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF, _PHILOX["offset"]
+
+
 def step_forward(sched: runtime.ScheduleDesc, model_output, sample, ts, ts_prev=None, coef=None, prev_sample=None,
-                 noise=None, want_scaled_next=False, tune=(0, 0)):
-    """One launch of psob200_step_logprob.  Scoring mode if ``prev_sample`` is given, else sampling
-    mode with explicit ``noise``.  Returns (log_prob[B] fp32, prev_out | None, scaled_next | None)."""
+                 noise=None, want_scaled_next=False, tune=(0, 0), philox=None, noise_rows=None, out_dtype=None):
+    """One launch of psob200_step_logprob.  Scoring mode if ``prev_sample`` is given, else sampling mode with explicit
+    ``noise``, or -- ``philox=(seed, offset)`` -- with N(0,1) draws generated inside the kernel (``noise_rows`` = B or 1 for the
+    batch-shared DMD2 draw, ``out_dtype`` = the dtype the noise would have had).  Returns (log_prob[B] fp32, prev_out | None,
+    scaled_next | None)."""
     dev = _lib.require_cuda(model_output, sample, prev_sample, noise)
     B, n = model_output.shape[0], _sample_numel(model_output)
     if sample.shape[0] != B or _sample_numel(sample) != n:
@@ -57,13 +69,21 @@ def step_forward(sched: runtime.ScheduleDesc, model_output, sample, ts, ts_prev=
         args.stride_prev_sample = st_ps
         keep += (ps,)
     else:
-        noise = noise.contiguous()
-        if noise.dtype not in (model_output.dtype, sample.dtype):
+        if philox is not None:
+            if noise is not None:
+                raise _lib.Psob200Error("pass either a noise tensor or philox=(seed, offset)")
+            ndt = out_dtype or model_output.dtype
+            args.use_philox, args.philox_seed, args.philox_offset = 1, int(philox[0]), int(philox[1])
+            args.noise_rows = B if noise_rows is None else int(noise_rows)
+        else:
+            noise = noise.contiguous()
+            ndt = noise.dtype
+            args.noise = noise.data_ptr()
+            args.noise_rows = noise.shape[0]
+        if ndt not in (model_output.dtype, sample.dtype):
             raise _lib.Psob200Error("noise dtype must be the model_output dtype (turbo) or the sample dtype (DMD)")
-        args.noise = noise.data_ptr()
-        args.noise_rows = noise.shape[0]
-        args.out_dtype = _lib.dtype_code(noise)
-        prev_out = torch.empty(model_output.shape, dtype=noise.dtype, device=dev)
+        args.out_dtype = _lib._DTYPES[ndt]
+        prev_out = torch.empty(model_output.shape, dtype=ndt, device=dev)
         args.prev_out = prev_out.data_ptr()
         if want_scaled_next:
             scaled = torch.empty_like(prev_out)
@@ -127,6 +147,17 @@ def x0_from_noise(alphas_cumprod_dev, model_output, sample, ts, out_dtype=None, 
         _lib.ts_dtype_code(ts), 1 if ts.numel() == 1 and mo.shape[0] > 1 else mo.shape[0], out.data_ptr(),
         mo.shape[0], n, _lib.dtype_code(mo), _lib.dtype_code(sa), _lib.dtype_code(out),
         runtime.status_word(dev).data_ptr(), _lib.current_stream(dev))
+    return out
+
+
+def scale_by_device_scalar(t: torch.Tensor, factor: torch.Tensor) -> torch.Tensor:
+    """``t * factor`` with ``factor`` a one-element tensor ON THE DEVICE: no read-back
+    (psob200_scale_inplace_by_device_scalar on a copy)."""
+    dev = _lib.require_cuda(t, factor)
+    out = t.contiguous().clone()
+    f32 = factor.detach().reshape(1).to(torch.float32)
+    _lib.launch(dev, "psob200_scale_inplace_by_device_scalar", out.data_ptr(), out.numel(), _lib.dtype_code(out),
+                f32.data_ptr(), _lib.current_stream(dev))
     return out
 
 

@@ -222,3 +222,73 @@ def test_broadcast_timestep_and_last_turbo_step(pso):
     want0 = x.cpu() + e.cpu() * (0.0 - sched.sigmas[3])  # sigma_down = sigma_to = 0: x0 prediction
     np.testing.assert_allclose(prev.cpu().numpy(), want0.numpy(), rtol=2e-6, atol=2e-6)
     pso.check_status()
+
+
+@pytest.mark.parametrize("kind,B,shape,dtype", [("turbo", 3, (4, 64, 64), torch.float32), ("turbo", 2, (4, 64, 64), torch.bfloat16),
+                                                ("dmd", 3, (4, 32, 32), torch.float32), ("turbo", 2, (3, 5, 7), torch.float32)])
+def test_in_kernel_philox_noise_matches_the_oracle_stream(pso, kind, B, shape, dtype):
+    """Throughput mode of the sampler (no generator): the N(0,1) draws are produced inside the step kernel.  With
+    model_output = sample = 0 the update is x' = s * noise, so the draws can be read back and compared with oracle/philox.py
+    (Philox4x32-10 + Box-Muller, pinned to the published known-answer vectors); the log-prob is that of the drawn sample."""
+    from oracle import philox
+    from pairwise_sample_optimization_b200 import _lib, runtime, step_ops
+    n = int(np.prod(shape))
+    z = torch.zeros((B,) + shape, device="cuda", dtype=dtype)
+    seed, offset = 0x1234567887654321, 5
+    if kind == "turbo":
+        sched = schedules.turbo_scheduler(4)
+        ts = torch.tensor([999, 749, 499][:B] + [999] * max(0, B - 3), device="cuda")
+        sd = runtime.turbo_schedule(sched, z.device, _lib.ts_dtype_code(ts))
+        lp, prev, scaled = step_ops.step_forward(sd, z, z, ts, philox=(seed, offset), out_dtype=dtype, want_scaled_next=True)
+        idx = torch.tensor(osteps.turbo_step_indices(sched, ts.cpu()))
+        _, _, s = schedules.turbo_coefficients(sched.sigmas, idx)
+        rows = B
+    else:
+        sched = schedules.dmd_scheduler()
+        ts = torch.full((B,), 749, device="cuda")
+        sd = runtime.dmd_schedule(sched, z.device, _lib.ts_dtype_code(ts))
+        lp, prev, _ = step_ops.step_forward(sd, z, z, ts, ts - 250, philox=(seed, offset), noise_rows=1, out_dtype=dtype)
+        _, _, s = schedules.dmd_coefficients(sched.alphas_cumprod, ts.cpu(), ts.cpu() - 250)
+        rows = 1
+    pso.check_status()
+    want = torch.from_numpy(philox.normal(rows * n, seed, offset)).reshape((rows,) + shape)
+    if dtype != torch.float32:
+        want = want.to(dtype).double()  # the reference draws randn(dtype=...): values representable in the tensor's type
+    got = prev.double().cpu() / s.double().reshape(-1, 1, 1, 1)
+    tol = 3e-6 if dtype == torch.float32 else 2.0 ** -8
+    assert (got - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+    if kind == "dmd":  # ONE draw shared by the whole batch (DS:123-124)
+        assert torch.equal(prev[0], prev[1]) and torch.equal(prev[1], prev[2])
+    # the log-prob is the log-prob of the sample it returned (scoring mode on the stored fp32 / rounded sample)
+    lp_want = -(want ** 2).reshape(rows, -1).mean(1) / 2 - torch.log(s.double()) - 0.5 * np.log(2 * np.pi)
+    assert (lp.double().cpu() - lp_want).abs().max().item() <= 2e-5 * lp_want.abs().max().item()
+    # another offset -> another stream; same (seed, offset) -> the same draws, whatever the launch geometry
+    _, prev2, _ = (step_ops.step_forward(sd, z, z, ts, philox=(seed, offset + 1), out_dtype=dtype) if kind == "turbo" else
+                   step_ops.step_forward(sd, z, z, ts, ts - 250, philox=(seed, offset + 1), noise_rows=1, out_dtype=dtype))
+    assert not torch.equal(prev2, prev)
+    if kind == "turbo" and n % 8 == 0:
+        _, prev3, _ = step_ops.step_forward(sd, z, z, ts, philox=(seed, offset), out_dtype=dtype, tune=(128, 2))
+        assert torch.equal(prev3, prev)
+
+
+def test_pipelines_draw_in_kernel_without_a_generator(pso):
+    """generator=None: the sampler loop draws inside the step kernel (runtime.set_sampler_noise("philox"), the default)."""
+    from pairwise_sample_optimization_b200 import runtime
+    B = 2
+    unet = _ToyUNet().cuda()
+    sched = schedules.turbo_scheduler(4)
+    emb = torch.randn(B, 77, 8, device="cuda")
+    torch.manual_seed(11)
+    out1 = pso.sdxl_turbo_pipeline_with_logprob(_Acc, None, unet, sched, 512, 512, num_inference_steps=4, prompt_embeds=emb,
+                                                pooled_prompt_embeds=emb[:, 0], add_time_ids=emb[:, 0, :6], output_type="latent")
+    assert len(out1[1]) == 4 and all(torch.isfinite(t).all() for t in out1[1]) and all(torch.isfinite(t).all() for t in out1[2])
+    lat = out1[1][1].float()
+    assert 0.5 < (lat.std() / sched.sigmas[1].item()).item() < 2.0  # noise of the right scale was injected
+    runtime.set_sampler_noise("torch")
+    try:
+        out2 = pso.sdxl_turbo_pipeline_with_logprob(_Acc, None, unet, sched, 512, 512, num_inference_steps=4, prompt_embeds=emb,
+                                                    pooled_prompt_embeds=emb[:, 0], add_time_ids=emb[:, 0, :6], output_type="latent")
+    finally:
+        runtime.set_sampler_noise("philox")
+    assert not torch.equal(out2[1][1], out1[1][1])
+    pso.check_status()
