@@ -12,11 +12,10 @@
 //
 // HBM traffic is the algorithmic 8N reads + 2N writes per pair.
 //
-// Three kernels share that structure (profiles/r01_pair_loss.md):
+// Two kernels share that structure (profiles/r01_pair_loss.md; a third design -- a TMA ring with the
+// residuals in registers, 44-57 % of HBM -- was measured in round 1 and is kept out of the product under tools/experiments/):
 //   pair_loss_grad_tmem_kernel  (fast path, pair_loss_tmem.cuh) residuals parked in TENSOR MEMORY (tcgen05.st / ld),
 //           1024 threads per SM, a per-thread cp.async ring of 192 KB, cluster of 1 (64^2 latents) or 2 (128^2);
-//   pair_loss_grad_tma_kernel   (second design, pair_loss_tma.cuh, kept for A/B timing: tune_threads = 1) 1-D TMA ring,
-//           residuals in registers, st.async partial-sum exchange;
 //   pair_loss_grad_kernel       (general path, this file) vectorised or scalar LDG, residuals in shared memory;
 //           any N, any alignment, up to 25600 elements per branch per CTA, one cluster per pair.
 //
@@ -217,7 +216,6 @@ __device__ __forceinline__ void residual8(const float (&vx)[8], const float (&vn
 
 }  // namespace psob200
 
-#include "pair_loss_tma.cuh"   // second design: persistent clusters + TMA ring, residuals in registers
 #include "pair_loss_tmem.cuh"  // fast path: residuals in tensor memory, per-thread cp.async ring
 
 namespace psob200 {
@@ -376,22 +374,6 @@ static int max_active_clusters(K kern, int threads, size_t smem, int cluster, in
 }
 
 template <typename TP, typename TL, bool HAS_REF>
-static int launch_pair_tma_inst(const PairKernelArgs& ka, int cluster, int sm_count, cudaStream_t stream) {
-  auto kern = pair_loss_grad_tma_kernel<TP, TL, HAS_REF>;
-  using Cfg = TmaCfg<TP, TL, HAS_REF>;
-  constexpr size_t smem = Cfg::kSmemBytes;
-  static PerDevice<size_t> configured;
-  static PerDevice<int> active[4];
-  const int rc = ensure_dynamic_smem(kern, smem, configured, "configure pair_loss_grad_tma_kernel");
-  if (rc != PSOB200_OK) return rc;
-  long long clusters = max_active_clusters(kern, kTmaThreads, smem, cluster, sm_count, 1, active);
-  if (clusters > ka.B) clusters = ka.B;  // persistent: every cluster loops over pairs cluster_id, +clusters, ...
-  const cudaError_t e = launch_cluster(kern, dim3((unsigned)(clusters * cluster)), dim3(kTmaThreads), smem, stream,
-                                       (unsigned)cluster, ka);
-  return consume_launch_error("launch pair_loss_grad_tma_kernel", e);
-}
-
-template <typename TP, typename TL, bool HAS_REF>
 static int launch_pair_tmem_inst(const PairKernelArgs& ka, int cluster, int sm_count, cudaStream_t stream) {
   auto kern = pair_loss_grad_tmem_kernel<TP, TL, HAS_REF>;
   using Cfg = V3Cfg<TP, TL, HAS_REF>;
@@ -421,13 +403,13 @@ static int tmem_cluster_for(long long nchunk, long long B, int sm_count, int tun
   return c;
 }
 
-// tune_threads: 0 = heuristics (the tensor-memory kernel); 1 = the TMA-ring kernel (second design, kept for A/B
-//               measurements); >= 32 = the general (LDG) kernel with that many threads.  tune_cluster: 0 = heuristics.
+// tune_threads: 0 = heuristics (the tensor-memory kernel); >= 32 = the general (LDG) kernel with that many threads.
+// tune_cluster: 0 = heuristics.
 static int launch_pair(PairKernelArgs ka, bool has_ref, int32_t pred_dtype, int32_t latent_dtype, bool vec_ok,
                        int tune_threads, int tune_cluster, int sm_count, cudaStream_t stream) {
   if (tune_cluster != 0 && tune_cluster != 1 && tune_cluster != 2 && tune_cluster != 4 && tune_cluster != 8)
     return PSOB200_ERR_INVALID_ARG;
-  if (tune_threads < 0) return PSOB200_ERR_INVALID_ARG;
+  if (tune_threads < 0 || (tune_threads > 0 && tune_threads < 32)) return PSOB200_ERR_INVALID_ARG;
   // ---- fast path: residuals in tensor memory
   if (vec_ok && tune_threads == 0) {
     const long long nchunk = ka.N / 8;
@@ -443,28 +425,6 @@ static int launch_pair(PairKernelArgs ka, bool has_ref, int32_t pred_dtype, int3
                      : launch_pair_tmem_inst<TP, TL, false>(k2, cluster, sm_count, stream);
     });
     if (rc != 1) return rc;
-    if (tune_cluster != 0) return PSOB200_ERR_SHAPE;
-  }
-  // ---- second design: persistent TMA ring, <= 2 * kTmaThreads chunks per branch per CTA
-  if (vec_ok && tune_threads == 1) {
-    const long long nchunk = ka.N / 8;
-    int cluster = tune_cluster;
-    if (cluster == 0) {
-      cluster = 1;
-      while (cluster < kMaxCluster && (nchunk + cluster - 1) / cluster > 2 * kTmaThreads) cluster <<= 1;
-      // small batches: spread a pair over more SMs as long as every CTA keeps >= 256 chunks
-      while (cluster < kMaxCluster && ka.B * cluster < sm_count && nchunk / (cluster * 2) >= 256) cluster <<= 1;
-    }
-    const long long cpc = (nchunk + cluster - 1) / cluster;
-    if (cpc <= 2 * kTmaThreads) {
-      ka.chunks_per_cta = (int)cpc;
-      return dispatch2(pred_dtype, latent_dtype, [&](auto tp, auto tl) -> int {
-        using TP = decltype(tp);
-        using TL = decltype(tl);
-        return has_ref ? launch_pair_tma_inst<TP, TL, true>(ka, cluster, sm_count, stream)
-                       : launch_pair_tma_inst<TP, TL, false>(ka, cluster, sm_count, stream);
-      });
-    }
     if (tune_cluster != 0) return PSOB200_ERR_SHAPE;
   }
   // ---- general path

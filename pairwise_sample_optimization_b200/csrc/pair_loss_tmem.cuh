@@ -16,10 +16,79 @@
 // function on one thread, pass 2 (TMEM -> g*r -> global).  The ring runs ahead across pairs, so HBM stays busy while a
 // pair is being finished.  Deterministic: fixed summation order, no atomics on the data path.
 //
-// Included by pair_loss.cu (needs PairKernelArgs, PairEntry, pair_scalar_function_fast and the shared helpers).
+// Included by pair_loss.cu (needs PairKernelArgs and the shared helpers).
 #pragma once
 
 namespace psob200 {
+
+constexpr int kTabPairs = 64;  // per-pair coefficients (fp64, dependent schedule-table loads) are resolved for 64 pairs at a time
+
+struct PairEntry {
+  StepCoef c[2];
+  float h[2];
+};
+
+// fp32 evaluation of the pair's scalar function from values in registers / shared memory only.  Every lane of
+// every warp of every CTA of the cluster runs it on identical inputs, so they all obtain the same multipliers.
+// S = {S_pol0, S_ref0, D0, S_pol1, S_ref1, D1}.  Returns the per-pair loss term; stats (8 floats) when asked.
+__device__ __forceinline__ float pair_scalar_function_fast(const PairKernelArgs& a, const float (&S)[6],
+                                                           const PairEntry& e, float& g0, float& g1, float (&st)[8]) {
+  const StepCoef c0 = e.c[0], c1 = e.c[1];
+  const float i0 = c0.inv_2s2n, i1 = c1.inv_2s2n;
+  const float invB = 1.0f / (float)a.B;
+  float per;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st[i] = 0.f;
+  if (a.mode == kModeOnline) {
+    const float kHalfLog2Pi = 0.918938533204672742f;
+    const float d0 = S[2] * i0, d1 = S[5] * i1;  // delta_k = logp_pol,k - logp_ref,k
+    const float lo = (float)a.log_lo, hi = (float)a.log_hi;
+    const bool open0 = (d0 >= lo) && (d0 <= hi), open1 = (d1 >= lo) && (d1 <= hi);
+    const float lr0 = open0 ? d0 : (d0 < lo ? lo : (d0 > hi ? hi : d0));  // log clamp(exp d, 1-eps, 1+eps); NaN propagates
+    const float lr1 = open1 ? d1 : (d1 < lo ? lo : (d1 > hi ? hi : d1));
+    const float z = a.beta * (e.h[0] * lr0 + e.h[1] * lr1);  // T:847-850
+    const float ez = expf(-fabsf(z));
+    per = log1pf(ez) + fmaxf(-z, 0.f);                           // softplus(-z) = -log sigmoid(z)
+    const float sig_neg = (z >= 0.f ? ez : 1.0f) / (1.0f + ez);  // sigmoid(-z), overflow-free
+    const float common = -sig_neg * invB * a.beta * a.loss_scale;
+    g0 = open0 ? common * e.h[0] * c0.a_over_s2n : 0.f;  // torch.clamp passes grad on the closed interval
+    g1 = open1 ? common * e.h[1] * c1.a_over_s2n : 0.f;
+    if (z != z) per = z;
+    st[0] = -S[0] * i0 - c0.log_s - kHalfLog2Pi;  // TS:108-114 / DS:129-135
+    st[1] = -S[1] * i0 - c0.log_s - kHalfLog2Pi;
+    st[2] = -S[3] * i1 - c1.log_s - kHalfLog2Pi;
+    st[3] = -S[4] * i1 - c1.log_s - kHalfLog2Pi;
+    st[4] = d0; st[5] = d1; st[6] = z; st[7] = per;
+  } else {
+    const float nu = a.nu, beta = a.beta;
+    const float lam = a.lam > 0.f ? a.lam : 0.f;              // P:1932
+    const float Lw = 2.0f * S[0] * i0, Ll = 2.0f * S[3] * i1;  // P:1885-1891
+    float logits, dl;
+    if (a.mode == kModeDbPso) {
+      logits = 2.0f * S[2] * i0 - nu * (2.0f * S[5] * i1);  // (Lref_w-L_w) - nu (Lref_l-L_l)   P:1919
+      const float z = beta * logits;
+      const float ez = expf(-fabsf(z));
+      per = log1pf(ez) + fmaxf(-z, 0.f);  // P:1925
+      const float sig_neg = (z >= 0.f ? ez : 1.0f) / (1.0f + ez);
+      dl = -beta * sig_neg * invB;
+      if (z != z) per = z;
+      st[2] = 2.0f * S[1] * i0;
+      st[3] = 2.0f * S[4] * i1;
+    } else {
+      logits = -(Lw - nu * Ll);  // P:1922
+      const float m = 1.0f - beta * logits;
+      per = m > 0.f ? m : (m == m ? 0.f : m);  // relu, NaN propagates   P:1927
+      dl = m > 0.f ? -beta * invB : 0.f;
+    }
+    per += lam * Ll;  // P:1932-1935
+    const float Gw = -dl, Gl = nu * dl + lam * invB;
+    g0 = a.loss_scale * Gw * (-2.0f * c0.a_over_s2n);
+    g1 = a.loss_scale * Gl * (-2.0f * c1.a_over_s2n);
+    st[0] = Lw; st[1] = Ll; st[4] = logits; st[5] = per;
+  }
+  return per;
+}
+
 
 constexpr int kV3SmemRing = 192 * 1024;
 constexpr int kV3TmemCols = 512;

@@ -43,6 +43,11 @@ def next_philox(seed=None):
     return (int(torch.initial_seed()) if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF, _PHILOX["offset"]
 
 
+def reset_philox(offset: int = 0) -> None:
+    """Restart the call counter of the in-kernel noise stream (reproducible runs: seed torch, then reset)."""
+    _PHILOX["offset"] = int(offset)
+
+
 def step_forward(sched: runtime.ScheduleDesc, model_output, sample, ts, ts_prev=None, coef=None, prev_sample=None,
                  noise=None, want_scaled_next=False, tune=(0, 0), philox=None, noise_rows=None, out_dtype=None):
     """One launch of psob200_step_logprob.  Scoring mode if ``prev_sample`` is given, else sampling mode with explicit

@@ -225,7 +225,7 @@ def test_broadcast_timestep_and_last_turbo_step(pso):
 
 
 @pytest.mark.parametrize("kind,B,shape,dtype", [("turbo", 3, (4, 64, 64), torch.float32), ("turbo", 2, (4, 64, 64), torch.bfloat16),
-                                                ("dmd", 3, (4, 32, 32), torch.float32), ("turbo", 2, (3, 5, 7), torch.float32)])
+                                                ("dmd", 3, (4, 32, 32), torch.float32), ("turbo", 2, (3, 5, 12), torch.float32)])
 def test_in_kernel_philox_noise_matches_the_oracle_stream(pso, kind, B, shape, dtype):
     """Throughput mode of the sampler (no generator): the N(0,1) draws are produced inside the step kernel.  With
     model_output = sample = 0 the update is x' = s * noise, so the draws can be read back and compared with oracle/philox.py
@@ -269,25 +269,31 @@ def test_in_kernel_philox_noise_matches_the_oracle_stream(pso, kind, B, shape, d
     if kind == "turbo" and n % 8 == 0:
         _, prev3, _ = step_ops.step_forward(sd, z, z, ts, philox=(seed, offset), out_dtype=dtype, tune=(128, 2))
         assert torch.equal(prev3, prev)
+    if kind == "turbo":  # a 4-draw group must not straddle two samples: per-sample noise needs N % 4 == 0
+        z7 = torch.zeros(B, 3, 5, 7, device="cuda", dtype=dtype)
+        with pytest.raises(Exception, match="shape"):
+            step_ops.step_forward(sd, z7, z7, ts, philox=(seed, offset), out_dtype=dtype)
 
 
 def test_pipelines_draw_in_kernel_without_a_generator(pso):
     """generator=None: the sampler loop draws inside the step kernel (runtime.set_sampler_noise("philox"), the default)."""
-    from pairwise_sample_optimization_b200 import runtime
+    from pairwise_sample_optimization_b200 import runtime, step_ops
     B = 2
     unet = _ToyUNet().cuda()
     sched = schedules.turbo_scheduler(4)
     emb = torch.randn(B, 77, 8, device="cuda")
-    torch.manual_seed(11)
-    out1 = pso.sdxl_turbo_pipeline_with_logprob(_Acc, None, unet, sched, 512, 512, num_inference_steps=4, prompt_embeds=emb,
-                                                pooled_prompt_embeds=emb[:, 0], add_time_ids=emb[:, 0, :6], output_type="latent")
+    def run():
+        torch.manual_seed(11)      # keys the in-kernel stream (and draws the initial latents)
+        step_ops.reset_philox()    # ... together with the process-wide call counter
+        return pso.sdxl_turbo_pipeline_with_logprob(_Acc, None, unet, sched, 512, 512, num_inference_steps=4, prompt_embeds=emb,
+                                                    pooled_prompt_embeds=emb[:, 0], add_time_ids=emb[:, 0, :6], output_type="latent")
+    out1, out1b = run(), run()
     assert len(out1[1]) == 4 and all(torch.isfinite(t).all() for t in out1[1]) and all(torch.isfinite(t).all() for t in out1[2])
-    lat = out1[1][1].float()
-    assert 0.5 < (lat.std() / sched.sigmas[1].item()).item() < 2.0  # noise of the right scale was injected
+    assert all(torch.equal(a, b) for a, b in zip(out1[1], out1b[1]))  # same seed, same call sequence: the same trajectory
+    assert not torch.equal(out1[1][1], out1[1][2])
     runtime.set_sampler_noise("torch")
     try:
-        out2 = pso.sdxl_turbo_pipeline_with_logprob(_Acc, None, unet, sched, 512, 512, num_inference_steps=4, prompt_embeds=emb,
-                                                    pooled_prompt_embeds=emb[:, 0], add_time_ids=emb[:, 0, :6], output_type="latent")
+        out2 = run()
     finally:
         runtime.set_sampler_noise("philox")
     assert not torch.equal(out2[1][1], out1[1][1])
