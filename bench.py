@@ -425,7 +425,12 @@ class B200Arm:
             ev0.record()
             marks[0].record()
             for i in range(K):
+                if self.args.profiler_range and i == K - 1:  # ncu --profile-from-start off: exactly the last timed step
+                    torch.cuda.profiler.start()
                 loss = self.step(i)
+                if self.args.profiler_range and i == K - 1:
+                    torch.cuda.synchronize()
+                    torch.cuda.profiler.stop()
                 marks[i + 1].record()
             ev1.record()
             self.barrier()
@@ -976,6 +981,9 @@ def main():
                     help="one launch sequence per projection instead of stacked q / k / v (k / v) groups")
     ap.add_argument("--no-inlaunch-deps", action="store_true",
                     help="A/B: t / u as launches of their own (PDL overlap) instead of tiles of the main launch")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the last timed step (for `ncu --profile-from-start off` launch lists; "
+                         "the printed numbers of such a run are not bench values)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager-on-this-GPU baseline")
     ap.add_argument("--no-turbo64", action="store_true", help="skip the short configs[1] block after the main timing")
     args = ap.parse_args()
