@@ -522,24 +522,28 @@ class B200Arm:
                  **({"tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1)} if is_main(k[0]) else
                     {"gbs": round(v[3] / (v[0] * 1e-3) / 1e9, 1)})}
                 for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])]
-        traffic, traffic_src = ncu_traffic("lora_gemm2_kernel@M8192_K1280+64_N1280_bf16") if self.name == "dmd128" else (None, None)
+        # per launch of the stacked q / k / v forward (the widest launch of the step); other launches: see profiles/r02_kernels.md
+        traffic, traffic_src = (ncu_traffic("lora_gemm2_kernel@stacked_qkv_fwd_M8192_K1280_N3840_r64_bf16")
+                                if self.name == "dmd128" and self.args.fuse_projections else (None, None))
         roofline = {"kernel": "lora_gemm2_kernel / lora_gemm_kernel main passes: y = x W^T + b + t B^T, dx = dy W + u A (tcgen05, "
-                              "frozen weight + adapter in one pass) over the 560 LoRA-wrapped projections",
+                              "frozen weight + adapter in one pass; t / u as tiles of the same launch; q / k / v stacked) over the "
+                              "560 LoRA-wrapped projections",
                     "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                     "frac": round(ach / peaks["tf_sustained"], 4), "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                     "launches_per_step": m_n, "avg_launch_us": round(m_ms * 1e3 / max(m_n, 1), 2),
                     "share_of_step": round(m_ms / ms_per_step, 4), "flops_per_step": m_fl,
-                    "algorithmic_flops": "2 M N (K + r) per launch (r = 0 for the frozen-reference pass)",
+                    "algorithmic_flops": "2 M N (K + r) per launch (r = 0 for the frozen-reference pass) + 2 M r K (2 M r N) for the "
+                                         "in-launch t (u) tiles",
                     "by_launch": [r_ for r_ in rows if is_main(r_["launch"])],
-                    "how": "one CUDA-event pair around EVERY launch (psob200 forward_phases / backward_phases issue the launches of "
-                           "a projection one at a time; event records captured as graph nodes) in one extra replayed step on ONE "
+                    "how": "one CUDA-event pair around EVERY launch (event records captured as graph nodes) in one extra replayed step on ONE "
                            "stream (in the timed step the frozen-reference forward shares the SMs from a second stream, which would "
-                           "charge its CTAs' residency to these intervals); includes the graph-node gaps around each launch and "
-                           "lacks the programmatic-dependent-launch overlap, so slightly pessimistic"}
+                           "charge its CTAs' residency to these intervals); includes the graph-node gaps around each launch, so "
+                           "slightly pessimistic"}
         s_ach = s_by / (s_ms * 1e-3) / 1e9 if s_ms > 0 else 0.0
-        skinny = {"kernel": "lora_gemm_kernel skinny passes: t = s x A^T, u = s dy B, dA += u^T x, dB += dy^T t (rank-r side of "
-                            "every projection; arithmetic intensity <= 84 flop/B, SURVEY.md section 8d)",
+        skinny = {"kernel": "lora_gemm_kernel rank-r side launches: dA += u^T x and dB += dy^T t of a projection (a stacked group) in "
+                            "ONE split-K launch, u = s dy B alone where no dx is needed (cross-attention k / v); arithmetic "
+                            "intensity <= 84 flop/B, SURVEY.md section 8d",
                   "bound": "hbm", "achieved": round(s_ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
                   "frac": round(s_ach / peaks["hbm"], 4), "launches_per_step": s_n,
                   "avg_launch_us": round(s_ms * 1e3 / max(s_n, 1), 2), "share_of_step": round(s_ms / ms_per_step, 4),
