@@ -436,6 +436,9 @@ PSOB200_API int psob200_lora_linear_backward(const psob200_lora_linear_args* arg
  *   backward (2 launches with `flags`)         u_g = scaling * dy_g B_g  (+ ut);   dx = sum_g dy_g W_g + u lora_a
  *                                              dA += u^T x  [G r, K];   dB_g += dy_g^T t_g  [N, r]   (fp32, accumulated)
  *
+ * With `flags` the tiles of the main problem SPIN until the tiles of t (u) of the same launch have published their rows: every
+ * CTA of the launch must be able to become resident, so keep at most one such launch in flight per device (issue the
+ * LoRA-enabled passes of a device from ONE stream; launches without adapters, and the weight-gradient launch, never wait).
  * dy[g] are G separate [M, N] gradients (their own row pitches lddy[g]); dx may be NULL (cross-attention k / v: the prompt
  * embeddings need no gradient).  G > 1 needs r % 8 == 0.  bias only for G = 1.  Phases and scratch as psob200_lora_linear_args.
  */

@@ -75,7 +75,9 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem + kStages2 * kStageABytes;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle is PROVABLY warp-uniform: ptxas then keeps the role loops (barrier phases, stage counters,
+  // UMMA / TMA descriptors) on the uniform datapath instead of moving ~20 per-thread registers to uniform ones (R2UR) per k-block
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
   const int stage_b_bytes = L.stage_b_bytes;  // half of the widest problem's B tile
