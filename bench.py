@@ -352,6 +352,7 @@ class B200Arm:
         self.ref_stream = torch.cuda.Stream() if (args.overlap_reference and not args.separate_forwards) else None
         self.graph = self.static_loss = self.side = None
         self.launches_per_micro = 0
+        self.one_step = None
 
     # ---- one micro-step (turbo trainer :771-861 / dmd2 trainer :773-864)
     def micro(self, batch, overlap=True, **extra):
@@ -471,12 +472,14 @@ class B200Arm:
 
     def gate(self):
         """One eager micro-step (untimed) with the loss kernel's per-pair statistics: how many clamp gates were open."""
-        if self.kind == "dreambooth" or self.args.separate_forwards:
+        if self.args.separate_forwards:
             return None
         self.bucket.zero_()
-        _, stats = self.micro(self.d, return_stats=True)
+        loss1, stats = self.micro(self.d, return_stats=True)
+        torch.cuda.synchronize()
+        self.one_step = {"loss": float(loss1.item()) * self.accum, "grad": self.bucket.flat.clone()}  # for the eager-arm parity check
         self.bucket.zero_()
-        if stats is None:
+        if self.kind == "dreambooth" or stats is None:
             return None
         delta = stats[:, 4:6].double()  # log pi_theta - log pi_ref per branch
         h = self.d["human_prefer"].double()
@@ -599,6 +602,17 @@ class B200Arm:
         torch.cuda.empty_cache()
 
 
+def lora_layers_in_module_order(unet):
+    from pairwise_sample_optimization_b200 import lora
+    return lora.lora_layers(unet)
+
+
+def flat_order(arm):
+    """For every LoRA layer in module order: (offset of A, offset of B) inside the arm's flat gradient buffer."""
+    off = {id(p): o for p, o in zip(arm.bucket.params, arm.bucket.offsets)}
+    return [(off[id(m.lora_A["default"].weight)], off[id(m.lora_B["default"].weight)]) for m in lora_layers_in_module_order(arm.unet)]
+
+
 def sampler_kernel_roofline(dev, peaks):
     """step_logprob_kernel in sampling mode (x' = mu + s noise, log-prob, next scaled UNet input) alone: 256 samples of
     4x128x128 bf16, Euler-ancestral schedule.  Algorithmic bytes per sample = 3 N read (prediction, latent, noise) + 2 N written
@@ -650,7 +664,7 @@ def lora_projection_vs_cublas(dev, shapes, r):
     return rows
 
 
-def gpu_eager_baseline(args, name, dev, host, reps=4):
+def gpu_eager_baseline(args, name, dev, host, reps=4, same_weights=None):
     """The reference's micro-step on THIS GPU with stock torch kernels: same architecture, same base weights (seed), same batch;
     stock nn.Linear + the peft-style LoRA module (oracle/lora.py: 3 cuBLAS GEMMs + scale + add), 4 separate forwards, the four
     step-with-logprob calls + inline loss restated in oracle/, autograd backward.  oracle/ is checker code: it is executed here
@@ -669,6 +683,11 @@ def gpu_eager_baseline(args, name, dev, host, reps=4):
     for m in wrapped:
         torch.nn.init.normal_(m.lora_B["default"].weight, std=0.01)
         m.lora_A.to(torch.bfloat16); m.lora_B.to(torch.bfloat16)
+    if same_weights is not None:  # the b200 arm's adapters (fp32 masters -> the bf16 values its kernels read)
+        for m, (A, Bm) in zip(wrapped, same_weights["adapters"]):
+            with torch.no_grad():
+                m.lora_A["default"].weight.copy_(A.to(torch.bfloat16))
+                m.lora_B["default"].weight.copy_(Bm.to(torch.bfloat16))
     unet.train()
     sched = make_scheduler(kind, dev) if kind != "dreambooth" else None
     d = {k: v.to(dev) for k, v in host.items()}
@@ -720,6 +739,25 @@ def gpu_eager_baseline(args, name, dev, host, reps=4):
             out["graph_replayed"] = {"unavailable": "the Euler-ancestral step of the reference syncs with the host once per sample "
                                                     "(turbo_inference_with_logprob.py:63): not capturable"}
     torch.cuda.synchronize()
+    if same_weights is not None:
+        # same weights, same batch, one micro-step: the reference's flow on stock kernels vs this repo's kernels
+        with torch.cuda.stream(side):
+            loss_e = float(one().item()) * accum
+        torch.cuda.synchronize()
+        g_ours = same_weights["grad"].double()
+        g_eager = torch.zeros_like(g_ours)
+        for m, (oa, ob) in zip(wrapped, same_weights["order"]):
+            ga, gb = m.lora_A["default"].weight.grad, m.lora_B["default"].weight.grad
+            g_eager[oa:oa + ga.numel()] = ga.double().flatten()
+            g_eager[ob:ob + gb.numel()] = gb.double().flatten()
+        cos = float((torch.dot(g_ours, g_eager) / (g_ours.norm() * g_eager.norm())).item())
+        out["same_weights_parity"] = {
+            "what": "one micro-step of both arms on the SAME base weights, adapters and batch (bf16 both; the eager arm also keeps "
+                    "its adapter gradients in bf16): the reference's flow on stock torch kernels vs this repo's kernels",
+            "loss_ours": round(same_weights["loss"], 6), "loss_eager": round(loss_e, 6),
+            "loss_rel_diff": round(abs(same_weights["loss"] - loss_e) / abs(loss_e), 6),
+            "grad_cosine": round(cos, 6), "grad_norm_ratio": round(float((g_ours.norm() / g_eager.norm()).item()), 5)}
+        del g_ours, g_eager
     del unet, wrapped
     import gc
     gc.collect()
@@ -771,6 +809,13 @@ def run_b200(args):
                    "timing": ("eager launches" if args.no_graph else "micro-step replayed from one CUDA graph; optimizer "
                               "boundary eager") + ", CUDA events around K steps, max over ranks"}
     host_batch = {k: v.clone() for k, v in arm.host.items()}
+    # the adapters and one micro-step's loss / flat gradient of this arm: the eager baseline re-runs the reference's flow on the
+    # SAME weights and batch and reports how far the two arms are apart (end-to-end parity at the full SDXL-architecture size)
+    same_weights = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline and arm.one_step is not None:
+        same_weights = {"adapters": [(m.lora_A["default"].weight.detach().clone(), m.lora_B["default"].weight.detach().clone())
+                                     for m in lora_layers_in_module_order(arm.unet)],
+                        "loss": arm.one_step["loss"], "grad": arm.one_step["grad"], "order": flat_order(arm)}
     arm.close()
     del arm
 
@@ -810,7 +855,7 @@ def run_b200(args):
         guarded("turbo64", turbo64_block)
     if rank == 0 and world == 1 and not args.no_eager_baseline:
         def eager_block():
-            eager = gpu_eager_baseline(args, args.config, dev, host_batch)
+            eager = gpu_eager_baseline(args, args.config, dev, host_batch, same_weights=same_weights)
             eager["ratio_ours_over_eager"] = round(t["value"] / eager["value"], 3)
             if "value" in eager.get("graph_replayed", {}):
                 eager["ratio_ours_over_graph_replayed"] = round(t["value"] / eager["graph_replayed"]["value"], 3)
