@@ -52,7 +52,11 @@ def _rel(got, want64):
 @pytest.mark.parametrize("G,M_shape,K,N,r,need_dx", [(3, (2, 300), 640, 640, 8, True), (3, (4, 256), 1280, 1280, 64, True),
                                                      (2, (4, 77), 2048, 640, 16, False), (2, (3, 77), 2048, 1280, 64, True),
                                                      (3, (1, 130), 320, 320, 128, True), (3, (8, 1024), 1280, 1280, 64, True),
-                                                     (3, (2, 1024), 640, 640, 8, True)])
+                                                     (3, (2, 1024), 640, 640, 8, True),
+                                                     # ragged everything: M, K and N off the tile / k-block / box sizes, tiles that
+                                                     # would straddle two stacked projections, reduction tails inside the stacked weight
+                                                     (2, (3, 77), 72, 200, 8, True), (3, (1, 300), 136, 264, 16, True),
+                                                     (3, (1, 5), 64, 48, 8, True)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_stacked_group_forward_backward_vs_oracle(L, G, M_shape, K, N, r, need_dx, dtype):
     layers = _layers(L, G, K, N, r, dtype, 3)
