@@ -313,6 +313,7 @@ class B200Arm:
             feed_forward.install_fused_geglu(unet)
         lora.set_wgrad_stream(args.wgrad_stream)
         lora.set_in_launch_dependencies(not args.no_inlaunch_deps)
+        lora.set_programmatic_launch(args.programmatic_launch)
         unet.train()
         if args.grad_checkpointing:
             unet.enable_gradient_checkpointing()  # turbo trainer :358
@@ -1028,6 +1029,9 @@ def main():
     ap.add_argument("--tiny", action="store_true", help="debug: the 32/64-channel fixture instead of the SDXL architecture")
     ap.add_argument("--no-fuse-projections", dest="fuse_projections", action="store_false", default=True,
                     help="one launch sequence per projection instead of stacked q / k / v (k / v) groups")
+    ap.add_argument("--programmatic-launch", action="store_true",
+                    help="A/B: projection kernels launched with programmatic stream serialization (prologue overlaps the "
+                         "preceding kernel's tail)")
     ap.add_argument("--no-inlaunch-deps", action="store_true",
                     help="A/B: t / u as launches of their own (PDL overlap) instead of tiles of the main launch")
     ap.add_argument("--profiler-range", action="store_true",

@@ -469,6 +469,11 @@ typedef struct psob200_lora_group_args {
   int32_t adapters_enabled;
   int32_t forward_phases;
   int32_t backward_phases;
+  /* bit 0: launch every kernel of the call with programmatic stream serialization; its TMA producer then executes
+   * griddepcontrol.wait before its first load, so that the launch latency and the prologue (barriers, tensor-memory
+   * allocation, tensor-map fetch) overlap the tail of WHATEVER kernel precedes it on the stream.  Safe for any predecessor:
+   * nothing is read or written before the wait has returned. */
+  int32_t launch_flags;
 } psob200_lora_group_args;
 
 PSOB200_API int psob200_lora_group_forward(const psob200_lora_group_args* args, void* stream);

@@ -932,18 +932,20 @@ extern "C" int psob200_lora_group_forward(const psob200_lora_group_args* args, v
     H.prob[0] = down; H.prob[0].signal = 1;
     H.prob[1] = main; H.prob[1].wait_seg = 1;
     H.flags = a.flags; H.flags_len = a.flags_len;
+    if (a.launch_flags & 1) H.pdl = 2 | 4;
     return launch_problems(H, st);
   }
   if (lora && (fph & PSOB200_FWD_DOWN)) {
     HostLaunch H = launch_defaults(a.dtype);
     H.n_prob = 1; H.prob[0] = down;
     H.pdl = (fph & PSOB200_FWD_MAIN) ? 1 : 0;  // the main pass reads t only in its last k-blocks: let it start early
+    if (a.launch_flags & 1) H.pdl |= 2 | 4;
     if ((rc = launch_problems(H, st)) != PSOB200_OK) return rc;
   }
   if (fph & PSOB200_FWD_MAIN) {
     HostLaunch H = launch_defaults(a.dtype);
     H.n_prob = 1; H.prob[0] = main;
-    H.pdl = (lora && (fph & PSOB200_FWD_DOWN)) ? 2 : 0;
+    H.pdl = (lora && (fph & PSOB200_FWD_DOWN)) ? 2 : ((a.launch_flags & 1) ? (2 | 4) : 0);
     return launch_problems(H, st);
   }
   return PSOB200_OK;
@@ -992,19 +994,20 @@ extern "C" int psob200_lora_group_backward(const psob200_lora_group_args* args, 
     for (int g = 0; g < G; ++g) { H.prob[g] = up[g]; H.prob[g].signal = 1; }
     H.prob[G] = dxp; H.prob[G].wait_seg = G;
     H.flags = a.flags; H.flags_len = a.flags_len;
+    if (a.launch_flags & 1) H.pdl = 2 | 4;
     if ((rc = launch_problems(H, st)) != PSOB200_OK) return rc;
   } else {
     if (need_u) {
       HostLaunch H = launch_defaults(a.dtype);
       H.b_mn = 1; H.n_prob = G;
       for (int g = 0; g < G; ++g) H.prob[g] = up[g];
-      H.pdl = need_dx ? 1 : 0;
+      H.pdl = (need_dx ? 1 : 0) | ((a.launch_flags & 1) ? (2 | 4) : 0);
       if ((rc = launch_problems(H, st)) != PSOB200_OK) return rc;
     }
     if (need_dx) {
       HostLaunch H = launch_defaults(a.dtype);
       H.b_mn = 1; H.n_prob = 1; H.prob[0] = dxp;
-      H.pdl = (lora && need_u) ? 2 : 0;
+      H.pdl = (lora && need_u) ? 2 : ((a.launch_flags & 1) ? (2 | 4) : 0);
       if ((rc = launch_problems(H, st)) != PSOB200_OK) return rc;
     }
   }
@@ -1039,6 +1042,7 @@ extern "C" int psob200_lora_group_backward(const psob200_lora_group_args* args, 
     }
   }
   H.n_prob = n;
+  if ((a.launch_flags & 1) && H.pdl == 0) H.pdl = 2 | 4;
   return launch_problems(H, st);
 }
 

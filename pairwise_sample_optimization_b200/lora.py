@@ -191,6 +191,13 @@ class LoRALinear(nn.Module):
 
 _FLAGS: dict = {}
 _IN_LAUNCH_DEPS = {"enabled": True}
+_LAUNCH_FLAGS = {"value": 1 if __import__("os").environ.get("PSOB200_PROGRAMMATIC_LAUNCH", "0") == "1" else 0}
+
+
+def set_programmatic_launch(enabled: bool) -> None:
+    """A/B switch (psob200_lora_group_args.launch_flags bit 0): launch the projection kernels with programmatic stream
+    serialization, so that their launch latency and prologue overlap the tail of the preceding kernel on the stream."""
+    _LAUNCH_FLAGS["value"] = 1 if enabled else 0
 
 
 def set_in_launch_dependencies(enabled: bool) -> None:
@@ -363,6 +370,7 @@ class _LoraGroupFn(torch.autograd.Function):
         a.M, a.K, a.N, a.r, a.G = M, K, N, r, G
         a.dtype = _lib.dtype_code(x2)
         a.adapters_enabled = int(enabled)
+        a.launch_flags = _LAUNCH_FLAGS["value"]
         want_wgrad = enabled and grad_mode and params[0].requires_grad  # False under no_grad (the frozen-reference pass)
         t = tt = None
         fl_t = by_t = 0.0
@@ -420,6 +428,7 @@ class _LoraGroupFn(torch.autograd.Function):
         a.M, a.K, a.N, a.r, a.G = M, K, N, r, G
         a.dtype = _lib.dtype_code(dy2[0])
         a.adapters_enabled = int(ctx.enabled)
+        a.launch_flags = _LAUNCH_FLAGS["value"]
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, dtype=dtype, device=dev)
