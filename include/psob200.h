@@ -472,7 +472,10 @@ typedef struct psob200_lora_group_args {
   /* bit 0: launch every kernel of the call with programmatic stream serialization; its TMA producer then executes
    * griddepcontrol.wait before its first load, so that the launch latency and the prologue (barriers, tensor-memory
    * allocation, tensor-map fetch) overlap the tail of WHATEVER kernel precedes it on the stream.  Safe for any predecessor:
-   * nothing is read or written before the wait has returned. */
+   * nothing is read or written before the wait has returned.
+   * bit 1: DETERMINISTIC weight gradients: the dA / dB reductions are not split over CTAs, so every element of the fp32
+   * gradient receives exactly one accumulation per launch (launches on a stream are ordered): bit-reproducible adapter
+   * gradients at the price of a less parallel launch (10-40 tiles instead of one wave of split tiles). */
   int32_t launch_flags;
 } psob200_lora_group_args;
 

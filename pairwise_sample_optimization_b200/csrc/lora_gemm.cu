@@ -1028,6 +1028,7 @@ extern "C" int psob200_lora_group_backward(const psob200_lora_group_args* args, 
     if (n + G > kMaxProb) {  // dA on its own launch, then the G dB problems
       H.n_prob = n;
       H.pdl = 1;
+      if (a.launch_flags & 2) H.split_k = 1;
       if ((rc = launch_problems(H, st)) != PSOB200_OK) return rc;
       H = launch_defaults(a.dtype);
       H.a_mn = 1; H.accumulate = 1; H.d_dtype = PSOB200_F32; H.pdl = 8;
@@ -1043,6 +1044,7 @@ extern "C" int psob200_lora_group_backward(const psob200_lora_group_args* args, 
   }
   H.n_prob = n;
   if ((a.launch_flags & 1) && H.pdl == 0) H.pdl = 2 | 4;
+  if (a.launch_flags & 2) H.split_k = 1;  // one accumulation per gradient element and launch: bit-reproducible
   return launch_problems(H, st);
 }
 

@@ -194,10 +194,17 @@ _IN_LAUNCH_DEPS = {"enabled": True}
 _LAUNCH_FLAGS = {"value": 1 if __import__("os").environ.get("PSOB200_PROGRAMMATIC_LAUNCH", "0") == "1" else 0}
 
 
+def set_deterministic_wgrad(enabled: bool) -> None:
+    """Bit-reproducible adapter gradients (psob200_lora_group_args.launch_flags bit 1): the dA / dB reductions are not split
+    over CTAs, so the fp32 atomic accumulation has exactly one contribution per element and launch.  Slower weight-gradient
+    launches (they are off the critical path with ``set_wgrad_stream(True)``)."""
+    _LAUNCH_FLAGS["value"] = (_LAUNCH_FLAGS["value"] & ~2) | (2 if enabled else 0)
+
+
 def set_programmatic_launch(enabled: bool) -> None:
     """A/B switch (psob200_lora_group_args.launch_flags bit 0): launch the projection kernels with programmatic stream
     serialization, so that their launch latency and prologue overlap the tail of the preceding kernel on the stream."""
-    _LAUNCH_FLAGS["value"] = 1 if enabled else 0
+    _LAUNCH_FLAGS["value"] = (_LAUNCH_FLAGS["value"] & ~1) | (1 if enabled else 0)
 
 
 def set_in_launch_dependencies(enabled: bool) -> None:

@@ -157,3 +157,28 @@ def test_processor_with_fused_projections_matches_the_per_projection_path(L):
         assert set(g_a) == set(g_b)
         for n in g_a:
             assert (g_a[n] - g_b[n]).abs().max().item() <= 2e-2 * g_a[n].abs().max().item() + 1e-6, n
+
+
+def test_deterministic_weight_gradients_are_bit_reproducible(L):
+    """set_deterministic_wgrad(True): no split-K, one accumulation per gradient element and launch -> identical bits run to run
+    (the default split reductions agree only to fp32 round-off), and the same values up to that round-off."""
+    dtype = torch.bfloat16
+    runs = []
+    for det in (True, True, False):
+        torch.manual_seed(21)
+        layers = _layers(L, 3, 640, 640, 16, dtype, 11)
+        group = L.LoRAProjectionGroup(layers)
+        x = _mk((4, 1000, 640), 5, 1.0, dtype).cuda().requires_grad_(True)
+        dys = [_mk((4, 1000, 640), 7 + g, 1.0, dtype).cuda() for g in range(3)]
+        L.set_deterministic_wgrad(det)
+        try:
+            for _ in range(2):  # two accumulating passes (gradient accumulation)
+                torch.autograd.backward(list(group(x)), dys)
+        finally:
+            L.set_deterministic_wgrad(False)
+        torch.cuda.synchronize()
+        runs.append([l.lora_A["default"].weight.grad.clone() for l in layers] + [l.lora_B["default"].weight.grad.clone() for l in layers])
+    for a, b in zip(runs[0], runs[1]):
+        assert torch.equal(a, b)
+    for a, c in zip(runs[0], runs[2]):
+        assert (a - c).abs().max().item() <= 1e-4 * c.abs().max().item()
