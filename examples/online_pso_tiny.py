@@ -82,7 +82,8 @@ def sample_epoch(unet, sched, cfg, n_prompts: int, steps: int = 4):
         lat = torch.stack(all_latents, dim=1)                                      # [B, steps, 4, 64, 64]  (T:587-612)
         out[f"latents_{k}"] = lat[:, :-1]                                          # T:617: the last step is not trained
         out[f"next_latents_{k}"] = lat[:, 1:]
-        out[f"input_latents_{k}"] = torch.stack(all_inputs, dim=1)
+        # the sampler runs under autocast like the reference's (TP:77): cast what the UNet will be fed again to its dtype
+        out[f"input_latents_{k}"] = torch.stack([t.to(torch.bfloat16) for t in all_inputs], dim=1)
         out[f"final_{k}"] = image
     unet.train()
     out["timesteps"] = sched.timesteps[:steps - 1].long()
