@@ -28,3 +28,19 @@ def test_b200_arm_json_line_on_the_tiny_fixture(built_lib):
         assert r["bound"] in ("tensor", "hbm") and r["achieved"] > 0 and r["peak"] > 0
         assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3 and r["launches_per_step"] > 0
     assert "workload" in line["config"] and line["clocks"]["sm_max_mhz"]
+    # round 2: the backward of the timed step is not vacuous, and the reference's flow on the same GPU is reported next to it
+    assert line["grad_norm"] > 0 and 0 < line["gate"]["open_fraction"] <= 1
+    eager = line["gpu_eager_baseline"]
+    assert eager["value"] > 0 and eager["ratio_ours_over_eager"] > 0
+    par = eager["same_weights_parity"]  # both arms on the same adapters and batch (tiny fixture: bf16 noise of ~40 layers)
+    assert par["loss_rel_diff"] <= 5e-2 and par["grad_cosine"] >= 0.9, par
+
+
+def test_b200_arm_dreambooth_config_on_the_tiny_fixture(built_lib):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--tiny", "--config", "dreambooth64", "--steps", "4", "--warmup", "3",
+                          "--no-cpu-baseline", "--no-kernel-figures"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["config"]["name"] == "dreambooth64" and line["config"]["loss_type"] == "pso" and line["value"] > 0
+    assert line["grad_norm"] > 0 and line["gpu_launches"] > 0 and line["gpu_eager_baseline"]["value"] > 0
+    assert line["gpu_eager_baseline"]["same_weights_parity"]["grad_cosine"] >= 0.9
