@@ -440,7 +440,7 @@ PSOB200_API int psob200_lora_linear_backward(const psob200_lora_linear_args* arg
  * CTA of the launch must be able to become resident, so keep at most one such launch in flight per device (issue the
  * LoRA-enabled passes of a device from ONE stream; launches without adapters, and the weight-gradient launch, never wait).
  * dy[g] are G separate [M, N] gradients (their own row pitches lddy[g]); dx may be NULL (cross-attention k / v: the prompt
- * embeddings need no gradient).  G > 1 needs r % 8 == 0.  bias only for G = 1.  Phases and scratch as psob200_lora_linear_args.
+ * embeddings need no gradient).  G > 1 needs r_stride % 8 == 0 (see r_stride).  bias only for G = 1.  Phases and scratch as psob200_lora_linear_args.
  */
 #define PSOB200_MAX_GROUP 3
 typedef struct psob200_lora_group_args {
@@ -477,6 +477,11 @@ typedef struct psob200_lora_group_args {
    * gradient receives exactly one accumulation per launch (launches on a stream are ordered): bit-reproducible adapter
    * gradients at the price of a less parallel launch (10-40 tiles instead of one wave of split tiles). */
   int32_t launch_flags;
+  /* Stride of the G column groups inside the stacked t / u (and of the row groups inside lora_a, tt, ut); 0 = r.  A rank that is
+   * not a multiple of 8 is stacked with r_stride = r rounded up to 8: lora_a is then [G r_stride, K] with ZERO rows behind each
+   * projection's r rows, t / u / tt / ut are G r_stride wide / tall; lora_b stays [G N, r] and the gradients d_lora_a
+   * [G r, K] / d_lora_b [G N, r] stay packed. */
+  int64_t r_stride;
 } psob200_lora_group_args;
 
 PSOB200_API int psob200_lora_group_forward(const psob200_lora_group_args* args, void* stream);

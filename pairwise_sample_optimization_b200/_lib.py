@@ -98,7 +98,8 @@ class LoraGroupArgs(C.Structure):
                 ("ldu", C.c_int64), ("ldut", C.c_int64), ("ld_da", C.c_int64), ("ld_db", C.c_int64), ("M", C.c_int64),
                 ("K", C.c_int64), ("N", C.c_int64), ("r", C.c_int64), ("G", C.c_int32), ("scaling", C.c_float),
                 ("dtype", C.c_int32), ("bias_dtype", C.c_int32), ("adapters_enabled", C.c_int32),
-                ("forward_phases", C.c_int32), ("backward_phases", C.c_int32), ("launch_flags", C.c_int32)]
+                ("forward_phases", C.c_int32), ("backward_phases", C.c_int32), ("launch_flags", C.c_int32),
+                ("r_stride", C.c_int64)]
 
 
 class FlatAdamwArgs(C.Structure):

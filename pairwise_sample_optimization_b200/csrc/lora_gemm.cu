@@ -879,7 +879,10 @@ static int group_check(const psob200_lora_group_args& a, bool backward) {
   if (a.G < 1 || a.G > PSOB200_MAX_GROUP || a.M <= 0 || a.K <= 0 || a.N <= 0 || !a.w) return PSOB200_ERR_INVALID_ARG;
   const bool lora = a.adapters_enabled != 0;
   if (lora && (!a.lora_a || !a.lora_b || a.r <= 0 || a.r * a.G > 4 * kBNMax)) return PSOB200_ERR_INVALID_ARG;
-  if (lora && a.G > 1 && (a.r % 8) != 0) return PSOB200_ERR_SHAPE;  // column group g of the stacked t / u starts at g * r: 16-byte aligned
+  // column group g of the stacked t / u starts at g * r_stride: 16-byte aligned (ranks that are not multiples of 8 are
+  // stacked with r_stride = r rounded up to 8: zero rows in lora_a, zero columns in t / u)
+  const long long rs = a.r_stride > 0 ? a.r_stride : a.r;
+  if (lora && (rs < a.r || (a.G > 1 && (rs % 8) != 0))) return PSOB200_ERR_SHAPE;
   if (a.G > 1 && a.bias) return PSOB200_ERR_INVALID_ARG;
   if (!backward && (!a.x || !a.y || (lora && !a.t))) return PSOB200_ERR_INVALID_ARG;
   if (backward) {
@@ -901,7 +904,8 @@ extern "C" int psob200_lora_group_forward(const psob200_lora_group_args* args, v
   if (rc != PSOB200_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool lora = a.adapters_enabled != 0;
-  const long long GN = a.G * a.N, Gr = a.G * a.r;
+  const long long rs = a.r_stride > 0 ? a.r_stride : a.r;
+  const long long GN = a.G * a.N, Gr = a.G * rs;  // width of the stacked t: G column groups of r_stride
   const int fph = a.forward_phases == 0 ? (PSOB200_FWD_DOWN | PSOB200_FWD_MAIN) : a.forward_phases;
   const bool fused = lora && fph == (PSOB200_FWD_DOWN | PSOB200_FWD_MAIN) && a.flags != nullptr;
 
@@ -921,7 +925,7 @@ extern "C" int psob200_lora_group_forward(const psob200_lora_group_args* args, v
   main.seg[0] = seg_kmajor(a.x, a.ldx, a.M, a.K, a.w, a.ldw, GN, a.K, a.K);
   if (lora) {
     main.seg[1] = seg_kmajor(a.t, a.ldt, a.M, Gr, a.lora_b, a.ldb, GN, a.r, a.r);
-    main.seg[1].a_gkoff = a.G > 1 ? (int)a.r : 0;
+    main.seg[1].a_gkoff = a.G > 1 ? (int)rs : 0;
   }
   main.bias = a.bias; main.bias_dtype = a.bias_dtype;
   main.d = a.y; main.ldd = a.ldy;
@@ -959,7 +963,8 @@ extern "C" int psob200_lora_group_backward(const psob200_lora_group_args* args, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool lora = a.adapters_enabled != 0;
   const int G = a.G;
-  const long long GN = G * a.N, Gr = G * a.r;
+  const long long rs = a.r_stride > 0 ? a.r_stride : a.r;
+  const long long GN = G * a.N, Gr = G * rs;
   const int ph = a.backward_phases == 0 ? (PSOB200_BWD_INPUT_GRAD | PSOB200_BWD_WEIGHT_GRAD) : a.backward_phases;
   const bool need_u = lora && (ph & PSOB200_BWD_U) && (a.dx != nullptr || a.ut != nullptr || a.d_lora_a != nullptr);
   const bool need_dx = a.dx != nullptr && (ph & PSOB200_BWD_DX);
@@ -968,11 +973,13 @@ extern "C" int psob200_lora_group_backward(const psob200_lora_group_args* args, 
   HostProblem up[PSOB200_MAX_GROUP] = {};
   for (int g = 0; g < G && lora; ++g) {
     HostProblem& p = up[g];
-    p.M = a.M; p.N = a.r; p.n_seg = 1; p.alpha = a.scaling; p.wait_seg = -1;
+    // N = r_stride: the columns beyond r are written as zeros (lora_b has only r columns: the TMA unit zero-fills), so that the
+    // padding of the stacked u never holds stale bits when dx multiplies it with lora_a's zero rows
+    p.M = a.M; p.N = rs; p.n_seg = 1; p.alpha = a.scaling; p.wait_seg = -1;
     p.seg[0] = seg_kmajor(a.dy[g], a.lddy[g], a.M, a.N, a.lora_b, a.ldb, GN, a.r, a.N);
     p.seg[0].b_off = (int)(g * a.N);
-    p.d = reinterpret_cast<unsigned char*>(a.u) + (size_t)g * a.r * 2; p.ldd = a.ldu;
-    if (a.ut) { p.dt = reinterpret_cast<unsigned char*>(a.ut) + (size_t)g * a.r * a.ldut * 2; p.lddt = a.ldut; }
+    p.d = reinterpret_cast<unsigned char*>(a.u) + (size_t)g * rs * 2; p.ldd = a.ldu;
+    if (a.ut) { p.dt = reinterpret_cast<unsigned char*>(a.ut) + (size_t)g * rs * a.ldut * 2; p.lddt = a.ldut; }
   }
   // dx = sum_g dy_g W_g + [u_1 .. u_G] [A_1; ..; A_G]   (W [N,K], A [r,K] reduction-major)
   HostProblem dxp = {};
@@ -1015,37 +1022,49 @@ extern "C" int psob200_lora_group_backward(const psob200_lora_group_args* args, 
   // dA[G r, K] += [u_1 .. u_G]^T x  (written transposed);  dB_g[N, r] += dy_g^T t_g : independent split reductions, one launch
   const bool want_da = (ph & PSOB200_BWD_DA) && a.d_lora_a != nullptr, want_db = (ph & PSOB200_BWD_DB) && a.d_lora_b != nullptr;
   if (!want_da && !want_db) return PSOB200_OK;
-  HostLaunch H = launch_defaults(a.dtype);
-  H.a_mn = 1; H.accumulate = 1; H.d_dtype = PSOB200_F32;
+  // problems of the weight-gradient launches: dA as ONE problem over the stacked u when the gradient rows are packed like the
+  // u columns (r_stride == r), else one per projection; then the G dB problems; at most kMaxProb per launch
+  HostProblem wp[2 * PSOB200_MAX_GROUP] = {};
   int n = 0;
   if (want_da) {
-    HostProblem& p = H.prob[n++];
-    p.M = a.K; p.N = Gr; p.n_seg = 1;
-    p.seg[0] = seg_kmajor(a.x, a.ldx, a.M, a.K, a.ut, a.ldut, Gr, a.M, a.M);
-    p.dt = a.d_lora_a; p.lddt = a.ld_da;
+    if (rs == a.r) {
+      HostProblem& p = wp[n++];
+      p.M = a.K; p.N = G * a.r; p.n_seg = 1; p.alpha = 1.0f; p.wait_seg = -1;
+      p.seg[0] = seg_kmajor(a.x, a.ldx, a.M, a.K, a.ut, a.ldut, Gr, a.M, a.M);
+      p.dt = a.d_lora_a; p.lddt = a.ld_da;
+    } else {
+      for (int g = 0; g < G; ++g) {
+        HostProblem& p = wp[n++];
+        p.M = a.K; p.N = a.r; p.n_seg = 1; p.alpha = 1.0f; p.wait_seg = -1;
+        p.seg[0] = seg_kmajor(a.x, a.ldx, a.M, a.K, a.ut, a.ldut, Gr, a.M, a.M);
+        p.seg[0].b_off = (int)(g * rs);
+        p.dt = a.d_lora_a + (size_t)g * a.r * a.ld_da; p.lddt = a.ld_da;
+      }
+    }
   }
   if (want_db) {
-    if (n + G > kMaxProb) {  // dA on its own launch, then the G dB problems
-      H.n_prob = n;
-      H.pdl = 1;
-      if (a.launch_flags & 2) H.split_k = 1;
-      if ((rc = launch_problems(H, st)) != PSOB200_OK) return rc;
-      H = launch_defaults(a.dtype);
-      H.a_mn = 1; H.accumulate = 1; H.d_dtype = PSOB200_F32; H.pdl = 8;
-      n = 0;
-    }
     for (int g = 0; g < G; ++g) {
-      HostProblem& p = H.prob[n++];
-      p.M = a.N; p.N = a.r; p.n_seg = 1;
+      HostProblem& p = wp[n++];
+      p.M = a.N; p.N = a.r; p.n_seg = 1; p.alpha = 1.0f; p.wait_seg = -1;
       p.seg[0] = seg_kmajor(a.dy[g], a.lddy[g], a.M, a.N, a.tt, a.ldtt, Gr, a.M, a.M);
-      p.seg[0].b_off = (int)(g * a.r);
+      p.seg[0].b_off = (int)(g * rs);
       p.d = a.d_lora_b + (size_t)g * a.N * a.ld_db; p.ldd = a.ld_db;
     }
   }
-  H.n_prob = n;
-  if ((a.launch_flags & 1) && H.pdl == 0) H.pdl = 2 | 4;
-  if (a.launch_flags & 2) H.split_k = 1;  // one accumulation per gradient element and launch: bit-reproducible
-  return launch_problems(H, st);
+  for (int first = 0; first < n; first += kMaxProb) {
+    const int cnt = n - first < kMaxProb ? n - first : kMaxProb;
+    const bool more = first + cnt < n;
+    HostLaunch H = launch_defaults(a.dtype);
+    H.a_mn = 1; H.accumulate = 1; H.d_dtype = PSOB200_F32;
+    H.n_prob = cnt;
+    for (int i = 0; i < cnt; ++i) H.prob[i] = wp[first + i];
+    // independent launches: the second may overlap the first entirely (it waits for it only before exiting)
+    H.pdl = (more ? 1 : 0) | (first > 0 ? 8 : 0);
+    if ((a.launch_flags & 1) && H.pdl == 0) H.pdl = 2 | 4;
+    if (a.launch_flags & 2) H.split_k = 1;  // one accumulation per gradient element and launch: bit-reproducible
+    if ((rc = launch_problems(H, st)) != PSOB200_OK) return rc;
+  }
+  return PSOB200_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- LoRA-wrapped Linear (G = 1)
@@ -1057,7 +1076,7 @@ static psob200_lora_group_args group_of_linear(const psob200_lora_linear_args& a
   g.flags = a.flags; g.flags_len = a.flags_len;
   g.ldx = a.ldx; g.ldw = a.ldw; g.lda = a.lda; g.ldb = a.ldb; g.ldy = a.ldy; g.ldt = a.ldt; g.ldtt = a.ldtt;
   g.lddy[0] = a.lddy; g.lddx = a.lddx; g.ldu = a.ldu; g.ldut = a.ldut; g.ld_da = a.ld_da; g.ld_db = a.ld_db;
-  g.M = a.M; g.K = a.K; g.N = a.N; g.r = a.r; g.G = 1;
+  g.M = a.M; g.K = a.K; g.N = a.N; g.r = a.r; g.G = 1; g.r_stride = 0;
   g.scaling = a.scaling; g.dtype = a.dtype; g.bias_dtype = a.bias_dtype; g.adapters_enabled = a.adapters_enabled;
   g.forward_phases = a.forward_phases; g.backward_phases = a.backward_phases;
   return g;

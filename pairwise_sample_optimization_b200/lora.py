@@ -244,6 +244,10 @@ class LoRAProjectionGroup:
         self.layers = layers
         self.G = len(layers)
         self.K, self.N = l0.in_features, l0.out_features
+        r = l0.r[l0.active_adapter]
+        # stride of the G column groups of the stacked t / u: the rank itself, or -- when it is not a multiple of 8 -- the rank
+        # rounded up to 8 (the groups must start on 16-byte boundaries): lora_a is then stacked with zero rows in between
+        self.r_stride = r if (self.G == 1 or r % 8 == 0) else _ceil8(r)
         self._op = {}     # which -> [versions, stacked 16-bit buffer]
         self._grad = {}   # which -> stacked fp32 gradient buffer (only without a flat bucket)
         if self.G > 1:
@@ -277,24 +281,35 @@ class LoRAProjectionGroup:
                    for g, t in enumerate(tensors))
 
     def stacked_operand(self, which: str, dtype: torch.dtype) -> torch.Tensor:
-        """[G r, K] (which = "a") or [G N, r] ("b") 16-bit, row pitch a multiple of 8 elements."""
+        """[G r_stride, K] (which = "a") or [G N, r] ("b") 16-bit, row pitch a multiple of 8 elements."""
         ops = [l._operand(which, dtype) for l in self.layers]
         if self.G == 1:
             return ops[0]
-        if self._adjacent(ops) and ops[0].stride(0) == ops[0].shape[1]:
+        r = ops[0].shape[0] if which == "a" else ops[0].shape[1]
+        packed = self.r_stride == r
+        if packed and self._adjacent(ops) and ops[0].stride(0) == ops[0].shape[1]:
             return ops[0].as_strided((self.G * ops[0].shape[0], ops[0].shape[1]), (ops[0].shape[1], 1))
+        # private stacked copy (members not adjacent, or a rank that needs padding), refreshed IN PLACE when a member changed:
+        # stable address (CUDA-graph friendly); FusedLoRAOptimizer.step() calls refresh_operands() for such groups
         params = [(l.lora_A if which == "a" else l.lora_B)[l.active_adapter].weight for l in self.layers]
         vers = tuple((p.data_ptr(), p._version) for p in params)
         hit = self._op.get((which, dtype))
         if hit is None or hit[1].device != ops[0].device:
-            hit = [None, torch.empty(self.G * ops[0].shape[0], ops[0].shape[1], dtype=dtype, device=ops[0].device)]
+            if which == "a":
+                buf = torch.zeros(self.G * self.r_stride, ops[0].shape[1], dtype=dtype, device=ops[0].device)
+            else:
+                buf = torch.zeros(self.G * ops[0].shape[0], _ceil8(r), dtype=dtype, device=ops[0].device)
+            hit = [None, buf]
             self._op[(which, dtype)] = hit
-        if hit[0] != vers:  # refreshed IN PLACE: stable address (CUDA-graph friendly)
-            rows = ops[0].shape[0]
+        if hit[0] != vers:
+            rows = self.r_stride if which == "a" else ops[0].shape[0]
             for g, o in enumerate(ops):
-                hit[1][g * rows:(g + 1) * rows].copy_(o)
+                hit[1][g * rows:g * rows + o.shape[0], :o.shape[1]].copy_(o)
             hit[0] = vers
-        return hit[1]
+        return hit[1] if which == "a" else hit[1][:, :r]
+
+    def has_private_operands(self) -> bool:
+        return bool(self._op)
 
     def refresh_operands(self) -> None:
         dtype = self.layers[0].base_layer.weight.dtype
@@ -366,15 +381,14 @@ class _LoraGroupFn(torch.autograd.Function):
             raise _lib.Psob200Error("stacked projections must be enabled / disabled together")
         name = l0.active_adapter
         r = l0.r[name]
-        if enabled and G > 1 and r % 8:
-            raise _lib.Psob200Error("stacked projections need a LoRA rank that is a multiple of 8")
+        rs = group.r_stride
         a = _lib.LoraGroupArgs()
         y = torch.empty(M, G * N, dtype=dtype, device=dev)
         a.x, a.ldx, a.w, a.ldw, a.y, a.ldy = x2.data_ptr(), K, w.data_ptr(), K, y.data_ptr(), G * N
         bias = l0.base_layer.bias if G == 1 else None
         if bias is not None:
             a.bias, a.bias_dtype = bias.data_ptr(), _lib.dtype_code(bias)
-        a.M, a.K, a.N, a.r, a.G = M, K, N, r, G
+        a.M, a.K, a.N, a.r, a.G, a.r_stride = M, K, N, r, G, rs
         a.dtype = _lib.dtype_code(x2)
         a.adapters_enabled = int(enabled)
         a.launch_flags = _LAUNCH_FLAGS["value"]
@@ -383,13 +397,13 @@ class _LoraGroupFn(torch.autograd.Function):
         fl_t = by_t = 0.0
         if enabled:
             la, lb = group.stacked_operand("a", dtype), group.stacked_operand("b", dtype)
-            gr8 = _ceil8(G * r)
+            gr8 = _ceil8(G * rs)
             t = torch.empty(M, gr8, dtype=dtype, device=dev)
             a.lora_a, a.lda, a.lora_b, a.ldb = la.data_ptr(), la.stride(0), lb.data_ptr(), lb.stride(0)
             a.t, a.ldt = t.data_ptr(), gr8
             a.scaling = float(l0.scaling[name])
             if want_wgrad:
-                tt = torch.empty(G * r, _ceil8(M), dtype=dtype, device=dev)
+                tt = torch.empty(G * rs, _ceil8(M), dtype=dtype, device=dev)
                 a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
             if _IN_LAUNCH_DEPS["enabled"]:
                 ws = _flags_workspace(dev)  # t becomes tiles of the same launch as y
@@ -432,7 +446,8 @@ class _LoraGroupFn(torch.autograd.Function):
             dy2.append(d)
             a.dy[g], a.lddy[g] = d.data_ptr(), d.stride(0)
         a.w, a.ldw, a.x, a.ldx = w.data_ptr(), K, x2.data_ptr(), K
-        a.M, a.K, a.N, a.r, a.G = M, K, N, r, G
+        rs = group.r_stride
+        a.M, a.K, a.N, a.r, a.G, a.r_stride = M, K, N, r, G, rs
         a.dtype = _lib.dtype_code(dy2[0])
         a.adapters_enabled = int(ctx.enabled)
         a.launch_flags = _LAUNCH_FLAGS["value"]
@@ -446,7 +461,7 @@ class _LoraGroupFn(torch.autograd.Function):
             la, lb = group.stacked_operand("a", dtype), group.stacked_operand("b", dtype)
             a.lora_a, a.lda, a.lora_b, a.ldb = la.data_ptr(), la.stride(0), lb.data_ptr(), lb.stride(0)
             a.scaling = float(l0.scaling[name])
-            gr8 = _ceil8(G * r)
+            gr8 = _ceil8(G * rs)
             u = torch.empty(M, gr8, dtype=dtype, device=dev)
             a.u, a.ldu = u.data_ptr(), gr8
             keep.append(u)
@@ -455,7 +470,7 @@ class _LoraGroupFn(torch.autograd.Function):
                 a.flags, a.flags_len = ws.data_ptr(), ws.numel()
             if ctx.want_wgrad:
                 ga, gb = group.stacked_grad("a"), group.stacked_grad("b")
-                ut = torch.empty(G * r, _ceil8(M), dtype=dtype, device=dev)
+                ut = torch.empty(G * rs, _ceil8(M), dtype=dtype, device=dev)
                 a.ut, a.ldut = ut.data_ptr(), ut.stride(0)
                 a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
                 a.d_lora_a, a.ld_da = ga.data_ptr(), ga.stride(0)
@@ -564,14 +579,15 @@ def fuse_attention_projections(model: nn.Module) -> int:
     one ``LoRAProjectionGroup`` (G = 3), ``to_k / to_v`` of every cross-attention module one (G = 2).  ``PSOAttnProcessor2_0``
     then issues one launch per group (forward), one for the input gradient and one for the weight gradients (backward) instead of
     2 + 4 per projection.  Call it after ``add_adapter`` and BEFORE building ``LoRAGradBucket`` / ``FusedLoRAOptimizer`` (the flat
-    layout follows ``lora_parameters()``, which keeps a group's matrices adjacent).  Modules whose rank is not a multiple of 8,
-    or whose projections have biases or different shapes, keep the per-projection path.  Returns the number of groups."""
+    layout follows ``lora_parameters()``, which keeps a group's matrices adjacent).  Modules whose projections have biases or
+    different shapes keep the per-projection path; a rank that is not a multiple of 8 is stacked with padded private operand
+    copies (refreshed by ``FusedLoRAOptimizer.step()`` / ``refresh_operands``).  Returns the number of groups."""
     n = 0
     for m in model.modules():
         q, k, v = (getattr(m, a, None) for a in ("to_q", "to_k", "to_v"))
         if not all(isinstance(t, LoRALinear) for t in (q, k, v)) or "_psob200_groups" in m.__dict__:
             continue
-        if q.r[q.active_adapter] % 8 or any(t.base_layer.bias is not None for t in (q, k, v)):
+        if any(t.base_layer.bias is not None for t in (q, k, v)):
             continue
         same = lambda a, b: (a.in_features, a.out_features, a.r, a.scaling) == (b.in_features, b.out_features, b.r, b.scaling)
         if same(k, v) and same(q, k):
@@ -746,6 +762,7 @@ class FusedLoRAOptimizer:
                  weight_decay: float = 1e-4, max_grad_norm: float = 1.0, exchange: Optional[SymmetricGradExchange] = None):
         self.exchange = exchange  # None: all_reduce() is one NCCL call; else the fused NVLink-multicast kernel
         self.layers = lora_layers(model)
+        self.groups = projection_groups(model)
         params = lora_parameters(model)
         if any(p.dtype != torch.float32 for p in params):
             raise _lib.Psob200Error("FusedLoRAOptimizer trains fp32 adapter parameters (the shipped mixed-precision recipes)")
@@ -819,6 +836,11 @@ class FusedLoRAOptimizer:
             if hit is not None:
                 hit[0] = -1
             lay._operand(which, dt)
+        for g in self.groups:  # stacked groups that keep private (padded) operand copies: re-stacked in place
+            if g.has_private_operands():
+                for hit in g._op.values():
+                    hit[0] = None
+                g.refresh_operands()
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         """In-place zero of the flat gradient (``step()`` already leaves it zeroed); ``param.grad`` stays a bucket view."""

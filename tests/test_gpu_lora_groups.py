@@ -56,7 +56,11 @@ def _rel(got, want64):
                                                      # ragged everything: M, K and N off the tile / k-block / box sizes, tiles that
                                                      # would straddle two stacked projections, reduction tails inside the stacked weight
                                                      (2, (3, 77), 72, 200, 8, True), (3, (1, 300), 136, 264, 16, True),
-                                                     (3, (1, 5), 64, 48, 8, True)])
+                                                     (3, (1, 5), 64, 48, 8, True),
+                                                     # ranks that are not multiples of 8 (BASELINE config 4: r = 4): stacked with
+                                                     # 8-wide column groups, zero rows in the stacked lora_a
+                                                     (3, (2, 300), 640, 640, 4, True), (2, (4, 77), 2048, 640, 12, False),
+                                                     (3, (2, 1024), 1280, 1280, 4, True)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_stacked_group_forward_backward_vs_oracle(L, G, M_shape, K, N, r, need_dx, dtype):
     layers = _layers(L, G, K, N, r, dtype, 3)
@@ -116,7 +120,8 @@ def test_fused_launches_equal_the_separate_launch_sequence(L):
         assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item()
 
 
-def test_processor_with_fused_projections_matches_the_per_projection_path(L):
+@pytest.mark.parametrize("rank", [8, 4])
+def test_processor_with_fused_projections_matches_the_per_projection_path(L, rank):
     from tests.test_gpu_lora import _Attention
     dtype = torch.bfloat16
     res = []
@@ -124,7 +129,7 @@ def test_processor_with_fused_projections_matches_the_per_projection_path(L):
         for cross in (None, 2048):
             torch.manual_seed(3)
             attn = _Attention(640, cross, 10, 64).to(device="cuda", dtype=dtype)
-            wrapped = L.add_adapter(attn, L.LoraConfig(r=8, lora_alpha=8))
+            wrapped = L.add_adapter(attn, L.LoraConfig(r=rank, lora_alpha=rank))
             g = torch.Generator().manual_seed(4)
             for m in wrapped:
                 with torch.no_grad():
@@ -135,7 +140,11 @@ def test_processor_with_fused_projections_matches_the_per_projection_path(L):
             opt = L.FusedLoRAOptimizer(attn)
             if fuse:  # the flat layout keeps a group's matrices adjacent: the stacked operands are views, not copies
                 grp = L.projection_groups(attn)[0]
-                assert grp.stacked_operand("a", dtype).data_ptr() == grp.layers[0]._operand("a", dtype).data_ptr()
+                if rank % 8 == 0:
+                    assert grp.stacked_operand("a", dtype).data_ptr() == grp.layers[0]._operand("a", dtype).data_ptr()
+                else:  # padded private copies: [G * 8, K] with zero rows behind each projection's r rows
+                    sa = grp.stacked_operand("a", dtype)
+                    assert sa.shape[0] == grp.G * 8 and float(sa[rank:8].abs().max()) == 0.0
                 assert grp.stacked_grad("b").data_ptr() == grp.layers[0].lora_B["default"].weight.grad.data_ptr()
             x = _mk((2, 256, 640), 9, 1.0, dtype).cuda().requires_grad_(True)
             enc = None if cross is None else _mk((2, 77, 2048), 10, 1.0, dtype).cuda()
@@ -149,6 +158,15 @@ def test_processor_with_fused_projections_matches_the_per_projection_path(L):
                 y0 = attn(x, encoder_hidden_states=enc)
             L.enable_adapters(attn)
             res[-1] = res[-1] + (y0.clone(),)
+            if fuse:  # the optimizer boundary keeps the stacked operands current (also the padded private copies)
+                opt.lr = 1e-2
+                opt.step()
+                grp = L.projection_groups(attn)[0]
+                for g, lay in enumerate(grp.layers):
+                    rs = grp.r_stride
+                    assert torch.equal(grp.stacked_operand("a", dtype)[g * rs:g * rs + rank], lay.lora_A["default"].weight.detach().to(dtype))
+                    n = lay.out_features
+                    assert torch.equal(grp.stacked_operand("b", dtype)[g * n:(g + 1) * n], lay.lora_B["default"].weight.detach().to(dtype))
     for k in (0, 1):  # self-attention, cross-attention
         (y_a, dx_a, g_a, y0_a), (y_b, dx_b, g_b, y0_b) = res[k], res[2 + k]
         assert torch.equal(y0_a, y0_b)  # the frozen-reference pass: same reduction order per element, any tile width
