@@ -155,13 +155,17 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
         unsigned char* sa = smem_a + stage * kStageABytes;
         unsigned char* sb = smem_b + stage * stage_b_bytes;
         if (ptx::elect_one()) {
-          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_pair);
-          ptx::tma_load_2d_pair(sa, ma, ka, m0, &full_bar[stage]);
-          if (L.b_mn) {
-            for (int j = 0; j < half_bn / 64; ++j)
-              ptx::tma_load_2d_pair(sb + j * (kBK * 128), mb, n0 + 64 * j, kk + boff, &full_bar[stage]);
+          if (L.diag & 12) {  // timing experiment: no operand loads (results are wrong)
+            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 0u);
           } else {
-            ptx::tma_load_2d_pair(sb, mb, kk, n0 + boff, &full_bar[stage]);
+            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_pair);
+            ptx::tma_load_2d_pair(sa, ma, ka, m0, &full_bar[stage]);
+            if (L.b_mn) {
+              for (int j = 0; j < half_bn / 64; ++j)
+                ptx::tma_load_2d_pair(sb + j * (kBK * 128), mb, n0 + 64 * j, kk + boff, &full_bar[stage]);
+            } else {
+              ptx::tma_load_2d_pair(sb, mb, kk, n0 + boff, &full_bar[stage]);
+            }
           }
         }
         __syncwarp();
@@ -193,10 +197,12 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
         const uint64_t a_desc = a_hi | (uint64_t)((ptx::smem_addr(smem_a + stage * kStageABytes) >> 4) & 0x3FFFu);
         const uint64_t b_desc = b_hi | (uint64_t)((ptx::smem_addr(smem_b + stage * stage_b_bytes) >> 4) & 0x3FFFu);
         if (ptx::elect_one()) {
+          if (!(L.diag & 1)) {  // (timing experiment: bit 0 skips the MMAs)
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            ptx::umma_f16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * b_step), idesc,
-                               (kb > ti.kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k)
+              ptx::umma_f16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * b_step), idesc,
+                                 (kb > ti.kb0 || k > 0) ? 1u : 0u);
+          }
           if (stage & 1) ptx::umma_commit_pair(&empty_bar[stage >> 1]);
           if (kb == ti.kb1 - 1) ptx::umma_commit_pair(&tmem_full_bar[acc]);
         }
