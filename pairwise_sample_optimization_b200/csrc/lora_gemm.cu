@@ -658,7 +658,7 @@ static int launch_problems(const HostLaunch& H, cudaStream_t stream) {
     P.nk_total = 0;
     for (int s = 0; s < hp.n_seg; ++s) {
       const HostSeg& sg = hp.seg[s];
-      P.nk[s] = (int)((sg.K + kBK - 1) / kBK);
+      P.nk[s] = pair ? (int)((sg.K + kBK2 - 1) / kBK2) : (int)((sg.K + kBK - 1) / kBK);  // stages: 128 deep (pairs) / 64 deep
       P.nk_total += P.nk[s];
       P.a_koff[s] = sg.a_koff; P.a_gkoff[s] = sg.a_gkoff; P.b_off[s] = sg.b_off;
       const int ma = H.a_mn ? get_map(sg.a, sg.a_rows, sg.a_cols, sg.lda, kBK) : get_map(sg.a, sg.a_rows, sg.a_cols, sg.lda, kBM);
@@ -732,7 +732,7 @@ static int launch_problems(const HostLaunch& H, cudaStream_t stream) {
   }
   if (pair) {
     L.stages = kStages2;
-    L.stage_b_bytes = (max_bn / 2) * kBK * 2;
+    L.stage_b_bytes = 2 * (max_bn / 2) * kBK * 2;  // two 64-deep sub-tiles of this CTA's half of the widest B tile
     // 0-2: general per output type (any bias type); then per 16-bit type: bias of the same type, no bias, problem lists
     int variant;
     if (H.d_dtype == PSOB200_F32) variant = 0;

@@ -19,9 +19,15 @@
 
 namespace psob200 {
 
-constexpr int kStageB2Bytes = (kBNMax / 2) * kBK * 2;                         // 16 KB: half of the widest B tile
-constexpr int kStages2 = 6;                                                   // 6 x (16 + 16) KB
-constexpr int kGemm2SmemBytes = kStages2 * (kStageABytes + kStageB2Bytes) + 1024;
+// A stage of the pair kernel holds TWO 64-deep k-blocks (128 reduction elements): the barrier round trip producer -> MMA warp ->
+// tcgen05.commit -> producer is paid once per 128 elements.  Measured with loads, MMAs and stores all disabled
+// (tools/diag_gemm3.py), the bare hand-shake of 64-deep stages cost 0.21 us per k-block -- 15.7 of the 26.0 us of a
+// (8192,1280,1280) launch -- more than the MMAs themselves.
+constexpr int kBK2 = 2 * kBK;                                                 // reduction elements per stage
+constexpr int kStageA2Bytes = 2 * kStageABytes;                               // 32 KB: two [128 x 64] swizzled sub-tiles
+constexpr int kStageB2Bytes = 2 * (kBNMax / 2) * kBK * 2;                     // 32 KB: two halves of the widest B tile's half
+constexpr int kStages2 = 3;                                                   // 3 x (32 + 32) KB
+constexpr int kGemm2SmemBytes = kStages2 * (kStageA2Bytes + kStageB2Bytes) + 1024;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                                // shared::cluster address -> even CTA of the pair
 
 namespace ptx {
@@ -68,19 +74,20 @@ template <typename TD, int kMode>  // one instantiation per output type / bias p
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmLaunch L) {
   extern __shared__ unsigned char gemm_smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kStages2], empty_bar[kStages2 / 2], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[kStages2], empty_bar[kStages2], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_a = smem;
-  unsigned char* smem_b = smem + kStages2 * kStageABytes;
+  unsigned char* smem_b = smem + kStages2 * kStageA2Bytes;
 
   // the warp index through a shuffle is PROVABLY warp-uniform: ptxas then keeps the role loops (barrier phases, stage counters,
   // UMMA / TMA descriptors) on the uniform datapath instead of moving ~20 per-thread registers to uniform ones (R2UR) per k-block
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
-  const int stage_b_bytes = L.stage_b_bytes;  // half of the widest problem's B tile
+  const int stage_b_bytes = L.stage_b_bytes;  // two 64-deep sub-tiles of half of the widest problem's B tile
+  const int sub_b_bytes = stage_b_bytes / 2;
   const int total_tiles = L.total_tiles;      // m_tiles count 256-row pair tiles here
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
@@ -96,7 +103,7 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
 #pragma unroll
     for (int s = 0; s < kStages2; ++s) ptx::mbar_init(&full_bar[s], 1);  // leader's arrive.expect_tx (both CTAs' bytes)
 #pragma unroll
-    for (int s = 0; s < kStages2 / 2; ++s) ptx::mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
+    for (int s = 0; s < kStages2; ++s) ptx::mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);   // multicast tcgen05.commit
@@ -131,13 +138,13 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
       decode_tile(L, t, ti);
       const GemmProblem& P = L.prob[ti.p];
       const int half_bn = P.bn / 2;
-      const uint32_t tx_pair = 2u * ((uint32_t)kStageABytes + (uint32_t)(half_bn * kBK * 2));
+      const uint32_t tx_pair = 2u * 2u * ((uint32_t)kStageABytes + (uint32_t)(half_bn * kBK * 2));  // 2 CTAs x 2 sub-tiles
       const int m0 = ti.m_blk * 256 + (int)rank * kBM, n0 = (int)ti.n0 + (int)rank * half_bn;
       int seg = 0, kbs = ti.kb0;
       while (kbs >= P.nk[seg]) { kbs -= P.nk[seg]; ++seg; }
       bool need_wait = P.wait_seg >= 0;
       for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
-        if ((stage & 1) == 0) ptx::mbar_wait(&empty_bar[stage >> 1], phase ^ 1u);
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (seg >= 1 && dep_pending) {
           asm volatile("griddepcontrol.wait;" ::: "memory");
           asm volatile("fence.proxy.async;" ::: "memory");
@@ -149,22 +156,25 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
         }
         const CUtensorMap* ma = &maps.m[P.map_a[seg]];
         const CUtensorMap* mb = &maps.m[P.map_b[seg]];
-        const int ka = kbs * kBK + P.a_koff[seg] + ti.group * P.a_gkoff[seg];
-        const int kk = kbs * kBK;
+        const int ka = kbs * kBK2 + P.a_koff[seg] + ti.group * P.a_gkoff[seg];
+        const int kk = kbs * kBK2;
         const int boff = P.b_off[seg];
-        unsigned char* sa = smem_a + stage * kStageABytes;
+        unsigned char* sa = smem_a + stage * kStageA2Bytes;
         unsigned char* sb = smem_b + stage * stage_b_bytes;
         if (ptx::elect_one()) {
           if (L.diag & 12) {  // timing experiment: no operand loads (results are wrong)
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 0u);
           } else {
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_pair);
-            ptx::tma_load_2d_pair(sa, ma, ka, m0, &full_bar[stage]);
-            if (L.b_mn) {
-              for (int j = 0; j < half_bn / 64; ++j)
-                ptx::tma_load_2d_pair(sb + j * (kBK * 128), mb, n0 + 64 * j, kk + boff, &full_bar[stage]);
-            } else {
-              ptx::tma_load_2d_pair(sb, mb, kk, n0 + boff, &full_bar[stage]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // the two 64-deep sub-tiles (beyond the segment's K the TMA unit fills zeros)
+              ptx::tma_load_2d_pair(sa + h * kStageABytes, ma, ka + h * kBK, m0, &full_bar[stage]);
+              if (L.b_mn) {
+                for (int j = 0; j < half_bn / 64; ++j)
+                  ptx::tma_load_2d_pair(sb + h * sub_b_bytes + j * (kBK * 128), mb, n0 + 64 * j, kk + h * kBK + boff, &full_bar[stage]);
+              } else {
+                ptx::tma_load_2d_pair(sb + h * sub_b_bytes, mb, kk + h * kBK, n0 + boff, &full_bar[stage]);
+              }
             }
           }
         }
@@ -194,17 +204,20 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
       for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after_sync();
-        const uint64_t a_desc = a_hi | (uint64_t)((ptx::smem_addr(smem_a + stage * kStageABytes) >> 4) & 0x3FFFu);
+        const uint64_t a_desc = a_hi | (uint64_t)((ptx::smem_addr(smem_a + stage * kStageA2Bytes) >> 4) & 0x3FFFu);
         const uint64_t b_desc = b_hi | (uint64_t)((ptx::smem_addr(smem_b + stage * stage_b_bytes) >> 4) & 0x3FFFu);
+        const uint64_t a_sub = (uint64_t)(kStageABytes >> 4), b_sub = (uint64_t)(sub_b_bytes >> 4);
         if (ptx::elect_one()) {
           if (!(L.diag & 1)) {  // (timing experiment: bit 0 skips the MMAs)
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-              ptx::umma_f16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * b_step), idesc,
-                                 (kb > ti.kb0 || k > 0) ? 1u : 0u);
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k)
+                ptx::umma_f16_pair(d_tmem, a_desc + h * a_sub + (uint64_t)(k * 2), b_desc + h * b_sub + (uint64_t)(k * b_step), idesc,
+                                   (kb > ti.kb0 || h > 0 || k > 0) ? 1u : 0u);
           }
-          if (stage & 1) ptx::umma_commit_pair(&empty_bar[stage >> 1]);
-          if (kb == ti.kb1 - 1) ptx::umma_commit_pair(&tmem_full_bar[acc]);
+          ptx::umma_commit_pair(&empty_bar[stage]);                          // the stage is reusable once these MMAs retire
+          if (kb == ti.kb1 - 1) ptx::umma_commit_pair(&tmem_full_bar[acc]);  // accumulator complete
         }
         __syncwarp();
         if (++stage == kStages2) { stage = 0; phase ^= 1u; }
