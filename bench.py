@@ -997,7 +997,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=12)
@@ -1039,7 +1039,11 @@ def main():
                          "the printed numbers of such a run are not bench values)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager-on-this-GPU baseline")
     ap.add_argument("--no-turbo64", action="store_true", help="skip the short configs[1] block after the main timing")
-    args = ap.parse_args()
+    return ap.parse_args(argv)
+
+
+def main():
+    args = parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:

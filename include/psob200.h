@@ -357,10 +357,18 @@ typedef struct psob200_gemm_args {
                    before reading the second K segment (a2); 6 = ... waits before its first load; 8 = independent of the
                    previous launch, may overlap it entirely (waits for it only before exiting).  0 = plain launch */
   int32_t diag; /* timing experiments only (results are then wrong): bit 0 skip the MMAs, bit 1 skip the stores,
-                   bit 2 skip the B loads */
+                   bits 2-3 skip the operand loads, bit 18 (0x40000) record the per-CTA timeline; A/B switches with
+                   correct results: bit 16 force / bit 17 forbid the CTA-pair kernel, bit 19 (0x80000) no interleaving of a
+                   pair's first two waiting tiles.  PSOB200_GEMM_DIAG in the environment is OR-ed into every launch */
 } psob200_gemm_args;
 
 PSOB200_API int psob200_lora_gemm(const psob200_gemm_args* args, void* stream);
+
+/* Diagnostics only (tools/diag_timeline.py): after a CTA-pair launch with diag bit 0x40000, copies that launch's per-CTA time
+ * stamps to `host_out` (synchronous): [cta][slot 0..7][globaltimer ns, SM cycle counter], 512 CTAs.  Slots: 0 entry, 1 prologue
+ * done, 2 first operands landed (leader CTA), 3 / 5 first / last accumulator complete, 4 / 6 first / last tile drained, 7 exit.
+ * Returns the number of values written (8192) or a negative error code. */
+PSOB200_API int psob200_lora_gemm_timeline(unsigned long long* host_out, long long capacity);
 
 /*
  * The LoRA-wrapped projection as the reference's stack runs it (peft==0.11.1 lora.Linear, created by

@@ -148,6 +148,7 @@ SIGNATURES = {
     "psob200_dmd_x0_from_noise": (C.c_int, [_fp, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64,
                                             C.c_int64, C.c_int32, C.c_int32, C.c_int32, _ip, _vp]),
     "psob200_lora_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "psob200_lora_gemm_timeline": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_longlong]),
     "psob200_lora_linear_forward": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
     "psob200_lora_linear_backward": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
     "psob200_lora_group_forward": (C.c_int, [C.POINTER(LoraGroupArgs), _vp]),

@@ -24,6 +24,8 @@
 //   warps 4-7   epilogue: tcgen05.ld 32x32b -> alpha, bias, convert -> global (also a transposed copy, or
 //               fp32 atomic accumulation for the split reductions); overlaps the next tile's MMAs.
 #include <atomic>
+#include <cstdlib>
+#include <type_traits>
 #include <mutex>
 
 #include "common.cuh"
@@ -39,7 +41,9 @@ constexpr int kMaxStages = 8;
 constexpr int kGemmThreads = 256;
 constexpr int kStageABytes = kBM * kBK * 2;      // 16 KB
 constexpr int kStageBBytes = kBNMax * kBK * 2;   // 32 KB
-constexpr int kGemmSmemBytes = kStages * (kStageABytes + kStageBBytes) + 1024;  // + slack for 1024 B alignment
+constexpr int kEpiStageDBytes = 32 * 128;         // output staging per epilogue warp: [32 rows][128 B] for the row-major output
+constexpr int kEpiStageBytesPerWarp = kEpiStageDBytes + 32 * 64;  // + [32 columns][32 rows x 2 B] for the transposed copy
+constexpr int kGemmSmemBytes = kStages * (kStageABytes + kStageBBytes) + 4 * kEpiStageBytesPerWarp + 1024;  // + 1024 B alignment slack
 constexpr int kTmemCols = 512;
 
 constexpr int kMaxSeg = 4;    // reduction segments per problem
@@ -161,10 +165,10 @@ constexpr int kEpiFused = kEpiAnyOut | kEpiBiasSameType;  // problem lists: outp
 // One 32-column chunk of one accumulator row: v[j] belongs to (row, n0 + j).
 template <typename TD, bool kAtomic, int kMode>
 __device__ __forceinline__ void store_chunk(const GemmProblem& p, const float (&v)[32], long long row, long long n0,
-                                            long long n_end) {
+                                            long long n_end, bool do_d = true, bool do_dt = true) {
   if (row >= p.M) return;
   const long long nleft = n_end - n0;  // columns of this chunk that belong to this tile and exist
-  if ((kMode & kEpiD) && ((kMode & 3) != kEpiAnyOut || p.d != nullptr)) {
+  if ((kMode & kEpiD) && do_d && ((kMode & 3) != kEpiAnyOut || p.d != nullptr)) {
     TD* dst = reinterpret_cast<TD*>(p.d) + row * p.ldd + n0;
     if constexpr (kAtomic) {
       float* acc = reinterpret_cast<float*>(dst);
@@ -199,7 +203,7 @@ __device__ __forceinline__ void store_chunk(const GemmProblem& p, const float (&
         if (j < nleft) dst[j] = cvt_out<TD>(v[j]);
     }
   }
-  if ((kMode & kEpiDt) && ((kMode & 3) != kEpiAnyOut || p.dt != nullptr)) {  // lanes hold consecutive rows: coalesced columns
+  if ((kMode & kEpiDt) && do_dt && ((kMode & 3) != kEpiAnyOut || p.dt != nullptr)) {  // lanes hold consecutive rows: coalesced columns
     TD* dst = reinterpret_cast<TD*>(p.dt) + n0 * p.lddt + row;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -211,16 +215,90 @@ __device__ __forceinline__ void store_chunk(const GemmProblem& p, const float (&
   }
 }
 
+// ---- row-major output through shared memory.  A lane of an epilogue warp owns one accumulator ROW: stored directly, one
+// instruction writes 16 bytes to each of 32 different lines (32 L1 transactions, half-filled sectors) -- measured, draining a
+// 256 x 224 tile took 2.3 us with the stores and 0.5 us without (tools/diag_timeline.py), and the drain of the last tile of a CTA
+// is never hidden.  Staged: the lane writes its 16-byte pieces into the warp's [32 rows][128 B] buffer (piece index XOR row & 7:
+// conflict-free both ways), then the warp writes whole 128-byte (64-byte) row segments, 4 (8) rows per instruction.
+template <typename TD>
+__device__ __forceinline__ void stage_chunk(unsigned char* stg, int lane, int piece0, const float (&v)[32]) {
+  constexpr int kPer = 16 / (int)sizeof(TD);  // elements per 16-byte piece
+#pragma unroll
+  for (int q = 0; q < 32 / kPer; ++q) {
+    uint4 w;
+    if constexpr (sizeof(TD) == 4) {
+      w = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+    } else {
+      uint32_t* pw = &w.x;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if constexpr (std::is_same<TD, __nv_bfloat16>::value) {
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 2 * i], v[8 * q + 2 * i + 1]);
+          pw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        } else {
+          const __half2 h2 = __floats2half2_rn(v[8 * q + 2 * i], v[8 * q + 2 * i + 1]);
+          pw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(stg + lane * 128 + (((piece0 + q) ^ (lane & 7)) << 4)) = w;
+  }
+}
+
+// write the staged rows: `kPieces` (4 or 8) 16-byte pieces per row starting at column n0
+template <typename TD, int kPieces>
+__device__ __forceinline__ void flush_staged(const GemmProblem& p, const unsigned char* stg, int lane, long long row0, long long n0) {
+  constexpr int kPer = 16 / (int)sizeof(TD);
+  __syncwarp();
+  const int q = lane % kPieces;
+  TD* dst = reinterpret_cast<TD*>(p.d) + n0 + q * kPer;
+#pragma unroll
+  for (int r = lane / kPieces; r < 32; r += 32 / kPieces) {
+    const uint4 w = *reinterpret_cast<const uint4*>(stg + r * 128 + ((q ^ (r & 7)) << 4));
+    if (row0 + r < p.M) stg_u4(dst + (row0 + r) * p.ldd, w);
+  }
+  __syncwarp();
+}
+
+// The transposed copy (16-bit outputs) of a whole 32 x 32 chunk through the second part of the staging buffer: direct, a lane
+// issues 32 two-byte stores per chunk (measured: + 1.5 us on the drain of a 256 x 64 t tile -- which every main tile of its row
+// block waits for); staged as [column][row], the warp writes each column's 64 bytes as 16-byte pieces, 8 columns per instruction.
+template <typename TD>
+__device__ __forceinline__ void store_chunk_t_staged(const GemmProblem& p, unsigned char* stg_t, int lane, const float (&v)[32],
+                                                     long long row0, long long n0) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) reinterpret_cast<TD*>(stg_t + j * 64)[lane] = cvt_out<TD>(v[j]);
+  __syncwarp();
+  TD* dst = reinterpret_cast<TD*>(p.dt) + row0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = i * 32 + lane, col = idx >> 2, part = idx & 3;
+    const uint4 w = *reinterpret_cast<const uint4*>(stg_t + idx * 16);
+    stg_u4(dst + (n0 + col) * p.lddt + part * 8, w);
+  }
+  __syncwarp();
+}
+
 // Drain one accumulator tile: TMEM -> registers (the load of chunk c+1 is in flight while chunk c is converted and
-// stored) -> alpha, bias -> global.
+// stored) -> alpha, bias -> global (row-major output through the warp's staging buffer `stg` when one is given).
 template <typename TD, bool kAtomic, int kMode>
 __device__ __forceinline__ void epilogue_tile(const GemmProblem& p, int diag, uint32_t taddr, long long row, long long n_tile0,
-                                              long long n_end, bool add_bias) {
+                                              long long n_end, bool add_bias, unsigned char* stg = nullptr) {
   const int chunks = (p.bn + 31) / 32;
+  const int lane = threadIdx.x & 31;
+  const long long row0 = row - lane;
+  // uniform over the warp: this tile's row-major output can take the staged path (16-byte aligned row segments)
+  const bool stage_ok = !kAtomic && (kMode & kEpiD) && stg != nullptr && p.d != nullptr && !(diag & 2) &&
+                        ((reinterpret_cast<uintptr_t>(reinterpret_cast<TD*>(p.d) + n_tile0) & 15u) == 0) &&
+                        (((unsigned long long)p.ldd * sizeof(TD)) & 15u) == 0;
+  const bool stage_t_ok = !kAtomic && (kMode & kEpiDt) && sizeof(TD) == 2 && stg != nullptr && p.dt != nullptr && !(diag & 2) &&
+                          row0 + 32 <= p.M && ((reinterpret_cast<uintptr_t>(reinterpret_cast<TD*>(p.dt) + row0) & 15u) == 0) &&
+                          (((unsigned long long)p.lddt * sizeof(TD)) & 15u) == 0;
   uint32_t raw[2][32];
   ptx::tmem_ld_32x32(taddr, raw[0]);
 #pragma unroll 1
   for (int c = 0; c < chunks; c += 2) {
+    long long pending_n0 = -1;  // 16-bit outputs: the first chunk of a 64-column unit is staged and waits for the second
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int cc = c + h;
@@ -241,7 +319,38 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& p, int diag, ui
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(raw[h][j]);
         }
-        if (!(diag & 2)) store_chunk<TD, kAtomic, kMode>(p, v, row, n0, n_end);
+        if (stage_ok && n0 + 32 <= n_end) {
+          if constexpr (sizeof(TD) == 4) {
+            stage_chunk<TD>(stg, lane, 0, v);
+            flush_staged<TD, 8>(p, stg, lane, row0, n0);
+          } else if (h == 0) {
+            stage_chunk<TD>(stg, lane, 0, v);
+            if (cc + 1 < chunks && n0 + 64 <= n_end) pending_n0 = n0;  // flushed together with the next chunk
+            else flush_staged<TD, 4>(p, stg, lane, row0, n0);
+          } else {  // h == 1: chunk h == 0 of this unit was whole, staged and is pending
+            stage_chunk<TD>(stg, lane, 4, v);
+            flush_staged<TD, 8>(p, stg, lane, row0, pending_n0);
+            pending_n0 = -1;
+          }
+          if constexpr ((kMode & kEpiDt) != 0) {
+            if (stage_t_ok) {
+              if constexpr (sizeof(TD) == 2) store_chunk_t_staged<TD>(p, stg + kEpiStageDBytes, lane, v, row0, n0);
+            } else {
+              store_chunk<TD, kAtomic, kMode>(p, v, row, n0, n_end, false);
+            }
+          }
+        } else if (!(diag & 2)) {
+          if constexpr ((kMode & kEpiDt) != 0 && sizeof(TD) == 2) {
+            if (stage_t_ok && n0 + 32 <= n_end) {
+              store_chunk_t_staged<TD>(p, stg + kEpiStageDBytes, lane, v, row0, n0);
+              store_chunk<TD, kAtomic, kMode>(p, v, row, n0, n_end, true, false);
+            } else {
+              store_chunk<TD, kAtomic, kMode>(p, v, row, n0, n_end);
+            }
+          } else {
+            store_chunk<TD, kAtomic, kMode>(p, v, row, n0, n_end);
+          }
+        }
       }
     }
   }
@@ -266,6 +375,7 @@ lora_gemm_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ 
   const int n_stages = L.stages;
   const int stage_b_bytes = L.stage_b_bytes;
   unsigned char* smem_b = smem + n_stages * kStageABytes;
+  unsigned char* smem_epi = smem + kStages * (kStageABytes + kStageBBytes);  // behind the operand ring at its largest
 
   // the warp index through a shuffle is PROVABLY warp-uniform: ptxas then keeps the role loops (barrier phases, stage counters,
   // UMMA / TMA descriptors) on the uniform datapath instead of moving ~20 per-thread registers to uniform ones (R2UR) per k-block
@@ -419,7 +529,7 @@ lora_gemm_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ 
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kBNMax;
-      epilogue_tile<TD, kAtomic, kMode>(P, L.diag, taddr, row, ti.n0, ti.n_end, add_bias);
+      epilogue_tile<TD, kAtomic, kMode>(P, L.diag, taddr, row, ti.n0, ti.n_end, add_bias, smem_epi + ew * kEpiStageBytesPerWarp);
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
@@ -491,6 +601,24 @@ static int make_map(CUtensorMap* map, const void* ptr, long long rows, long long
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PSOB200_OK : PSOB200_ERR_DRIVER;
+}
+
+// Fewest pair tiles for which a launch goes to the CTA-pair kernel.  Tuning override: PSOB200_PAIR_MIN_TILES (read once).
+static int pair_min_tiles(int sms) {
+  static const int env = [] { const char* e = getenv("PSOB200_PAIR_MIN_TILES"); return e ? atoi(e) : 0; }();
+  return env > 0 ? env : sms / 2;
+}
+
+// Diagnostics: bits OR-ed into every launch's `diag` (PSOB200_GEMM_DIAG, read once; e.g. 0x40000 = record the timeline).
+static int env_diag() {
+  static const int env = [] { const char* e = getenv("PSOB200_GEMM_DIAG"); return e ? (int)strtol(e, nullptr, 0) : 0; }();
+  return env;
+}
+
+// Tuning experiment: tile width of the main problem of fused (in-launch dependency) CTA-pair launches (PSOB200_FUSED_BN).
+static int env_fused_bn() {
+  static const int env = [] { const char* e = getenv("PSOB200_FUSED_BN"); return e ? atoi(e) : 0; }();
+  return env;
 }
 
 static int gemm_sm_count() {
@@ -611,8 +739,9 @@ static int launch_problems(const HostLaunch& H, cudaStream_t stream) {
     long long other = 0;
     for (int i = 0; i + 1 < H.n_prob; ++i) other += (H.prob[i].M + 255) / 256;  // the skinny problems: one tile per row block
     big_bn2 = big.tune_bn > 0 ? big.tune_bn : choose_bn2(big.M, big_gn, big_groups, H.b_mn != 0, sms / 2, other);
+    if (any_dep && big.tune_bn == 0 && env_fused_bn() > 0 && env_fused_bn() % unit == 0) big_bn2 = env_fused_bn();
     const long long pair_tiles = ((big.M + 255) / 256) * big_groups * ((big_gn + big_bn2 - 1) / big_bn2);
-    const bool want = (H.diag & 0x10000) || (pair_tiles >= sms / 2 && big_gn >= 128 && !(H.diag & 0x20000));
+    const bool want = (H.diag & 0x10000) || (pair_tiles >= pair_min_tiles(sms) && big_gn >= 128 && !(H.diag & 0x20000));
     pair = eligible && want && big_bn2 <= kBNMax;
   }
   const int tile_m = pair ? 256 : kBM;
@@ -710,7 +839,7 @@ static int launch_problems(const HostLaunch& H, cudaStream_t stream) {
   L.a_mn = H.a_mn ? 1 : 0;
   L.b_mn = H.b_mn ? 1 : 0;
   L.atomic = H.accumulate ? 1 : 0;
-  L.diag = H.diag;
+  L.diag = H.diag | env_diag();
   L.pdl = H.pdl;
   if (any_dep) {
     if (H.flags_len < max_m_tiles + 1) return PSOB200_ERR_WORKSPACE;
@@ -853,6 +982,14 @@ extern "C" int psob200_lora_gemm(const psob200_gemm_args* args, void* stream) {
     if (g.b_reduction_major) { sg.b_rows = ks[s]; sg.b_cols = g.N; } else { sg.b_rows = g.N; sg.b_cols = ks[s]; }
   }
   return launch_problems(H, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int psob200_lora_gemm_timeline(unsigned long long* host_out, long long capacity) {
+  // diagnostics (diag bit 0x40000 of a CTA-pair launch): synchronous copy of the per-CTA time stamps of the last such launch
+  const long long n = (long long)kTimelineCtas * kTimelineSlots * 2;
+  if (host_out == nullptr || capacity < n) return PSOB200_ERR_INVALID_ARG;
+  const cudaError_t e = cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * n);
+  return e == cudaSuccess ? (int)n : consume_launch_error("psob200_lora_gemm_timeline", e);
 }
 
 // ---------------------------------------------------------------------------------------------- stacked LoRA projections

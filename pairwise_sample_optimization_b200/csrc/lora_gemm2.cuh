@@ -27,7 +27,7 @@ constexpr int kBK2 = 2 * kBK;                                                 //
 constexpr int kStageA2Bytes = 2 * kStageABytes;                               // 32 KB: two [128 x 64] swizzled sub-tiles
 constexpr int kStageB2Bytes = 2 * (kBNMax / 2) * kBK * 2;                     // 32 KB: two halves of the widest B tile's half
 constexpr int kStages2 = 3;                                                   // 3 x (32 + 32) KB
-constexpr int kGemm2SmemBytes = kStages2 * (kStageA2Bytes + kStageB2Bytes) + 1024;
+constexpr int kGemm2SmemBytes = kStages2 * (kStageA2Bytes + kStageB2Bytes) + 4 * kEpiStageBytesPerWarp + 1024;  // + output staging
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                                // shared::cluster address -> even CTA of the pair
 
 namespace ptx {
@@ -70,6 +70,50 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 }  // namespace ptx
 
+// Timeline experiment (diag bit 0x40000): per CTA, 8 time stamps (globaltimer ns, SM cycle counter) -- 0 entry, 1 prologue done,
+// 2 first operands landed (leader), 3 first accumulator complete, 4 first tile drained, 5 last accumulator complete, 6 last tile
+// drained, 7 exit.  Read back with psob200_lora_gemm_timeline (tools/diag_timeline.py).
+constexpr int kTimelineCtas = 512, kTimelineSlots = 8;
+__device__ unsigned long long g_timeline[kTimelineCtas * kTimelineSlots * 2];
+__device__ __forceinline__ void timeline_stamp(int diag, int slot) {
+  if ((diag & 0x40000) && blockIdx.x < kTimelineCtas) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    g_timeline[(blockIdx.x * kTimelineSlots + slot) * 2] = ns;
+    g_timeline[(blockIdx.x * kTimelineSlots + slot) * 2 + 1] = (unsigned long long)clock64();
+  }
+}
+
+// The order in which a pair's producer and MMA warps walk its tiles: tile after tile -- except when the pair's FIRST tile waits for
+// rows of this launch (its adapter segment reads the t / u rows that the t / u tiles of the same first wave are still writing) and
+// a second such tile follows.  Then:  base(T0) -> base(T1) -> adapter(T0) -> adapter(T1)  with both tensor-memory accumulators
+// open.  Measured (tools/diag_timeline_group.py, (8192,1280,1280), r = 64): a first-wave main tile had its base segments done at
+// ~9 us and its accumulator complete at 17 us -- t tile 8.7 us, drain + release 4 us, acquire + load + MMA 4 us -- on 42 of the 74
+// pairs, 12 of which then ran two more tiles: the launch took 37 us against 25 us for the frozen pass.
+struct TileWalk {
+  bool couple;
+  __device__ __forceinline__ void init(const GemmLaunch& L, int cluster_id, int n_clusters) {
+    couple = false;
+    const int t1 = cluster_id + n_clusters;
+    if (t1 < L.total_tiles && !(L.diag & 0x80000)) {
+      TileInfo a, b;
+      decode_tile(L, cluster_id, a);
+      decode_tile(L, t1, b);
+      couple = L.prob[a.p].wait_seg > 0 && L.prob[b.p].wait_seg > 0;
+    }
+  }
+  // part -> (index of the tile in this pair's sequence, which: 0 whole tile, 1 the segments before wait_seg, 2 the rest)
+  __device__ __forceinline__ void part(int part, int& it, int& which) const {
+    if (couple && part < 4) { it = part & 1; which = part < 2 ? 1 : 2; }
+    else { it = couple ? part - 2 : part; which = 0; }
+  }
+};
+__device__ __forceinline__ int wait_kblock(const GemmProblem& P) {  // first k-block of segment wait_seg
+  int kb = 0;
+  for (int s = 0; s < P.wait_seg; ++s) kb += P.nk[s];
+  return kb;
+}
+
 template <typename TD, int kMode>  // one instantiation per output type / bias presence (code size: see lora_gemm_kernel)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmLaunch L) {
@@ -80,10 +124,12 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem + kStages2 * kStageA2Bytes;
+  unsigned char* smem_epi = smem + kStages2 * (kStageA2Bytes + kStageB2Bytes);  // 4 x 4 KB: one staging buffer per epilogue warp
 
   // the warp index through a shuffle is PROVABLY warp-uniform: ptxas then keeps the role loops (barrier phases, stage counters,
   // UMMA / TMA descriptors) on the uniform datapath instead of moving ~20 per-thread registers to uniform ones (R2UR) per k-block
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) timeline_stamp(L.diag, 0);
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
   const int stage_b_bytes = L.stage_b_bytes;  // two 64-deep sub-tiles of half of the widest problem's B tile
@@ -118,10 +164,14 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+  // second cluster barrier (the pair's tensor memory is allocated): the TMA producer only ARRIVES and starts loading -- it never
+  // touches tensor memory -- and completes its wait after its loop (the first operands land while the others still wait here)
   ptx::tc_fence_before_sync();
-  ptx::cluster_sync_all();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  if (warp != 0) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tmem_base = tmem_base_slot;  // (not meaningful in warp 0)
+  if (threadIdx.x == 0) timeline_stamp(L.diag, 1);
 
   if (warp == 0) {
     // ================================================================= TMA producer (both CTAs: own A rows, own half of B)
@@ -133,10 +183,18 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
       asm volatile("fence.proxy.async;" ::: "memory");
       dep_pending = false;
     }
-    for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+    TileWalk walk;
+    walk.init(L, cluster_id, n_clusters);
+    for (int part = 0;; ++part) {
+      int it, which;
+      walk.part(part, it, which);
+      const int t = cluster_id + it * n_clusters;
+      if (t >= total_tiles) break;
       TileInfo ti;
       decode_tile(L, t, ti);
       const GemmProblem& P = L.prob[ti.p];
+      if (which == 1) ti.kb1 = wait_kblock(P);
+      if (which == 2) ti.kb0 = wait_kblock(P);
       const int half_bn = P.bn / 2;
       const uint32_t tx_pair = 2u * 2u * ((uint32_t)kStageABytes + (uint32_t)(half_bn * kBK * 2));  // 2 CTAs x 2 sub-tiles
       const int m0 = ti.m_blk * 256 + (int)rank * kBM, n0 = (int)ti.n0 + (int)rank * half_bn;
@@ -183,6 +241,7 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
         if (++kbs == P.nk[seg]) { kbs = 0; ++seg; }
       }
     }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // the wait of the second cluster barrier (see above)
   } else if (warp == 1 && leader) {
     // ================================================================= MMA issuer (leader CTA, M = 256 across the pair)
     const uint64_t a_hi = ptx::smem_desc_sw128(0, 0, 1024);
@@ -190,20 +249,31 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
     const uint32_t b_step = L.b_mn ? 2048u >> 4 : 32u >> 4;
     int stage = 0;
     uint32_t phase = 0;
-    int iter = 0;
-    for (int t = cluster_id; t < total_tiles; t += n_clusters, ++iter) {
+    TileWalk walk;
+    walk.init(L, cluster_id, n_clusters);
+    for (int part = 0;; ++part) {
+      int iter, which;
+      walk.part(part, iter, which);
+      const int t = cluster_id + iter * n_clusters;
+      if (t >= total_tiles) break;
       TileInfo ti;
       decode_tile(L, t, ti);
+      const int tile_kb0 = ti.kb0, tile_kb1 = ti.kb1;
+      if (which == 1) ti.kb1 = wait_kblock(L.prob[ti.p]);
+      if (which == 2) ti.kb0 = wait_kblock(L.prob[ti.p]);
       const uint32_t idesc = (1u << 4) | ((uint32_t)L.ab_format << 7) | ((uint32_t)L.ab_format << 10) |
                              ((uint32_t)L.b_mn << 16) | (((uint32_t)L.prob[ti.p].bn >> 3) << 17) | ((256u >> 4) << 24);
       const int acc = iter & 1;
       const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
-      ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);  // both CTAs' epilogues have drained this accumulator
-      ptx::tc_fence_after_sync();
+      if (which != 2) {
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);  // both CTAs' epilogues have drained this accumulator
+        ptx::tc_fence_after_sync();
+      }
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * kBNMax;
       for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after_sync();
+        if (part == 0 && kb == ti.kb0 && lane == 0) timeline_stamp(L.diag, 2);
         const uint64_t a_desc = a_hi | (uint64_t)((ptx::smem_addr(smem_a + stage * kStageA2Bytes) >> 4) & 0x3FFFu);
         const uint64_t b_desc = b_hi | (uint64_t)((ptx::smem_addr(smem_b + stage * stage_b_bytes) >> 4) & 0x3FFFu);
         const uint64_t a_sub = (uint64_t)(kStageABytes >> 4), b_sub = (uint64_t)(sub_b_bytes >> 4);
@@ -214,10 +284,10 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k)
                 ptx::umma_f16_pair(d_tmem, a_desc + h * a_sub + (uint64_t)(k * 2), b_desc + h * b_sub + (uint64_t)(k * b_step), idesc,
-                                   (kb > ti.kb0 || h > 0 || k > 0) ? 1u : 0u);
+                                   (kb > tile_kb0 || h > 0 || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit_pair(&empty_bar[stage]);                          // the stage is reusable once these MMAs retire
-          if (kb == ti.kb1 - 1) ptx::umma_commit_pair(&tmem_full_bar[acc]);  // accumulator complete
+          if (kb == tile_kb1 - 1) ptx::umma_commit_pair(&tmem_full_bar[acc]);  // accumulator complete
         }
         __syncwarp();
         if (++stage == kStages2) { stage = 0; phase ^= 1u; }
@@ -237,10 +307,12 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
       const bool add_bias = P.bias != nullptr;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after_sync();
+      if (threadIdx.x == 128) { if (iter == 0) timeline_stamp(L.diag, 3); timeline_stamp(L.diag, 5); }
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kBNMax;
-      epilogue_tile<TD, false, kMode>(P, L.diag, taddr, row, ti.n0, ti.n_end, add_bias);
+      epilogue_tile<TD, false, kMode>(P, L.diag, taddr, row, ti.n0, ti.n_end, add_bias, smem_epi + ew * kEpiStageBytesPerWarp);
       ptx::tc_fence_before_sync();
       __syncwarp();
+      if (threadIdx.x == 128) { if (iter == 0) timeline_stamp(L.diag, 4); timeline_stamp(L.diag, 6); }
       if (lane == 0) ptx::mbar_arrive_leader(&tmem_empty_bar[acc]);
       if (P.signal) {  // publish these rows to the tiles of this launch that read them (8 warps = one pair tile)
         __threadfence();
@@ -264,6 +336,7 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
       __threadfence();
     }
   }
+  if (threadIdx.x == 0) timeline_stamp(L.diag, 7);
 }
 
 }  // namespace psob200
