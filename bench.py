@@ -308,6 +308,8 @@ class B200Arm:
         unet.set_attn_processor(lora.PSOAttnProcessor2_0())
         if args.fuse_projections:  # q / k / v (k / v) of every attention stacked into one launch per direction
             lora.fuse_attention_projections(unet)
+            if args.kv_bank:  # the k / v projections of all 70 cross-attention layers (prompt embeddings only): one launch per shape
+                lora.fuse_cross_attention_kv(unet)
         if args.fused_geglu:  # the feed-forward's gated GELU on one fused kernel each way (outside SURVEY section 8's rows)
             from pairwise_sample_optimization_b200 import feed_forward
             feed_forward.install_fused_geglu(unet)
@@ -802,6 +804,9 @@ def run_b200(args):
                    "weight_gradients": "dA / dB launches on a side stream" if args.wgrad_stream else "in stream order",
                    "projections": ("q / k / v (k / v) stacked: one launch per group and direction, t / u as tiles of the main "
                                    "launch" if args.fuse_projections else "one launch sequence per projection"),
+                   "cross_attention_kv": ("k / v of all cross-attention layers in one launch per shape at forward start (they read "
+                                          "the prompt embeddings only); backward per layer" if (args.kv_bank and args.fuse_projections)
+                                          else "per block"),
                    "feed_forward": "fused GEGLU kernels" if args.fused_geglu else "stock torch GEGLU",
                    "l2_policy": "working set larger than L2 (5.1 GB of bf16 weights streamed every forward)",
                    "forwards": "4 separate (as the reference)" if args.separate_forwards else
@@ -1029,6 +1034,8 @@ def parse_args(argv=None):
     ap.add_argument("--tiny", action="store_true", help="debug: the 32/64-channel fixture instead of the SDXL architecture")
     ap.add_argument("--no-fuse-projections", dest="fuse_projections", action="store_false", default=True,
                     help="one launch sequence per projection instead of stacked q / k / v (k / v) groups")
+    ap.add_argument("--no-kv-bank", dest="kv_bank", action="store_false", default=True,
+                    help="A/B: cross-attention k / v projections launched per block instead of once per forward for all blocks")
     ap.add_argument("--programmatic-launch", action="store_true",
                     help="A/B: projection kernels launched with programmatic stream serialization (prologue overlaps the "
                          "preceding kernel's tail)")

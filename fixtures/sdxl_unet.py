@@ -110,6 +110,7 @@ class Attention(nn.Module):
         inner = heads * dim_head
         self.heads, self.scale = heads, dim_head ** -0.5
         self.residual_connection, self.rescale_output_factor = False, 1.0
+        self.is_cross_attention = cross_attention_dim is not None  # (diffusers 0.27.0 Attention sets the same attribute)
         self.to_q = nn.Linear(query_dim, inner, bias=False)
         self.to_k = nn.Linear(cross_attention_dim or query_dim, inner, bias=False)
         self.to_v = nn.Linear(cross_attention_dim or query_dim, inner, bias=False)

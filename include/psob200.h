@@ -449,6 +449,9 @@ PSOB200_API int psob200_lora_linear_backward(const psob200_lora_linear_args* arg
  * LoRA-enabled passes of a device from ONE stream; launches without adapters, and the weight-gradient launch, never wait).
  * dy[g] are G separate [M, N] gradients (their own row pitches lddy[g]); dx may be NULL (cross-attention k / v: the prompt
  * embeddings need no gradient).  G > 1 needs r_stride % 8 == 0 (see r_stride).  bias only for G = 1.  Phases and scratch as psob200_lora_linear_args.
+ * The BACKWARD takes at most PSOB200_MAX_GROUP projections (dy[] pointers); the FORWARD any G with G N < 2^31: the k / v
+ * projections of EVERY cross-attention layer read the same prompt embeddings (TP:136, T:775-805 pass one encoder_hidden_states to
+ * all 70 blocks), so one forward launch can produce all of them (lora.CrossKVBank), the backward staying per layer.
  */
 #define PSOB200_MAX_GROUP 3
 typedef struct psob200_lora_group_args {

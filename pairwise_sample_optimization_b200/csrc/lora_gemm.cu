@@ -1013,9 +1013,12 @@ static HostLaunch launch_defaults(int32_t dtype) {
 }
 
 static int group_check(const psob200_lora_group_args& a, bool backward) {
-  if (a.G < 1 || a.G > PSOB200_MAX_GROUP || a.M <= 0 || a.K <= 0 || a.N <= 0 || !a.w) return PSOB200_ERR_INVALID_ARG;
+  // the backward takes the G gradients as separate pointers (dy[PSOB200_MAX_GROUP]); the forward reads ONE input and writes one
+  // stacked output, for any number of stacked projections (e.g. the k / v projections of every cross-attention layer at once)
+  if (a.G < 1 || (backward && a.G > PSOB200_MAX_GROUP) || a.M <= 0 || a.K <= 0 || a.N <= 0 || !a.w) return PSOB200_ERR_INVALID_ARG;
   const bool lora = a.adapters_enabled != 0;
-  if (lora && (!a.lora_a || !a.lora_b || a.r <= 0 || a.r * a.G > 4 * kBNMax)) return PSOB200_ERR_INVALID_ARG;
+  if (lora && (!a.lora_a || !a.lora_b || a.r <= 0 || (backward && a.r * a.G > 4 * kBNMax))) return PSOB200_ERR_INVALID_ARG;
+  if ((long long)a.G * a.N > 0x7fffffffLL - 256) return PSOB200_ERR_SHAPE;
   // column group g of the stacked t / u starts at g * r_stride: 16-byte aligned (ranks that are not multiples of 8 are
   // stacked with r_stride = r rounded up to 8: zero rows in lora_a, zero columns in t / u)
   const long long rs = a.r_stride > 0 ? a.r_stride : a.r;

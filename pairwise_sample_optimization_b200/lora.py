@@ -265,12 +265,13 @@ class LoRAProjectionGroup:
     def stacked_weight(self) -> torch.Tensor:
         if self.G == 1:
             return self.layers[0].base_layer.weight
-        w, l0 = self.weight, self.layers[0]
-        if l0.base_layer.weight.data_ptr() != w.data_ptr() or w.device != l0.base_layer.weight.device:  # model.to(...) moved the members
-            w = torch.cat([l.base_layer.weight.detach() for l in self.layers], dim=0).contiguous()
-            for g, l in enumerate(self.layers):
-                l.base_layer.weight.data = w[g * self.N:(g + 1) * self.N]
-            self.weight = w
+        ws = [l.base_layer.weight.detach() for l in self.layers]
+        if self._adjacent(ws):  # views of this group's buffer -- or of a bigger one (CrossKVBank stacks many groups)
+            return ws[0].as_strided((self.G * self.N, self.K), (self.K, 1))
+        w = torch.cat(ws, dim=0).contiguous()  # model.to(...) moved the members
+        for g, l in enumerate(self.layers):
+            l.base_layer.weight.data = w[g * self.N:(g + 1) * self.N]
+        self.weight = w
         return w
 
     def _adjacent(self, tensors) -> bool:
@@ -359,65 +360,10 @@ class _LoraGroupFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x: torch.Tensor, group: LoRAProjectionGroup, grad_mode: bool, *params):
-        l0 = group.layers[0]
-        w = group.stacked_weight()
-        dev = _lib.require_cuda(x, w)
-        dtype = w.dtype
-        if dtype not in (torch.bfloat16, torch.float16):
-            raise _lib.Psob200Error(f"the tcgen05 LoRA path needs bf16/fp16 base weights, got {dtype}")
-        G, K, N = group.G, group.K, group.N
-        if x.shape[-1] != K:
-            raise _lib.Psob200Error(f"input feature size {x.shape[-1]} != in_features {K}")
-        x2 = x.detach().reshape(-1, K)
-        if x2.dtype != dtype:
-            x2 = x2.to(dtype)
-        if not x2.is_contiguous() or x2.data_ptr() % 16:
-            x2 = x2.contiguous()
-        if K % 8 or w.stride(0) != K or w.data_ptr() % 16:
-            raise _lib.Psob200Error("base weight must be contiguous with in_features a multiple of 8")
-        M = x2.shape[0]
-        enabled = not l0._disable_adapters
-        if any(l._disable_adapters != l0._disable_adapters for l in group.layers):
-            raise _lib.Psob200Error("stacked projections must be enabled / disabled together")
-        name = l0.active_adapter
-        r = l0.r[name]
-        rs = group.r_stride
-        a = _lib.LoraGroupArgs()
-        y = torch.empty(M, G * N, dtype=dtype, device=dev)
-        a.x, a.ldx, a.w, a.ldw, a.y, a.ldy = x2.data_ptr(), K, w.data_ptr(), K, y.data_ptr(), G * N
-        bias = l0.base_layer.bias if G == 1 else None
-        if bias is not None:
-            a.bias, a.bias_dtype = bias.data_ptr(), _lib.dtype_code(bias)
-        a.M, a.K, a.N, a.r, a.G, a.r_stride = M, K, N, r, G, rs
-        a.dtype = _lib.dtype_code(x2)
-        a.adapters_enabled = int(enabled)
-        a.launch_flags = _LAUNCH_FLAGS["value"]
-        want_wgrad = enabled and grad_mode and params[0].requires_grad  # False under no_grad (the frozen-reference pass)
-        t = tt = None
-        fl_t = by_t = 0.0
-        if enabled:
-            la, lb = group.stacked_operand("a", dtype), group.stacked_operand("b", dtype)
-            gr8 = _ceil8(G * rs)
-            t = torch.empty(M, gr8, dtype=dtype, device=dev)
-            a.lora_a, a.lda, a.lora_b, a.ldb = la.data_ptr(), la.stride(0), lb.data_ptr(), lb.stride(0)
-            a.t, a.ldt = t.data_ptr(), gr8
-            a.scaling = float(l0.scaling[name])
-            if want_wgrad:
-                tt = torch.empty(G * rs, _ceil8(M), dtype=dtype, device=dev)
-                a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
-            if _IN_LAUNCH_DEPS["enabled"]:
-                ws = _flags_workspace(dev)  # t becomes tiles of the same launch as y
-                a.flags, a.flags_len = ws.data_ptr(), ws.numel()
-            fl_t = 2.0 * M * G * r * K
-            by_t = 2 * (G * r * K + M * G * r * (2 if tt is not None else 1))
-        if _TIMING is None:
-            _lib.launch(dev, "psob200_lora_group_forward", C.byref(a), _lib.current_stream(dev))
-        else:  # instrumented pass: the same launch between its own pair of events
-            role = ("y = x W^T + t B^T (t = s x A^T as tiles of the same launch)" if enabled else "y = x W^T (frozen reference)")
-            _timed_launch(dev, lambda: _lib.lib().psob200_lora_group_forward(C.byref(a), _lib.current_stream(dev)),
-                          "psob200_lora_group_forward", role, 2.0 * M * G * N * (K + (r if enabled else 0)) + fl_t,
-                          2 * (M * K + G * N * K + M * G * N + (G * N * r if enabled else 0)) + by_t, (M, K, G * N, r if enabled else 0))
-        ctx.group, ctx.enabled, ctx.x_shape, ctx.x_dtype, ctx.want_wgrad = group, enabled, x.shape, x.dtype, want_wgrad
+        want_wgrad = grad_mode and params[0].requires_grad  # False under no_grad (the frozen-reference pass)
+        x2, y, tt, enabled = _group_forward_launch(x, group, want_wgrad)
+        G, N = group.G, group.N
+        ctx.group, ctx.enabled, ctx.x_shape, ctx.x_dtype, ctx.want_wgrad = group, enabled, x.shape, x.dtype, want_wgrad and enabled
         ctx.save_for_backward(x2, tt)
         y = y.view(*x.shape[:-1], G * N)
         if G == 1:
@@ -426,92 +372,160 @@ class _LoraGroupFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *dys):
-        group: LoRAProjectionGroup = ctx.group
-        x2, tt = ctx.saved_tensors
-        l0 = group.layers[0]
-        w = group.stacked_weight()
-        dev, dtype = w.device, w.dtype
-        G, K, N = group.G, group.K, group.N
-        M = x2.shape[0]
-        name = l0.active_adapter
-        r = l0.r[name]
-        a = _lib.LoraGroupArgs()
-        dy2 = []
-        for g in range(G):
-            d = dys[g].reshape(-1, N)
-            if d.dtype != dtype:
-                d = d.to(dtype)
-            if d.stride(1) != 1 or d.stride(0) % 8 or d.data_ptr() % 16:
-                d = d.contiguous()
-            dy2.append(d)
-            a.dy[g], a.lddy[g] = d.data_ptr(), d.stride(0)
-        a.w, a.ldw, a.x, a.ldx = w.data_ptr(), K, x2.data_ptr(), K
-        rs = group.r_stride
-        a.M, a.K, a.N, a.r, a.G, a.r_stride = M, K, N, r, G, rs
-        a.dtype = _lib.dtype_code(dy2[0])
-        a.adapters_enabled = int(ctx.enabled)
-        a.launch_flags = _LAUNCH_FLAGS["value"]
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty(M, K, dtype=dtype, device=dev)
-            a.dx, a.lddx = dx.data_ptr(), K
-        keep = []
-        wg = False
-        if ctx.enabled:
-            la, lb = group.stacked_operand("a", dtype), group.stacked_operand("b", dtype)
-            a.lora_a, a.lda, a.lora_b, a.ldb = la.data_ptr(), la.stride(0), lb.data_ptr(), lb.stride(0)
-            a.scaling = float(l0.scaling[name])
-            gr8 = _ceil8(G * rs)
-            u = torch.empty(M, gr8, dtype=dtype, device=dev)
-            a.u, a.ldu = u.data_ptr(), gr8
-            keep.append(u)
-            if _IN_LAUNCH_DEPS["enabled"]:
-                ws = _flags_workspace(dev)
-                a.flags, a.flags_len = ws.data_ptr(), ws.numel()
-            if ctx.want_wgrad:
-                ga, gb = group.stacked_grad("a"), group.stacked_grad("b")
-                ut = torch.empty(G * rs, _ceil8(M), dtype=dtype, device=dev)
-                a.ut, a.ldut = ut.data_ptr(), ut.stride(0)
-                a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
-                a.d_lora_a, a.ld_da = ga.data_ptr(), ga.stride(0)
-                a.d_lora_b, a.ld_db = gb.data_ptr(), gb.stride(0)
-                keep += [ut, ga, gb]
-                wg = True
-        if dx is not None or wg:
-            side = _WGRAD_SIDE["enabled"] and wg and _TIMING is None
-            if _TIMING is not None:  # instrumented pass: one launch at a time, each between its own pair of events
-                eb = 2
-                if dx is not None or wg:
-                    fl = (2.0 * M * K * G * N if dx is not None else 0.0) + (2.0 * M * G * r * (N + (K if dx is not None else 0)) if ctx.enabled else 0.0)
-                    by = eb * (M * G * N + (G * N * K + M * K if dx is not None else 0) + ((G * N * r + G * r * K + M * G * r * (2 if wg else 1)) if ctx.enabled else 0))
-                    role = ("dx = dy W + u A (u = s dy B as tiles of the same launch)" if dx is not None else "u = s dy B")
-                    a.backward_phases = 3
-                    _timed_launch(dev, lambda: _lib.lib().psob200_lora_group_backward(C.byref(a), _lib.current_stream(dev)),
-                                  "psob200_lora_group_backward", role, fl, by, (M, K, G * N, r if ctx.enabled else 0))
-                if wg:
-                    a.backward_phases = 12
-                    _timed_launch(dev, lambda: _lib.lib().psob200_lora_group_backward(C.byref(a), _lib.current_stream(dev)),
-                                  "psob200_lora_group_backward", "dA += u^T x ; dB += dy^T t (one launch)",
-                                  2.0 * M * G * r * (K + N), eb * (M * K + M * G * N + 2 * M * G * r) + 4 * G * r * (K + N),
-                                  (M, K, G * N, r))
-            else:
-                if side:
-                    a.backward_phases = 3  # PSOB200_BWD_INPUT_GRAD: u (+ ut), dx
-                _lib.launch(dev, "psob200_lora_group_backward", C.byref(a), _lib.current_stream(dev))
+        return _group_backward(ctx, dys) + (None,) * (2 * ctx.group.G)
+
+
+def _group_forward_launch(x: torch.Tensor, group: LoRAProjectionGroup, want_wgrad: bool):
+    """psob200_lora_group_forward for ``group``: returns (x as the [M, K] operand, y [M, G N], tt or None, adapters enabled)."""
+    l0 = group.layers[0]
+    w = group.stacked_weight()
+    dev = _lib.require_cuda(x, w)
+    dtype = w.dtype
+    if dtype not in (torch.bfloat16, torch.float16):
+        raise _lib.Psob200Error(f"the tcgen05 LoRA path needs bf16/fp16 base weights, got {dtype}")
+    G, K, N = group.G, group.K, group.N
+    if x.shape[-1] != K:
+        raise _lib.Psob200Error(f"input feature size {x.shape[-1]} != in_features {K}")
+    x2 = x.detach().reshape(-1, K)
+    if x2.dtype != dtype:
+        x2 = x2.to(dtype)
+    if not x2.is_contiguous() or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    if K % 8 or w.stride(0) != K or w.data_ptr() % 16:
+        raise _lib.Psob200Error("base weight must be contiguous with in_features a multiple of 8")
+    M = x2.shape[0]
+    enabled = not l0._disable_adapters
+    if any(l._disable_adapters != l0._disable_adapters for l in group.layers):
+        raise _lib.Psob200Error("stacked projections must be enabled / disabled together")
+    name = l0.active_adapter
+    r = l0.r[name]
+    rs = group.r_stride
+    a = _lib.LoraGroupArgs()
+    y = torch.empty(M, G * N, dtype=dtype, device=dev)
+    a.x, a.ldx, a.w, a.ldw, a.y, a.ldy = x2.data_ptr(), K, w.data_ptr(), K, y.data_ptr(), G * N
+    bias = l0.base_layer.bias if G == 1 else None
+    if bias is not None:
+        a.bias, a.bias_dtype = bias.data_ptr(), _lib.dtype_code(bias)
+    a.M, a.K, a.N, a.r, a.G, a.r_stride = M, K, N, r, G, rs
+    a.dtype = _lib.dtype_code(x2)
+    a.adapters_enabled = int(enabled)
+    a.launch_flags = _LAUNCH_FLAGS["value"]
+    want_wgrad = enabled and want_wgrad
+    t = tt = None
+    fl_t = by_t = 0.0
+    if enabled:
+        la, lb = group.stacked_operand("a", dtype), group.stacked_operand("b", dtype)
+        gr8 = _ceil8(G * rs)
+        t = torch.empty(M, gr8, dtype=dtype, device=dev)
+        a.lora_a, a.lda, a.lora_b, a.ldb = la.data_ptr(), la.stride(0), lb.data_ptr(), lb.stride(0)
+        a.t, a.ldt = t.data_ptr(), gr8
+        a.scaling = float(l0.scaling[name])
+        if want_wgrad:
+            tt = torch.empty(G * rs, _ceil8(M), dtype=dtype, device=dev)
+            a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
+        if _IN_LAUNCH_DEPS["enabled"]:
+            ws = _flags_workspace(dev)  # t becomes tiles of the same launch as y
+            a.flags, a.flags_len = ws.data_ptr(), ws.numel()
+        fl_t = 2.0 * M * G * r * K
+        by_t = 2 * (G * r * K + M * G * r * (2 if tt is not None else 1))
+    if _TIMING is None:
+        _lib.launch(dev, "psob200_lora_group_forward", C.byref(a), _lib.current_stream(dev))
+    else:  # instrumented pass: the same launch between its own pair of events
+        role = ("y = x W^T + t B^T (t = s x A^T as tiles of the same launch)" if enabled else "y = x W^T (frozen reference)")
+        _timed_launch(dev, lambda: _lib.lib().psob200_lora_group_forward(C.byref(a), _lib.current_stream(dev)),
+                      "psob200_lora_group_forward", role, 2.0 * M * G * N * (K + (r if enabled else 0)) + fl_t,
+                      2 * (M * K + G * N * K + M * G * N + (G * N * r if enabled else 0)) + by_t, (M, K, G * N, r if enabled else 0))
+    return x2, y, tt, enabled
+
+
+def _group_backward(ctx, dys):
+    """psob200_lora_group_backward for the node ``ctx`` (``ctx.group``, saved (x2, tt)): returns (dx, None, None)."""
+    group: LoRAProjectionGroup = ctx.group
+    x2, tt = ctx.saved_tensors
+    l0 = group.layers[0]
+    w = group.stacked_weight()
+    dev, dtype = w.device, w.dtype
+    G, K, N = group.G, group.K, group.N
+    M = x2.shape[0]
+    name = l0.active_adapter
+    r = l0.r[name]
+    a = _lib.LoraGroupArgs()
+    dy2 = []
+    for g in range(G):
+        d = dys[g].reshape(-1, N)
+        if d.dtype != dtype:
+            d = d.to(dtype)
+        if d.stride(1) != 1 or d.stride(0) % 8 or d.data_ptr() % 16:
+            d = d.contiguous()
+        dy2.append(d)
+        a.dy[g], a.lddy[g] = d.data_ptr(), d.stride(0)
+    a.w, a.ldw, a.x, a.ldx = w.data_ptr(), K, x2.data_ptr(), K
+    rs = group.r_stride
+    a.M, a.K, a.N, a.r, a.G, a.r_stride = M, K, N, r, G, rs
+    a.dtype = _lib.dtype_code(dy2[0])
+    a.adapters_enabled = int(ctx.enabled)
+    a.launch_flags = _LAUNCH_FLAGS["value"]
+    dx = None
+    if ctx.needs_input_grad[0]:
+        dx = torch.empty(M, K, dtype=dtype, device=dev)
+        a.dx, a.lddx = dx.data_ptr(), K
+    keep = []
+    wg = False
+    if ctx.enabled:
+        la, lb = group.stacked_operand("a", dtype), group.stacked_operand("b", dtype)
+        a.lora_a, a.lda, a.lora_b, a.ldb = la.data_ptr(), la.stride(0), lb.data_ptr(), lb.stride(0)
+        a.scaling = float(l0.scaling[name])
+        gr8 = _ceil8(G * rs)
+        u = torch.empty(M, gr8, dtype=dtype, device=dev)
+        a.u, a.ldu = u.data_ptr(), gr8
+        keep.append(u)
+        if _IN_LAUNCH_DEPS["enabled"]:
+            ws = _flags_workspace(dev)
+            a.flags, a.flags_len = ws.data_ptr(), ws.numel()
+        if ctx.want_wgrad:
+            ga, gb = group.stacked_grad("a"), group.stacked_grad("b")
+            ut = torch.empty(G * rs, _ceil8(M), dtype=dtype, device=dev)
+            a.ut, a.ldut = ut.data_ptr(), ut.stride(0)
+            a.tt, a.ldtt = tt.data_ptr(), tt.stride(0)
+            a.d_lora_a, a.ld_da = ga.data_ptr(), ga.stride(0)
+            a.d_lora_b, a.ld_db = gb.data_ptr(), gb.stride(0)
+            keep += [ut, ga, gb]
+            wg = True
+    if dx is not None or wg:
+        side = _WGRAD_SIDE["enabled"] and wg and _TIMING is None
+        if _TIMING is not None:  # instrumented pass: one launch at a time, each between its own pair of events
+            eb = 2
+            if dx is not None or wg:
+                fl = (2.0 * M * K * G * N if dx is not None else 0.0) + (2.0 * M * G * r * (N + (K if dx is not None else 0)) if ctx.enabled else 0.0)
+                by = eb * (M * G * N + (G * N * K + M * K if dx is not None else 0) + ((G * N * r + G * r * K + M * G * r * (2 if wg else 1)) if ctx.enabled else 0))
+                role = ("dx = dy W + u A (u = s dy B as tiles of the same launch)" if dx is not None else "u = s dy B")
+                a.backward_phases = 3
+                _timed_launch(dev, lambda: _lib.lib().psob200_lora_group_backward(C.byref(a), _lib.current_stream(dev)),
+                              "psob200_lora_group_backward", role, fl, by, (M, K, G * N, r if ctx.enabled else 0))
+            if wg:
+                a.backward_phases = 12
+                _timed_launch(dev, lambda: _lib.lib().psob200_lora_group_backward(C.byref(a), _lib.current_stream(dev)),
+                              "psob200_lora_group_backward", "dA += u^T x ; dB += dy^T t (one launch)",
+                              2.0 * M * G * r * (K + N), eb * (M * K + M * G * N + 2 * M * G * r) + 4 * G * r * (K + N),
+                              (M, K, G * N, r))
+        else:
             if side:
-                st = _wgrad_side_stream(dev)
-                st.wait_stream(torch.cuda.current_stream(dev))
-                a.backward_phases = 12  # PSOB200_BWD_WEIGHT_GRAD: dA, dB
-                _lib.launch(dev, "psob200_lora_group_backward", C.byref(a), st.cuda_stream)
-                _WGRAD_SIDE["pending"].setdefault(dev, []).append((x2, tt, dy2, keep))  # alive until the join
-                keep = []
-                _arm_wgrad_join(dev)
-        del keep
-        if dx is not None:
-            dx = dx.view(ctx.x_shape)
-            if dx.dtype != ctx.x_dtype:
-                dx = dx.to(ctx.x_dtype)
-        return (dx, None, None) + (None,) * (2 * G)
+                a.backward_phases = 3  # PSOB200_BWD_INPUT_GRAD: u (+ ut), dx
+            _lib.launch(dev, "psob200_lora_group_backward", C.byref(a), _lib.current_stream(dev))
+        if side:
+            st = _wgrad_side_stream(dev)
+            st.wait_stream(torch.cuda.current_stream(dev))
+            a.backward_phases = 12  # PSOB200_BWD_WEIGHT_GRAD: dA, dB
+            _lib.launch(dev, "psob200_lora_group_backward", C.byref(a), st.cuda_stream)
+            _WGRAD_SIDE["pending"].setdefault(dev, []).append((x2, tt, dy2, keep))  # alive until the join
+            keep = []
+            _arm_wgrad_join(dev)
+    del keep
+    if dx is not None:
+        dx = dx.view(ctx.x_shape)
+        if dx.dtype != ctx.x_dtype:
+            dx = dx.to(ctx.x_dtype)
+    return (dx, None, None)
 
 
 def _grad_buffer(p: torch.nn.Parameter) -> torch.Tensor:
@@ -590,7 +604,10 @@ def fuse_attention_projections(model: nn.Module) -> int:
         if any(t.base_layer.bias is not None for t in (q, k, v)):
             continue
         same = lambda a, b: (a.in_features, a.out_features, a.r, a.scaling) == (b.in_features, b.out_features, b.r, b.scaling)
-        if same(k, v) and same(q, k):
+        cross = getattr(m, "is_cross_attention", None)  # diffusers' Attention says so; otherwise: k / v read another width than q
+        if cross is None:
+            cross = not same(q, k)
+        if not cross and same(k, v) and same(q, k):
             members, key = [q, k, v], "qkv"
         elif same(k, v):
             members, key = [k, v], "kv"
@@ -604,8 +621,112 @@ def fuse_attention_projections(model: nn.Module) -> int:
     return n
 
 
+# ---- the k / v projections of EVERY cross-attention layer in one launch ---------------------------------------------------
+# They all read the prompt embeddings and nothing else (the trainers pass one ``encoder_hidden_states`` to every block: T:775-805,
+# TP:136): 70 launches per UNet forward with M = 2B x 77 rows -- 25-50 tiles on 148 SMs, 24-34 us each, on the blocks' critical
+# path.  ``fuse_cross_attention_kv(unet)`` stacks them per shape (SDXL: 20 projections of width 640, 120 of width 1280) into
+# forward-only groups whose ONE launch at the start of the forward writes every block's k and v; each block's processor picks its
+# columns up.  The backward stays per layer (the gradients arrive block by block): every block gets its own autograd node over
+# views of the bank's results, with the same psob200_lora_group_backward launches as before.
+
+
+class _Precomputed:
+    """Forward results of one stacked group, produced by a bank launch (kept out of autograd's sight)."""
+
+    def __init__(self, x2, y, tt, enabled):
+        self.x2, self.y, self.tt, self.enabled = x2, y, tt, enabled
+
+
+class _PrecomputedGroupFn(torch.autograd.Function):
+    """Autograd node of ONE stacked group whose forward was part of a ``CrossKVBank`` launch: the forward hands out views, the
+    backward is the group's own ``psob200_lora_group_backward``."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, group: LoRAProjectionGroup, pre: _Precomputed, *params):
+        ctx.group, ctx.enabled, ctx.x_shape, ctx.x_dtype = group, pre.enabled, x.shape, x.dtype
+        ctx.want_wgrad = pre.enabled and pre.tt is not None
+        ctx.save_for_backward(pre.x2, pre.tt)
+        N = group.N
+        y = pre.y.view(*x.shape[:-1], group.G * N)
+        return tuple(y[..., g * N:(g + 1) * N] for g in range(group.G))
+
+    @staticmethod
+    def backward(ctx, *dys):
+        return _group_backward(ctx, dys) + (None,) * (2 * ctx.group.G)
+
+
+class CrossKVBank:
+    """The ``to_k`` / ``to_v`` groups of cross-attention layers of one shape, stacked for the forward."""
+
+    def __init__(self, members):
+        self.members = list(members)  # (attention module, its LoRAProjectionGroup "kv")
+        layers = [l for _, g in self.members for l in g.layers]
+        self.all = LoRAProjectionGroup(layers)  # re-homes the frozen weights into ONE [sum G N, K] matrix
+        for _, g in self.members:
+            g.weight = None  # (its members are views of the bank's matrix now: stacked_weight() finds them adjacent)
+        for l in layers:
+            l.__dict__["_psob200_bank"] = self
+
+    def __call__(self, enc: torch.Tensor) -> None:
+        l0 = self.all.layers[0]
+        want = torch.is_grad_enabled() and l0.lora_A[l0.active_adapter].weight.requires_grad
+        x2, y, tt, enabled = _group_forward_launch(enc, self.all, want)
+        N, rs = self.all.N, self.all.r_stride
+        col = row = 0
+        for attn, g in self.members:
+            ys = y[:, col:col + g.G * N]
+            if want and enabled:
+                params = []
+                for l in g.layers:
+                    params += [l.lora_A[l.active_adapter].weight, l.lora_B[l.active_adapter].weight]
+                pre = _Precomputed(x2, ys, tt[row:row + g.G * rs] if tt is not None else None, enabled)
+                key, value = _PrecomputedGroupFn.apply(enc, g, pre, *params)
+            else:
+                yv = ys.view(*enc.shape[:-1], g.G * N)
+                key, value = yv[..., :N], yv[..., N:]
+            attn.__dict__["_psob200_kv"] = (enc, key, value)
+            col += g.G * N
+            row += g.G * rs
+
+
+def fuse_cross_attention_kv(unet: nn.Module) -> int:
+    """Stack the cross-attention ``to_k`` / ``to_v`` groups of ``unet`` (made by ``fuse_attention_projections``) into
+    ``CrossKVBank``s, one per (in_features, out_features, rank, scaling, dtype), and install the forward pre-hook that runs them on
+    the ``encoder_hidden_states`` the UNet is called with (third positional argument or keyword, diffusers 0.27.0
+    ``UNet2DConditionModel.forward``).  Call it after ``fuse_attention_projections`` and BEFORE building ``LoRAGradBucket`` /
+    ``FusedLoRAOptimizer`` (``lora_parameters()`` then lays a bank's matrices out next to each other, so that the stacked adapter
+    operands are views of the flat buffers instead of copies).  Modules with ``norm_cross`` keep their in-place projections, as do
+    gradient-checkpointed recomputations and calls with another ``encoder_hidden_states``.  Returns the number of banks."""
+    if "_psob200_kv_banks" in unet.__dict__:
+        return len(unet.__dict__["_psob200_kv_banks"])
+    by_shape = {}
+    for m in unet.modules():
+        groups = m.__dict__.get("_psob200_groups")
+        if not groups or "kv" not in groups or getattr(m, "norm_cross", None):
+            continue
+        g = groups["kv"]
+        l0 = g.layers[0]
+        key = (g.K, g.N, l0.r[l0.active_adapter], l0.scaling[l0.active_adapter], l0.base_layer.weight.dtype, l0.base_layer.weight.device)
+        by_shape.setdefault(key, []).append((m, g))
+    banks = [CrossKVBank(members) for members in by_shape.values() if len(members) > 1]
+    unet.__dict__["_psob200_kv_banks"] = banks
+
+    def hook(module, args, kwargs):
+        enc = kwargs.get("encoder_hidden_states", args[2] if len(args) > 2 else None)
+        if torch.is_tensor(enc) and enc.is_cuda:
+            for bank in banks:
+                if enc.shape[-1] == bank.all.K:
+                    bank(enc)
+        return None
+
+    if banks:
+        unet.__dict__["_psob200_kv_hook"] = unet.register_forward_pre_hook(hook, with_kwargs=True)
+    return len(banks)
+
+
 def projection_groups(model: nn.Module) -> list:
-    return [g for m in model.modules() for g in m.__dict__.get("_psob200_groups", {}).values()]
+    out = [g for m in model.modules() for g in m.__dict__.get("_psob200_groups", {}).values()]
+    return out + [b.all for b in model.__dict__.get("_psob200_kv_banks", [])]
 
 
 def refresh_operands(model: nn.Module) -> None:
@@ -617,9 +738,17 @@ def refresh_operands(model: nn.Module) -> None:
 
 def lora_parameters(model: nn.Module):
     """The trainable adapter matrices in FLAT-LAYOUT order: per projection ``A, B``; for a stacked group all ``A`` of its
-    members, then all ``B`` -- so that a group's matrices are adjacent in the flat buffers built from this list."""
+    members, then all ``B``; for a ``CrossKVBank`` all ``A`` of all its groups, then all ``B`` -- so that a group's (a bank's)
+    matrices are adjacent in the flat buffers built from this list."""
     out, seen = [], set()
     for m in lora_layers(model):
+        bank = m.__dict__.get("_psob200_bank")
+        if bank is not None:  # all A of the bank (block by block: a block's k / v stay adjacent), then all B
+            if id(bank) not in seen:
+                seen.add(id(bank))
+                out += [l.lora_A[l.active_adapter].weight for l in bank.all.layers]
+                out += [l.lora_B[l.active_adapter].weight for l in bank.all.layers]
+            continue
         g = m.__dict__.get("_psob200_group")
         if g is None:
             n = m.active_adapter
@@ -907,7 +1036,10 @@ class PSOAttnProcessor2_0:
                 encoder_hidden_states = hidden_states
             elif getattr(attn, "norm_cross", None):
                 encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
-            if groups is not None and "kv" in groups:
+            pre = attn.__dict__.pop("_psob200_kv", None)  # fuse_cross_attention_kv: produced by the bank launch at forward start
+            if pre is not None and pre[0] is encoder_hidden_states:
+                key, value = pre[1], pre[2]
+            elif groups is not None and "kv" in groups:
                 key, value = groups["kv"](encoder_hidden_states)
             else:
                 key = attn.to_k(encoder_hidden_states)

@@ -1,6 +1,7 @@
 """Parity of the configuration bench.py actually TIMES: ``product_micro_step_batched`` (win + lose rows in
 one forward of batch 2B) + the frozen-reference forward on a second stream + the dA / dB launches on the weight-gradient side
-stream + the fused GEGLU kernels, captured in ONE CUDA graph and replayed, with the fused optimizer boundary
+stream + stacked projections (``fuse_attention_projections``, ``fuse_cross_attention_kv``) + the fused GEGLU kernels, captured in
+ONE CUDA graph and replayed, with the fused optimizer boundary
 (``FusedLoRAOptimizer.step``: clip + AdamW + zero_grad + 16-bit operand refresh) between replays.
 
 1. tiny fixture (BASELINE config 1) against the reference's flow restated on the CPU in fp32 (``oracle_micro_step``: 4
@@ -71,6 +72,8 @@ def test_graph_replayed_bench_configuration_vs_oracle_across_an_optimizer_bounda
             mg.lora_A["default"].weight.copy_(A); mg.lora_B["default"].weight.copy_(Bm)
     cpu.train(); gpu.train()
     gpu.set_attn_processor(lora.PSOAttnProcessor2_0())
+    assert lora.fuse_attention_projections(gpu) > 0   # q / k / v (k / v) stacked, as bench.py runs them
+    assert lora.fuse_cross_attention_kv(gpu) > 0      # ... and the k / v of all cross-attention layers in one launch per forward
     assert feed_forward.install_fused_geglu(gpu) > 0
     lora.set_wgrad_stream(True)
     try:

@@ -200,3 +200,79 @@ def test_deterministic_weight_gradients_are_bit_reproducible(L):
         assert torch.equal(a, b)
     for a, c in zip(runs[0], runs[2]):
         assert (a - c).abs().max().item() <= 1e-4 * c.abs().max().item()
+
+
+@pytest.mark.parametrize("rank", [8, 4])
+def test_cross_attention_kv_bank_matches_the_per_block_launches(L, rank):
+    """lora.fuse_cross_attention_kv: the k / v projections of every cross-attention layer (same prompt embeddings) as ONE forward
+    launch per shape, backward per layer.  Tiny SDXL-architecture UNet: frozen pass bit-identical, policy pass and every adapter
+    gradient equal to the per-block path (same reductions per element; the split-K weight-gradient sums to fp32 round-off), the
+    stacked adapter operands are views of the flat buffers (no copies) for ranks that need no padding, and an optimizer step
+    reaches the bank's operands."""
+    from fixtures import sdxl_unet
+    cfg = sdxl_unet.tiny_config()
+    dtype = torch.bfloat16
+    res = []
+    for bank in (False, True):
+        torch.manual_seed(0)
+        unet = sdxl_unet.UNet2DConditionModel(cfg).to(dtype).cuda()
+        wrapped = L.add_adapter(unet, L.LoraConfig(r=rank, lora_alpha=rank))
+        g = torch.Generator().manual_seed(1)
+        for m in wrapped:
+            with torch.no_grad():
+                m.lora_B["default"].weight.copy_(torch.randn(m.lora_B["default"].weight.shape, generator=g) * 0.05)
+        unet.train()
+        unet.set_attn_processor(L.PSOAttnProcessor2_0())
+        assert L.fuse_attention_projections(unet) > 0
+        if bank:
+            n_banks = L.fuse_cross_attention_kv(unet)
+            assert n_banks >= 1
+            assert L.fuse_cross_attention_kv(unet) == n_banks  # idempotent
+        L.set_deterministic_wgrad(True)
+        try:
+            opt = L.FusedLoRAOptimizer(unet, lr=1e-2, weight_decay=0.0, max_grad_norm=1e9)
+            if bank:
+                for b in unet.__dict__["_psob200_kv_banks"]:
+                    assert len(b.members) > 1
+                    l0 = b.all.layers[0]
+                    assert b.all.stacked_weight().data_ptr() == l0.base_layer.weight.data_ptr()
+                    for _, grp in b.members:  # the per-layer groups find their members inside the bank's matrix: no second copy
+                        assert grp.stacked_weight().data_ptr() == grp.layers[0].base_layer.weight.data_ptr()
+                    if rank % 8 == 0:
+                        assert b.all.stacked_operand("a", dtype).data_ptr() == l0._operand("a", dtype).data_ptr()
+                        assert not b.all.has_private_operands()
+            B = 2
+            x = _mk((B, 4, 16, 16), 3, 1.0, dtype).cuda()
+            enc = _mk((B, 77, cfg.cross_attention_dim), 4, 1.0, dtype).cuda()
+            pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
+            cond = {"text_embeds": _mk((B, pooled), 5, 1.0, dtype).cuda(), "time_ids": torch.ones(B, 6, device="cuda", dtype=dtype)}
+            ts = torch.tensor([999, 499], device="cuda")
+            out = unet(x, ts, enc, added_cond_kwargs=cond).sample
+            if bank:  # every stashed projection was consumed by its block
+                assert not any("_psob200_kv" in m.__dict__ for m in unet.modules())
+            out.backward(_mk(tuple(out.shape), 6, 1.0, dtype).cuda())
+            torch.cuda.synchronize()
+            grads = opt.bucket.flat.clone()
+            names = [id(p) for p in L.lora_parameters(unet)]
+            by_name = {n: p.grad.clone() for n, p in unet.named_parameters() if p.requires_grad}
+            L.disable_adapters(unet)
+            with torch.no_grad():
+                out0 = unet(x, ts, enc, added_cond_kwargs=cond).sample
+            L.enable_adapters(unet)
+            opt.step()  # the optimizer boundary must reach the operands the bank launch reads
+            with torch.no_grad():
+                out1 = unet(x, ts, enc, added_cond_kwargs=cond).sample
+            torch.cuda.synchronize()
+            res.append((out.detach().clone(), out0.clone(), by_name, out1.clone(), len(names)))
+        finally:
+            L.set_deterministic_wgrad(False)
+    (y_a, y0_a, g_a, y1_a, n_a), (y_b, y0_b, g_b, y1_b, n_b) = res
+    assert n_a == n_b
+    assert torch.equal(y0_a, y0_b)                      # frozen reference pass
+    assert torch.equal(y_a, y_b)                        # policy pass: the same reductions per element
+    assert set(g_a) == set(g_b)
+    worst = max(((g_a[n] - g_b[n]).abs().max().item() / (g_a[n].abs().max().item() + 1e-12)) for n in g_a)
+    assert worst <= 2e-2, worst                         # (the stock attention / convolution backward kernels are not bit-reproducible)
+    assert any(v.abs().max().item() > 0 for v in g_a.values())
+    assert not torch.equal(y1_a, y_a)                   # the step changed the adapters ...
+    assert (y1_a.float() - y1_b.float()).abs().max().item() <= 2e-2 * y1_a.float().abs().max().item()  # ... the same way in both
