@@ -992,7 +992,9 @@ class FusedLoRAOptimizer:
         lay = sd["layout"]
         if lay["numel"] != self.flat_param.numel() or list(lay["offsets"]) != [int(o) for o in self.bucket.offsets] or \
                 [list(x) for x in lay["shapes"]] != [list(p.shape) for p in self.bucket.params]:
-            raise _lib.Psob200Error("optimizer state was saved for a different adapter layout (rank / target modules differ)")
+            raise _lib.Psob200Error("optimizer state was saved for a different flat layout: rank / target modules differ, or "
+                                    "fuse_attention_projections / fuse_cross_attention_kv were not called the same way before "
+                                    "the optimizer was built (lora_parameters() orders the buffers by group and bank)")
         dev = self.flat_param.device
         with torch.no_grad():
             self.flat_param.copy_(sd["flat_param"].to(dev))
