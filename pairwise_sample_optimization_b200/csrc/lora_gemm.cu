@@ -82,6 +82,7 @@ struct GemmLaunch {
   int n_prob;
   int total_tiles;
   int ab_format, a_mn, b_mn, atomic, diag;
+  int n_acc, acc_stride;    // CTA-pair kernel: tensor-memory accumulators and their column stride (2 x 256 or 3 x 160)
   int stages;               // even; stage = 16 KB of A + stage_b_bytes of B
   int stage_b_bytes;        // of the widest problem
   int pdl;                  // programmatic dependent launch role bits (psob200_gemm_args.pdl)
@@ -861,6 +862,8 @@ static int launch_problems(const HostLaunch& H, cudaStream_t stream) {
   }
   if (pair) {
     L.stages = kStages2;
+    L.n_acc = max_bn <= 160 ? 3 : 2;
+    L.acc_stride = max_bn <= 160 ? 160 : kBNMax;
     L.stage_b_bytes = 2 * (max_bn / 2) * kBK * 2;  // two 64-deep sub-tiles of this CTA's half of the widest B tile
     // 0-2: general per output type (any bias type); then per 16-bit type: bias of the same type, no bias, problem lists
     int variant;

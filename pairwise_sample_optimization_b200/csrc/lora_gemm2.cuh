@@ -28,6 +28,7 @@ constexpr int kStageA2Bytes = 2 * kStageABytes;                               //
 constexpr int kStageB2Bytes = 2 * (kBNMax / 2) * kBK * 2;                     // 32 KB: two halves of the widest B tile's half
 constexpr int kStages2 = 3;                                                   // 3 x (32 + 32) KB
 constexpr int kGemm2SmemBytes = kStages2 * (kStageA2Bytes + kStageB2Bytes) + 4 * kEpiStageBytesPerWarp + 1024;  // + output staging
+constexpr int kMaxAcc2 = 3;                                                   // accumulators in tensor memory (2 x 256 or 3 x 160 columns)
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                                // shared::cluster address -> even CTA of the pair
 
 namespace ptx {
@@ -118,7 +119,7 @@ template <typename TD, int kMode>  // one instantiation per output type / bias p
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmLaunch L) {
   extern __shared__ unsigned char gemm_smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kStages2], empty_bar[kStages2], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[kStages2], empty_bar[kStages2], tmem_full_bar[kMaxAcc2], tmem_empty_bar[kMaxAcc2];
   __shared__ uint32_t tmem_base_slot;
 
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -136,6 +137,9 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
   const int sub_b_bytes = stage_b_bytes / 2;
   const int total_tiles = L.total_tiles;      // m_tiles count 256-row pair tiles here
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  // tensor-memory accumulators: two of 256 columns, or -- when no tile of the launch is wider than 160 -- three of 160: a pair
+  // whose first two tiles are interleaved (TileWalk) then starts its third tile while the first two drain
+  const int n_acc = L.n_acc, acc_stride = L.acc_stride;
 
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < L.n_prob; ++p)
@@ -151,7 +155,7 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
 #pragma unroll
     for (int s = 0; s < kStages2; ++s) ptx::mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < kMaxAcc2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);   // multicast tcgen05.commit
       ptx::mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps of each CTA (waited on by the leader only)
     }
@@ -263,13 +267,13 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
       if (which == 2) ti.kb0 = wait_kblock(L.prob[ti.p]);
       const uint32_t idesc = (1u << 4) | ((uint32_t)L.ab_format << 7) | ((uint32_t)L.ab_format << 10) |
                              ((uint32_t)L.b_mn << 16) | (((uint32_t)L.prob[ti.p].bn >> 3) << 17) | ((256u >> 4) << 24);
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
+      const int acc = iter % n_acc;
+      const uint32_t acc_phase = (uint32_t)((iter / n_acc) & 1);
       if (which != 2) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);  // both CTAs' epilogues have drained this accumulator
         ptx::tc_fence_after_sync();
       }
-      const uint32_t d_tmem = tmem_base + (uint32_t)acc * kBNMax;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
       for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after_sync();
@@ -301,14 +305,14 @@ lora_gemm2_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__
       TileInfo ti;
       decode_tile(L, t, ti);
       const GemmProblem& P = L.prob[ti.p];
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (uint32_t)((iter >> 1) & 1);
+      const int acc = iter % n_acc;
+      const uint32_t acc_phase = (uint32_t)((iter / n_acc) & 1);
       const long long row = (long long)ti.m_blk * 256 + (long long)rank * kBM + ew * 32 + lane;
       const bool add_bias = P.bias != nullptr;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after_sync();
       if (threadIdx.x == 128) { if (iter == 0) timeline_stamp(L.diag, 3); timeline_stamp(L.diag, 5); }
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kBNMax;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * acc_stride);
       epilogue_tile<TD, false, kMode>(P, L.diag, taddr, row, ti.n0, ti.n_end, add_bias, smem_epi + ew * kEpiStageBytesPerWarp);
       ptx::tc_fence_before_sync();
       __syncwarp();
