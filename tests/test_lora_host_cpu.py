@@ -144,3 +144,55 @@ def test_host_logic_of_the_late_additions(built_lib):
         feed_forward.geglu(torch.randn(2, 16))
     lora.set_wgrad_stream(True)
     lora.set_wgrad_stream(False)
+
+
+def test_stacking_and_flat_layout_host_logic(built_lib):
+    """fuse_attention_projections / fuse_cross_attention_kv need no GPU for their bookkeeping: which modules are stacked how,
+    the frozen weights as views of one matrix (values unchanged), and lora_parameters() ordering the flat buffers so that a
+    group's -- and a bank's -- matrices are adjacent."""
+    from pairwise_sample_optimization_b200 import lora
+    torch.manual_seed(0)
+    unet = sdxl_unet.UNet2DConditionModel(sdxl_unet.tiny_config())
+    wrapped = lora.add_adapter(unet, lora.LoraConfig(r=8, lora_alpha=8))
+    before = {id(m): m.base_layer.weight.detach().clone() for m in wrapped}
+    plain_order = [id(p) for p in lora.lora_parameters(unet)]
+    n_groups = lora.fuse_attention_projections(unet)
+    attn = [m for m in unet.modules() if isinstance(m, sdxl_unet.Attention)]
+    assert n_groups == len(attn) and lora.fuse_attention_projections(unet) == 0  # every module once
+    for m in attn:  # cross-attention is stacked as k / v even where its widths equal the query's (tiny fixture: 64 = 64)
+        assert set(m.__dict__["_psob200_groups"]) == ({"kv"} if m.is_cross_attention else {"qkv"})
+    n_banks = lora.fuse_cross_attention_kv(unet)
+    assert n_banks >= 1 and lora.fuse_cross_attention_kv(unet) == n_banks
+    banks = unet.__dict__["_psob200_kv_banks"]
+    cross = [m for m in attn if m.is_cross_attention]
+    assert sum(len(b.members) for b in banks) == len(cross)
+    for m in wrapped:  # re-homed, not changed
+        assert torch.equal(m.base_layer.weight, before[id(m)])
+    for b in banks:
+        w = b.all.stacked_weight()
+        assert w.shape == (b.all.G * b.all.N, b.all.K) and w.data_ptr() == b.all.layers[0].base_layer.weight.data_ptr()
+        for _, g in b.members:  # the per-layer groups (backward) see their members inside the bank's matrix
+            assert g.stacked_weight().data_ptr() == g.layers[0].base_layer.weight.data_ptr()
+            assert g.stacked_weight().untyped_storage().data_ptr() == w.untyped_storage().data_ptr()
+    assert [g for g in lora.projection_groups(unet) if g in [b.all for b in banks]]  # the optimizer refreshes their operands too
+    # flat layout: same parameters as before, a bank = all its A (layer by layer: k, v adjacent), then all its B
+    params = lora.lora_parameters(unet)
+    assert sorted(id(p) for p in params) == sorted(plain_order) and len(set(id(p) for p in params)) == len(params)
+    pos = {id(p): i for i, p in enumerate(params)}
+    for b in banks:
+        a_pos = [pos[id(l.lora_A["default"].weight)] for l in b.all.layers]
+        b_pos = [pos[id(l.lora_B["default"].weight)] for l in b.all.layers]
+        assert a_pos == list(range(a_pos[0], a_pos[0] + len(a_pos)))
+        assert b_pos == list(range(a_pos[-1] + 1, a_pos[-1] + 1 + len(b_pos)))
+    for m in attn:
+        if not m.is_cross_attention:
+            g = m.__dict__["_psob200_groups"]["qkv"]
+            a_pos = [pos[id(l.lora_A["default"].weight)] for l in g.layers]
+            b_pos = [pos[id(l.lora_B["default"].weight)] for l in g.layers]
+            assert a_pos == list(range(a_pos[0], a_pos[0] + 3)) and b_pos == list(range(a_pos[0] + 3, a_pos[0] + 6))
+    # the bucket built from this order hands every group / bank adjacent fp32 slices
+    bucket = lora.LoRAGradBucket(params, align=8)
+    for b in banks:
+        for _, g in b.members:
+            v = [l.lora_A["default"].weight._psob200_grad_view for l in g.layers]
+            assert g._adjacent(v)
