@@ -48,7 +48,9 @@ def timeline(fn, between, label):
               f"   | since own entry: median {float(own.median()):6.2f} us")
 
 
-for (M, K, N) in [(8192, 1280, 1280), (2048, 1280, 1280)]:
+import sys as _sys
+SHAPES = [tuple(int(v) for v in a.split(',')) for a in _sys.argv[1:]] or [(8192, 1280, 1280), (2048, 1280, 1280)]
+for (M, K, N) in SHAPES:
     x, w = rn(M, K), rn(N, K)
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     print(f"M={M} K={K} N={N}")
