@@ -696,7 +696,8 @@ def fuse_cross_attention_kv(unet: nn.Module) -> int:
     ``UNet2DConditionModel.forward``).  Call it after ``fuse_attention_projections`` and BEFORE building ``LoRAGradBucket`` /
     ``FusedLoRAOptimizer`` (``lora_parameters()`` then lays a bank's matrices out next to each other, so that the stacked adapter
     operands are views of the flat buffers instead of copies).  Modules with ``norm_cross`` keep their in-place projections, as do
-    gradient-checkpointed recomputations and calls with another ``encoder_hidden_states``.  Returns the number of banks."""
+    calls with another ``encoder_hidden_states``; the recomputation of a gradient-checkpointed block picks up the same k / v as its
+    first pass.  Returns the number of banks."""
     if "_psob200_kv_banks" in unet.__dict__:
         return len(unet.__dict__["_psob200_kv_banks"])
     by_shape = {}
@@ -1038,7 +1039,9 @@ class PSOAttnProcessor2_0:
                 encoder_hidden_states = hidden_states
             elif getattr(attn, "norm_cross", None):
                 encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
-            pre = attn.__dict__.pop("_psob200_kv", None)  # fuse_cross_attention_kv: produced by the bank launch at forward start
+            # fuse_cross_attention_kv: produced by the bank launch at the start of this forward.  Not popped: a gradient-checkpointed
+            # block runs again in the backward and must take the same path (the bank's next launch overwrites the entry)
+            pre = attn.__dict__.get("_psob200_kv")
             if pre is not None and pre[0] is encoder_hidden_states:
                 key, value = pre[1], pre[2]
             elif groups is not None and "kv" in groups:

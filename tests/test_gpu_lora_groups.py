@@ -248,8 +248,9 @@ def test_cross_attention_kv_bank_matches_the_per_block_launches(L, rank):
             cond = {"text_embeds": _mk((B, pooled), 5, 1.0, dtype).cuda(), "time_ids": torch.ones(B, 6, device="cuda", dtype=dtype)}
             ts = torch.tensor([999, 499], device="cuda")
             out = unet(x, ts, enc, added_cond_kwargs=cond).sample
-            if bank:  # every stashed projection was consumed by its block
-                assert not any("_psob200_kv" in m.__dict__ for m in unet.modules())
+            if bank:  # every cross-attention module got its k / v from the bank launch of THIS forward
+                stashed = [m.__dict__["_psob200_kv"] for m in unet.modules() if "_psob200_kv" in m.__dict__]
+                assert len(stashed) == sum(len(b.members) for b in unet.__dict__["_psob200_kv_banks"]) and all(p[0] is enc for p in stashed)
             out.backward(_mk(tuple(out.shape), 6, 1.0, dtype).cuda())
             torch.cuda.synchronize()
             grads = opt.bucket.flat.clone()
@@ -276,3 +277,45 @@ def test_cross_attention_kv_bank_matches_the_per_block_launches(L, rank):
     assert any(v.abs().max().item() > 0 for v in g_a.values())
     assert not torch.equal(y1_a, y_a)                   # the step changed the adapters ...
     assert (y1_a.float() - y1_b.float()).abs().max().item() <= 2e-2 * y1_a.float().abs().max().item()  # ... the same way in both
+
+
+def test_cross_attention_kv_bank_with_gradient_checkpointing(L):
+    """Checkpointed blocks (turbo trainer :358) run their forward twice: both passes take the k / v the bank launch of that forward
+    produced (same autograd structure: non-reentrant checkpointing checks it) -- the adapter gradients must be those of the plain
+    run (each exactly once)."""
+    from fixtures import sdxl_unet
+    cfg = sdxl_unet.tiny_config()
+    dtype = torch.bfloat16
+    res = []
+    for ckpt in (False, True):
+        torch.manual_seed(0)
+        unet = sdxl_unet.UNet2DConditionModel(cfg).to(dtype).cuda()
+        wrapped = L.add_adapter(unet, L.LoraConfig(r=8, lora_alpha=8))
+        g = torch.Generator().manual_seed(1)
+        for m in wrapped:
+            with torch.no_grad():
+                m.lora_B["default"].weight.copy_(torch.randn(m.lora_B["default"].weight.shape, generator=g) * 0.05)
+        unet.train()
+        unet.set_attn_processor(L.PSOAttnProcessor2_0())
+        assert L.fuse_attention_projections(unet) > 0 and L.fuse_cross_attention_kv(unet) >= 1
+        if ckpt:
+            unet.enable_gradient_checkpointing()
+        L.set_deterministic_wgrad(True)
+        try:
+            opt = L.FusedLoRAOptimizer(unet)
+            B = 2
+            x = _mk((B, 4, 16, 16), 3, 1.0, dtype).cuda()
+            enc = _mk((B, 77, cfg.cross_attention_dim), 4, 1.0, dtype).cuda()
+            pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
+            cond = {"text_embeds": _mk((B, pooled), 5, 1.0, dtype).cuda(), "time_ids": torch.ones(B, 6, device="cuda", dtype=dtype)}
+            out = unet(x, torch.tensor([999, 499], device="cuda"), enc, added_cond_kwargs=cond).sample
+            out.backward(_mk(tuple(out.shape), 6, 1.0, dtype).cuda())
+            torch.cuda.synchronize()
+            res.append((out.detach().clone(), opt.bucket.flat.clone()))
+        finally:
+            L.set_deterministic_wgrad(False)
+    (y_a, g_a), (y_b, g_b) = res
+    assert torch.equal(y_a, y_b)
+    assert g_a.abs().max().item() > 0
+    cos = torch.dot(g_a.double(), g_b.double()) / (g_a.double().norm() * g_b.double().norm())
+    assert cos.item() >= 0.9995 and abs(g_b.norm().item() / g_a.norm().item() - 1.0) <= 1e-2, (cos.item(), g_a.norm().item(), g_b.norm().item())
