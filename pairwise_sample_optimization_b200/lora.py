@@ -667,7 +667,10 @@ class CrossKVBank:
         for l in layers:
             l.__dict__["_psob200_bank"] = self
 
-    def __call__(self, enc: torch.Tensor) -> None:
+    def __call__(self, enc: torch.Tensor, state: Optional[dict] = None) -> None:
+        """``state["live"]`` is cleared when the forward that made these entries returns: afterwards only the recomputation of a
+        gradient-checkpointed block (inside a backward pass) may still use them -- never a later, unrelated call with the same tensor."""
+        state = state if state is not None else {"live": True}
         l0 = self.all.layers[0]
         want = torch.is_grad_enabled() and l0.lora_A[l0.active_adapter].weight.requires_grad
         x2, y, tt, enabled = _group_forward_launch(enc, self.all, want)
@@ -684,7 +687,7 @@ class CrossKVBank:
             else:
                 yv = ys.view(*enc.shape[:-1], g.G * N)
                 key, value = yv[..., :N], yv[..., N:]
-            attn.__dict__["_psob200_kv"] = (enc, key, value)
+            attn.__dict__["_psob200_kv"] = (enc, key, value, state)
             col += g.G * N
             row += g.G * rs
 
@@ -712,16 +715,25 @@ def fuse_cross_attention_kv(unet: nn.Module) -> int:
     banks = [CrossKVBank(members) for members in by_shape.values() if len(members) > 1]
     unet.__dict__["_psob200_kv_banks"] = banks
 
+    live = []
+
     def hook(module, args, kwargs):
         enc = kwargs.get("encoder_hidden_states", args[2] if len(args) > 2 else None)
         if torch.is_tensor(enc) and enc.is_cuda:
+            state = {"live": True}
+            live.append(state)
             for bank in banks:
                 if enc.shape[-1] == bank.all.K:
-                    bank(enc)
+                    bank(enc, state)
+        return None
+
+    def done(module, args, output):
+        while live:
+            live.pop()["live"] = False
         return None
 
     if banks:
-        unet.__dict__["_psob200_kv_hook"] = unet.register_forward_pre_hook(hook, with_kwargs=True)
+        unet.__dict__["_psob200_kv_hook"] = (unet.register_forward_pre_hook(hook, with_kwargs=True), unet.register_forward_hook(done))
     return len(banks)
 
 
@@ -1042,6 +1054,8 @@ class PSOAttnProcessor2_0:
             # fuse_cross_attention_kv: produced by the bank launch at the start of this forward.  Not popped: a gradient-checkpointed
             # block runs again in the backward and must take the same path (the bank's next launch overwrites the entry)
             pre = attn.__dict__.get("_psob200_kv")
+            if pre is not None and not (pre[3]["live"] or torch._C._current_graph_task_id() != -1):
+                pre = None  # left over from an earlier forward: only that forward and its backward may use it
             if pre is not None and pre[0] is encoder_hidden_states:
                 key, value = pre[1], pre[2]
             elif groups is not None and "kv" in groups:

@@ -251,6 +251,15 @@ def test_cross_attention_kv_bank_matches_the_per_block_launches(L, rank):
             if bank:  # every cross-attention module got its k / v from the bank launch of THIS forward
                 stashed = [m.__dict__["_psob200_kv"] for m in unet.modules() if "_psob200_kv" in m.__dict__]
                 assert len(stashed) == sum(len(b.members) for b in unet.__dict__["_psob200_kv_banks"]) and all(p[0] is enc for p in stashed)
+            if bank:  # ... and a later direct call of a block with the same tensor does NOT reuse them (the adapters may have changed)
+                m = next(mm for mm in unet.modules() if "_psob200_kv" in mm.__dict__)
+                e0, k0, v0, state = m.__dict__["_psob200_kv"]
+                assert state["live"] is False
+                m.__dict__["_psob200_kv"] = (e0, torch.full_like(k0, float("nan")), torch.full_like(v0, float("nan")), state)
+                h = _mk((B, 64, m.to_q.in_features), 8, 1.0, dtype).cuda()
+                with torch.no_grad():
+                    direct = m(h, encoder_hidden_states=enc)
+                assert direct.shape == h.shape and bool(torch.isfinite(direct).all())
             out.backward(_mk(tuple(out.shape), 6, 1.0, dtype).cuda())
             torch.cuda.synchronize()
             grads = opt.bucket.flat.clone()
