@@ -62,6 +62,7 @@ def build(rank: int = 8, seed: int = 0, lr: float = 2e-4):
                                            target_modules=["to_k", "to_q", "to_v", "to_out.0"]))       # T:338-345
     unet.set_attn_processor(lora.PSOAttnProcessor2_0())
     lora.fuse_attention_projections(unet)
+    lora.fuse_cross_attention_kv(unet)  # k / v of all cross-attention layers: one launch per UNet forward
     opt = lora.FusedLoRAOptimizer(unet, lr=lr, weight_decay=1e-4, max_grad_norm=1.0)                     # T:428-448, :859
     return cfg, unet, opt
 
