@@ -328,3 +328,39 @@ def test_cross_attention_kv_bank_with_gradient_checkpointing(L):
     assert g_a.abs().max().item() > 0
     cos = torch.dot(g_a.double(), g_b.double()) / (g_a.double().norm() * g_b.double().norm())
     assert cos.item() >= 0.9995 and abs(g_b.norm().item() / g_a.norm().item() - 1.0) <= 1e-2, (cos.item(), g_a.norm().item(), g_b.norm().item())
+
+
+def test_many_stacked_projections_forward_with_row_block_fastest_tile_order(L):
+    """The forward takes any number of stacked projections (a cross-attention bank: here 20 x [1280, 2048] = 105 MB of frozen
+    weights against 616 rows).  With a weight matrix larger than L2 can hold and only a few row blocks, the tiles are walked row
+    blocks fastest (every weight tile read once); the results must be bit-identical to the 20 single-projection launches, with and
+    without adapters, and t^T (the operand of the per-layer dB launches) must be the transpose of t."""
+    dtype = torch.bfloat16
+    G, M, K, N, r = 20, 616, 2048, 1280, 64
+    layers = _layers(L, G, K, N, r, dtype, 31)
+    x = _mk((8, 77, K), 5, 1.0, dtype).cuda()
+    with torch.no_grad():
+        singles = [lay(x).clone() for lay in layers]           # per-projection launches (column tiles fastest, weights fit L2)
+        for lay in layers: lay.enable_adapters(False)
+        frozen_singles = [lay(x).clone() for lay in layers]
+        for lay in layers: lay.enable_adapters(True)
+    group = L.LoRAProjectionGroup(layers)
+    assert group.stacked_weight().numel() * 2 > 48e6
+    with torch.no_grad():
+        outs = group(x)
+    assert len(outs) == G
+    for g in range(G):
+        assert torch.equal(outs[g], singles[g]), g
+    x2, y, tt, enabled = L._group_forward_launch(x, group, True)   # grad mode: also writes t^T for the weight-gradient launches
+    torch.cuda.synchronize()
+    assert enabled and tt is not None and tt.shape[0] == G * r
+    assert torch.equal(y.view(8, 77, G * N)[..., :N], singles[0])
+    t_ref = (x2.float() @ torch.cat([l._operand("a", dtype) for l in layers]).float().t() * float(layers[0].scaling["default"]))
+    got = tt[:, :M].float().t()
+    assert (got - t_ref).abs().max().item() <= 2.0 ** -7 * t_ref.abs().max().item()
+    with torch.no_grad():
+        for lay in layers: lay.enable_adapters(False)
+        outs0 = group(x)
+        for lay in layers: lay.enable_adapters(True)
+    for g in range(G):
+        assert torch.equal(outs0[g], frozen_singles[g]), g
