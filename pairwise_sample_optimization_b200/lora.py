@@ -304,8 +304,16 @@ class LoRAProjectionGroup:
             self._op[(which, dtype)] = hit
         if hit[0] != vers:
             rows = self.r_stride if which == "a" else ops[0].shape[0]
-            for g, o in enumerate(ops):
-                hit[1][g * rows:g * rows + o.shape[0], :o.shape[1]].copy_(o)
+            src = [p.detach() for p in params]
+            if self._adjacent(src):
+                # the members' parameters are consecutive slices of one flat buffer (FusedLoRAOptimizer / LoRAGradBucket built from
+                # lora_parameters()): ONE strided, converting copy instead of G (a cross-attention bank stacks 120 projections)
+                s0 = src[0]
+                stacked = s0.as_strided((self.G, s0.shape[0], s0.shape[1]), (s0.numel(), s0.shape[1], 1))
+                hit[1].view(self.G, rows, hit[1].shape[1])[:, :s0.shape[0], :s0.shape[1]].copy_(stacked)
+            else:
+                for g, o in enumerate(ops):
+                    hit[1][g * rows:g * rows + o.shape[0], :o.shape[1]].copy_(o)
             hit[0] = vers
         return hit[1] if which == "a" else hit[1][:, :r]
 

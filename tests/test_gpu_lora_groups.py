@@ -83,7 +83,10 @@ def test_stacked_group_forward_backward_vs_oracle(L, G, M_shape, K, N, r, need_d
         _ulp_ok(ys[g].detach().reshape(-1, N), o["y"].reshape(-1, N), dtype, f"y[{g}]", slack_y)
         dx_want = dx_want + o["dX"]
         slack_dx = slack_dx + (o["U"].abs() @ A.detach().cpu().to(dtype).double().abs())
-        assert _rel(A.grad, o["dA"]) <= 1e-3 and _rel(Bm.grad, o["dB"]) <= 1e-3, (g, _rel(A.grad, o["dA"]), _rel(Bm.grad, o["dB"]))
+        # dA / dB inherit the 1-ulp differences of the 16-bit t / u that the y / dx checks allow (fp32 vs fp64 accumulation before the
+        # rounding): 1.0e-3 - 1.5e-3 of max |gradient| at r = 128 with 130 rows, depending on the lora_A that LoRALinear's gaussian init
+        # draws (80 runs on the SAME inputs give bit-identical y, t^T and dx, and dA / dB that differ by 1e-7: split-K atomics order)
+        assert _rel(A.grad, o["dA"]) <= 2e-3 and _rel(Bm.grad, o["dB"]) <= 2e-3, (g, _rel(A.grad, o["dA"]), _rel(Bm.grad, o["dB"]))
     if need_dx:
         _ulp_ok(x.grad.reshape(-1, K), dx_want.reshape(-1, K), dtype, "dx", slack_dx)
     else:

@@ -196,3 +196,39 @@ def test_stacking_and_flat_layout_host_logic(built_lib):
         for _, g in b.members:
             v = [l.lora_A["default"].weight._psob200_grad_view for l in g.layers]
             assert g._adjacent(v)
+
+
+def test_padded_stacked_operands_refresh_in_one_copy(built_lib):
+    """Ranks that are not multiples of 8 (BASELINE config 4: r = 4) are stacked through padded private copies.  Once the members'
+    parameters are consecutive slices of the flat buffer, the refresh is ONE strided copy; it must give exactly what the
+    member-by-member refresh gives, also after the parameters changed."""
+    from pairwise_sample_optimization_b200 import lora
+    torch.manual_seed(0)
+    dtype = torch.bfloat16
+    layers = []
+    for _ in range(5):
+        lay = lora.LoRALinear(torch.nn.Linear(32, 48, bias=False).to(dtype), 4, 4)
+        with torch.no_grad():
+            lay.lora_B["default"].weight.normal_(std=0.05)
+        layers.append(lay)
+    loose = lora.LoRAProjectionGroup(layers)                      # parameters allocated one by one: member-by-member copies
+    a_slow, b_slow = loose.stacked_operand("a", dtype).clone(), loose.stacked_operand("b", dtype).clone()
+    params = [l.lora_A["default"].weight for l in layers] + [l.lora_B["default"].weight for l in layers]
+    flat = torch.cat([p.detach().flatten() for p in params])      # the flat layout of lora_parameters(): all A, then all B
+    off = 0
+    for p in params:
+        p.data = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    packed = lora.LoRAProjectionGroup(layers)
+    assert packed._adjacent([l.lora_A["default"].weight.detach() for l in layers])
+    a_fast, b_fast = packed.stacked_operand("a", dtype), packed.stacked_operand("b", dtype)
+    assert a_fast.shape == (5 * 8, 32) and torch.equal(a_fast, a_slow) and torch.equal(b_fast, b_slow)
+    assert float(a_fast.view(5, 8, 32)[:, 4:].abs().max()) == 0.0  # the zero rows behind each projection's r rows stay zero
+    with torch.no_grad():
+        for p in params:
+            p.add_(0.25)                                          # (in-place: bumps the version the refresh looks at)
+    a2, b2 = packed.stacked_operand("a", dtype), packed.stacked_operand("b", dtype)
+    for g, l in enumerate(layers):
+        assert torch.equal(a2[g * 8:g * 8 + 4], l.lora_A["default"].weight.detach().to(dtype))
+        assert torch.equal(b2[g * 48:(g + 1) * 48], l.lora_B["default"].weight.detach().to(dtype))
+    assert a2.data_ptr() == a_fast.data_ptr()                     # refreshed in place (CUDA-graph friendly)
