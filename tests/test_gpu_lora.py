@@ -70,8 +70,10 @@ def test_lora_linear_forward_backward_vs_oracle(L, M_shape, K, N, r, bias, dtype
     A16, B16 = A.detach().to(dtype).double().cpu(), Bm.detach().to(dtype).double().cpu()
     _ulp_ok(y.detach(), o["y"], dtype, "y", slack=o["T"].abs() @ B16.abs().t())
     _ulp_ok(x.grad, o["dX"], dtype, "dX", slack=o["U"].abs() @ A16.abs())
-    assert A.grad.dtype == torch.float32 and _rel(A.grad, o["dA"]) <= 1e-3
-    assert Bm.grad.dtype == torch.float32 and _rel(Bm.grad, o["dB"]) <= 1e-3
+    # (2e-3: dA / dB inherit the 1-ulp differences of the 16-bit t / u that the y / dX checks allow -- up to 1.5e-3 of max |gradient|
+    # at r = 128 with ~130 rows, depending on the lora_A that the gaussian init draws; see test_gpu_lora_groups.py)
+    assert A.grad.dtype == torch.float32 and _rel(A.grad, o["dA"]) <= 2e-3
+    assert Bm.grad.dtype == torch.float32 and _rel(Bm.grad, o["dB"]) <= 2e-3
     # the reference's own (unrounded, fp64) arithmetic: same numbers to bf16 accuracy
     dX, dA, dB = olora.lora_linear_grads(x.detach().cpu(), lay.base_layer.weight.cpu(), A.detach().to(dtype).cpu(),
                                          Bm.detach().to(dtype).cpu(), dy.cpu(), scaling=2.0)
